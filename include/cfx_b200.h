@@ -1,0 +1,150 @@
+/* cfx_b200.h -- C ABI of the B200 charge-flux Ewald electrostatics library (libcfx_b200.so).
+ *
+ * Boundary being replaced (reference file:line, all under /root/reference):
+ *   - CalcCoulForceKernel::initialize(const System&, const CoulForce&)   openmmapi/include/CoulKernels.h:29
+ *       -> cfx_create(): takes exactly the parameter arrays CoulForce stores
+ *          (openmmapi/include/CoulForce.h:138-149) plus the System's default box
+ *          (platforms/reference/src/ReferenceCoulKernels.cpp:400).
+ *   - CalcCoulForceKernel::execute(ContextImpl&, bool includeForces, bool includeEnergy)
+ *                                                                         openmmapi/include/CoulKernels.h:37
+ *       -> cfx_execute() (host buffers, what a Reference/CPU-style platform holds,
+ *          platforms/reference/src/ReferenceCoulKernels.cpp:14-27) and cfx_execute_device()
+ *          (device buffers, what a CUDA-style platform holds, platforms/cuda/src/CudaCoulKernels.cpp:529-557).
+ *   - ~KernelImpl -> cfx_destroy().
+ *   - C++ exceptions (OpenMMException) -> int status + cfx_last_error(); the C++ plugin adapter
+ *     (openmm_chargeflux_b200/plugin/) rethrows them as OpenMMException.
+ *
+ * Units follow OpenMM: nm, elementary charge, kJ/mol, radians. All arrays are caller-owned and only
+ * read during the call; the handle owns every device allocation, stream and CUDA graph.
+ * One handle per host thread; no global state besides the per-thread last-error string.
+ *
+ * There is no CPU fallback: every entry point that computes fails with CFX_ERR_CUDA when no sm_100
+ * device is usable.
+ */
+#ifndef CFX_B200_H_
+#define CFX_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CFX_OK            0
+#define CFX_ERR_ARGUMENT  1   /* bad sizes / indices / null pointers / unsupported box            */
+#define CFX_ERR_CUDA      2   /* CUDA runtime error or no usable device                          */
+#define CFX_ERR_STATE     3   /* getter called before the data it returns was computed           */
+
+/* Coulomb constant shared by oracle, reference build and kernels. */
+#define CFX_ONE_4PI_EPS0 138.935456
+
+/* Index into the energy[] output of cfx_execute*. total = self + recip + direct + excl (PBC,
+ * ReferenceCoulKernels.cpp:633) or the all-pairs sum (non-PBC, :436-491; only TOTAL/DIRECT/EXCL used). */
+enum { CFX_E_SELF = 0, CFX_E_RECIP = 1, CFX_E_DIRECT = 2, CFX_E_EXCL = 3, CFX_E_TOTAL = 4, CFX_E_COUNT = 5 };
+
+/* Parameter block: one field per CoulForce storage vector (CoulForce.h:138-149), in the layout the
+ * getters return them (CoulForce.cpp:28-32,65-68,85-90,104-110,127-136). */
+typedef struct cfx_system_desc {
+    int32_t        num_particles;
+    const double*  charge;              /* [N]    base charge q0                                    */
+    const double*  sigma;               /* [N]    LJ sigma (nm), combined as (s_i+s_j)/2             */
+    const double*  epsilon;             /* [N]    LJ epsilon (kJ/mol), combined as 4*sqrt(e_i*e_j)   */
+    int32_t        num_exceptions;
+    const int32_t* exception_pairs;     /* [2X]   excluded pairs (p1,p2)                            */
+    int32_t        num_flux_bonds;
+    const int32_t* flux_bond_idx;       /* [2nb]  (p1,p2)                                           */
+    const double*  flux_bond_params;    /* [2nb]  (k [e/nm], b [nm])                                */
+    int32_t        num_flux_angles;
+    const int32_t* flux_angle_idx;      /* [3na]  (p1,p2,p3), p2 is the apex                        */
+    const double*  flux_angle_params;   /* [2na]  (k [e/rad], theta0 [rad])                         */
+    int32_t        num_flux_waters;
+    const int32_t* flux_water_idx;      /* [3nw]  (O,H1,H2)                                         */
+    const double*  flux_water_params;   /* [5nw]  (k1,k2,kub,b0,ub0)                                */
+    double         cutoff;              /* nm; PBC only                                             */
+    double         ewald_tol;           /* PBC only                                                 */
+    int32_t        use_pbc;
+    double         default_box[9];      /* row-major a,b,c; alpha/kmax are fixed from this at create */
+} cfx_system_desc;
+
+/* Execution options (all optional; pass NULL for defaults). */
+typedef struct cfx_options {
+    int32_t device;        /* CUDA device ordinal; -1 = current device                              */
+    int32_t shard_rank;    /* this handle's rank in a k-vector / spatial-tile sharded evaluation     */
+    int32_t shard_count;   /* number of ranks sharing one evaluation (1 = whole evaluation here)     */
+    int32_t use_graph;     /* 1 = replay the step as one CUDA graph (default), 0 = plain launches    */
+    int32_t reserved[4];
+} cfx_options;
+
+typedef struct cfx_handle cfx_handle;
+
+/* Derived Ewald parameters (ReferenceCoulKernels.cpp:401-420). */
+typedef struct cfx_ewald_params {
+    double  alpha;
+    int32_t kmax[3];
+    int64_t num_kvectors;   /* half-space count the reference loops over (:519-555)                 */
+} cfx_ewald_params;
+
+/* Per-evaluation counters, for benchmarks. */
+typedef struct cfx_stats {
+    int64_t pairs_in_cutoff;    /* in-cutoff, non-excluded i<j pairs of the last evaluation         */
+    int64_t pair_candidates;    /* distance tests the pair kernel executed                          */
+    int64_t kernel_launches;    /* kernels of this library launched by the last evaluation          */
+    int32_t cells[3];
+    int32_t reserved;
+} cfx_stats;
+
+const char* cfx_last_error(void);
+int  cfx_device_count(void);
+
+int  cfx_create(const cfx_system_desc* desc, const cfx_options* opts, cfx_handle** out);
+void cfx_destroy(cfx_handle* h);
+
+/* Host-buffer evaluation (the reference-facing call). positions: [3N] double, unwrapped, nm.
+ * box: row-major a,b,c (only read when use_pbc). energy: [CFX_E_COUNT] written. forces: [3N] double,
+ * ADDED to (as the reference adds to the platform's force vector, ReferenceCoulKernels.cpp:455-630);
+ * may be NULL. Flag semantics mirror the reference, including its quirks:
+ * PBC: recip energy only if include_energy, the other components always; pair/recip forces and
+ * dE/dq only if include_forces, self dE/dq and the chain rule always. */
+int  cfx_execute(cfx_handle* h, const double* positions, const double* box,
+                 int include_forces, int include_energy, double* energy, double* forces);
+
+/* Device-buffer evaluation on `stream` (a cudaStream_t passed as void*). d_positions: [3N] double on
+ * the handle's device. d_force_fixed: int64 [3][Npad] fixed-point (value*2^32, the OpenMM CUDA
+ * platform convention, PBCForce.cu:336-338), ADDED to atomically; Npad = cfx_padded_num_particles().
+ * d_dedq_fixed (may be NULL): int64 [Npad] fixed-point dE/dq, ADDED to. d_energy (may be NULL):
+ * double[CFX_E_COUNT], ADDED to. Asynchronous: returns after enqueueing. With shard_count > 1 the
+ * outputs are this rank's partial sums; the caller all-reduces them (sum) across ranks. */
+int  cfx_execute_device(cfx_handle* h, const double* d_positions, const double* box,
+                        int include_forces, int include_energy,
+                        long long* d_force_fixed, long long* d_dedq_fixed, double* d_energy, void* stream);
+
+int  cfx_padded_num_particles(const cfx_handle* h);
+int  cfx_get_ewald_params(const cfx_handle* h, cfx_ewald_params* out);
+int  cfx_get_stats(const cfx_handle* h, cfx_stats* out);
+
+/* Parity / debug getters for the last cfx_execute (host arrays, user particle order). */
+int  cfx_get_charges(cfx_handle* h, double* q /*[N]*/);
+int  cfx_get_dedq(cfx_handle* h, double* dedq /*[N]*/);
+int  cfx_num_jacobian_rows(const cfx_handle* h);                      /* P = 4nb + 9na + 9nw           */
+int  cfx_get_jacobian(cfx_handle* h, int32_t* dq_idx /*[P]*/, int32_t* dx_idx /*[P]*/, double* val /*[3P]*/);
+/* In-cutoff non-excluded pairs (i<j) of the last PBC evaluation, sorted lexicographically.
+ * Call with pairs == NULL to get the count. */
+int  cfx_get_neighbor_pairs(cfx_handle* h, int32_t* pairs /*[2*count]*/, int64_t capacity, int64_t* count);
+/* Exclusion lists as CSR (symmetric, sorted): row_ptr [N+1], cols [2X']. */
+int  cfx_get_exclusions(cfx_handle* h, int32_t* row_ptr, int32_t* cols, int64_t capacity, int64_t* count);
+
+/* Timing helpers for bench.py: average device time (ms) of `iters` back-to-back evaluations on
+ * device-resident positions (CUDA events on the handle's stream), and a per-kernel breakdown
+ * (names joined by ';', times in ms, averaged over iters). */
+int  cfx_time_device(cfx_handle* h, const double* d_positions, const double* box,
+                     int include_forces, int include_energy, int iters, float* ms_per_eval);
+int  cfx_time_kernels(cfx_handle* h, const double* d_positions, const double* box, int iters,
+                      char* names, int names_capacity, float* ms, int ms_capacity, int* count);
+/* Sustained FP32 FMA throughput of the device (TFLOP/s), the roofline denominator the path is
+ * bounded by (MEASURED_PEAKS.json has no FP32 CUDA-core figure). */
+int  cfx_measure_fp32_peak(int device, int iters, double* tflops, double* sm_clock_mhz_est);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CFX_B200_H_ */
