@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py -- charge-flux Ewald force evaluations per second on B200 (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c4] [--impl reference]
+
+One "step" = one full CalcCoulForceKernel::execute (energy + forces): charge-flux assembly, Ewald
+direct + explicit-k reciprocal + self + excluded-pair correction and the dE/dq.dq/dx chain rule, on the
+synthetic flexible-water box named in `config.workload`.
+
+  value     whole-job force-evals/s with positions resident in HBM, CUDA events around every step,
+            L2 flushed between steps, max over ranks.
+  e2e       the same through the reference-facing call with HOST buffers: pinned H2D of the positions
+            and D2H of forces + energy inside the timed region.
+  roofline  dominant kernel: algorithmic FLOP / its CUDA-event duration, against the FP32 FMA peak
+            measured live on this GPU (MEASURED_PEAKS.json has no CUDA-core figure; the path is
+            FP32-FMA bound, not HBM or tensor bound).
+  cpu_baseline  the plugin's Reference-platform kernel (oracle/_ref when present, else the oracle port)
+            on one host core, bounded sample, extrapolated in the number of k-vectors.
+
+`--impl reference` times that CPU implementation alone (the reference platform is single-threaded).
+N > 1 (launched by torchrun): k-vectors and direct-space i-tiles sharded over the ranks, one NCCL
+all-reduce of the fixed-point forces per step; total work fixed => "scaling": "strong".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "charge-flux Ewald force-evals/sec (ns/day), 32k-atom water, 1/2/4/8 B200"
+UNIT = "force-evals/s"
+WORKLOADS = {
+    "c2": "c2: 4,095-atom periodic flexible-water box, cutoff 1.0 nm, Ewald tol 1e-4, bond+angle charge flux",
+    "c3": "c3: 32,766-atom periodic flexible-water box, cutoff 1.0 nm, Ewald tol 1e-5, bond+angle charge flux",
+    "c4": "c4: 262,143-atom periodic flexible-water box, cutoff 1.0 nm, Ewald tol 1e-5, bond+angle charge flux",
+}
+TIMESTEP_FS = 0.5
+
+
+def ns_per_day(evals_per_s):
+    # evals/s x fs/step x 1e-6 ns/fs x 86400 s/day (x 0.0432 at 0.5 fs)
+    return evals_per_s * TIMESTEP_FS * 86.4e-3
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.QUERY, "--format=csv,noheader",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, line in self.rows:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                mhz, mx = float(parts[1].split()[0]), float(parts[2].split()[0])
+            except ValueError:
+                continue
+            smax.append(mx)
+            if t0 - 0.05 <= t <= t1 + 0.05:
+                sm.append(mhz)
+                for name, val in zip(names, parts[5:9]):
+                    if val == "Active":
+                        reasons.add(name)
+        if not sm:
+            sm = [float(r[1].split(",")[1].split()[0]) for r in self.rows[-3:]] if self.rows else [0.0]
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU reference (oracle/ is only ever the thing MEASURED here in the cpu_baseline / --impl reference legs)
+# --------------------------------------------------------------------------------------------------
+def _cpu_factory():
+    from oracle import Oracle, ReferenceBuild, oracle_available, reference_available
+    if reference_available():
+        return "reference", (lambda force, default_box: ReferenceBuild(force, default_box))
+    if not oracle_available():
+        import __graft_entry__ as g
+        g.build_oracle()
+    return "port", (lambda force, default_box: Oracle(force, default_box))
+
+
+def _kcount(kmax):
+    kx, ky, kz = kmax
+    return (kz - 1) + (ky - 1) * (2 * kz - 1) + (kx - 1) * (2 * ky - 1) * (2 * kz - 1)
+
+
+def _kmax_rule(length, alpha, tol):
+    """The reference's kmax rule (ReferenceCoulKernels.cpp:32-35,403-420), used only to pick the default box."""
+    k = 1
+    while 0.05 * np.sqrt(length * alpha) * k * np.exp(-(k * np.pi / (length * alpha)) ** 2) > tol:
+        k += 1
+    return k + 1 if k % 2 == 0 else k
+
+
+def cpu_reference_sample(pos, box, force, target_kmax, make):
+    """Time one execute of the CPU reference whose k lattice is a sub-block (kmax <= target_kmax, fixed
+    through the default box exactly as the reference's own rule does) of the full one.
+    Returns (seconds, K_sample, kmax_sample, K_full)."""
+    tol, rc = force.getEwaldErrorTolerance(), force.getCutoffDistance()
+    alpha = np.sqrt(-np.log(2 * tol)) / rc
+    nfull = _kcount([_kmax_rule(box[d, d], alpha, tol) for d in range(3)])
+    div = 1.0
+    while max(_kmax_rule(box[d, d] / div, alpha, tol) for d in range(3)) > target_kmax:
+        div *= 1.05
+    h = make(force, box / div)
+    k = h.ewald_params()[1]
+    t = time.perf_counter()
+    h.execute(pos, box, True, True)
+    dt = time.perf_counter() - t
+    return dt, _kcount(k), k, nfull
+
+
+def cpu_baseline(pos, box, force, budget_s=25.0):
+    kind, make = _cpu_factory()
+    t_nonk, k0, _, nfull = cpu_reference_sample(pos, box, force, 1, make)          # kmax=(1,1,1): no k-vectors
+    n = len(pos)
+    # pick the sample so the k part takes ~budget: ~2 loops x (cos+sin) per (atom,k), ~45 ns each on one core
+    per_ak = 9.0e-8
+    target = 3
+    for km in (5, 7, 9, 11, 13):
+        ks = ((2 * km - 1) ** 3 - 1) // 2
+        if ks * n * per_ak <= max(budget_s - 2 * t_nonk, 2.0):
+            target = km
+    t_s, ks, kmax_s, nfull = cpu_reference_sample(pos, box, force, target, make)
+    t_full = t_nonk + max(t_s - t_nonk, 0.0) * nfull / max(ks, 1)
+    return {"value": 1.0 / t_full, "unit": UNIT, "cores": 1, "kind": kind,
+            "sample": "one execute with kmax=%s (%d of %d half-space k-vectors, fixed via the default box as the reference's own "
+                      "rule does) = %.2f s, and one with no k-vectors = %.2f s (direct+self+exclusion+chain rule); "
+                      "k part scaled by %d/%d; single thread (the reference platform has no threading)"
+                      % (tuple(kmax_s), ks, nfull, t_s, t_nonk, nfull, ks),
+            "seconds_per_eval_extrapolated": t_full}
+
+
+def run_reference_arm(args, pos, box, force, workload):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    kind, make = _cpu_factory()
+    total_calls = args.steps + args.warmup
+    t_nonk, _, _, nfull = cpu_reference_sample(pos, box, force, 1, make)
+    budget = max(150.0 / max(total_calls, 1) - t_nonk, 0.3)
+    n = len(pos)
+    target = 3
+    for km in (5, 7, 9, 11):
+        if (((2 * km - 1) ** 3 - 1) // 2) * n * 9.0e-8 <= budget:
+            target = km
+    times, ks_used, kmax_used = [], None, None
+    for it in range(total_calls):
+        t_s, ks, kmax_s, nfull = cpu_reference_sample(pos, box, force, target, make)
+        if it >= args.warmup:
+            times.append(t_nonk + max(t_s - t_nonk, 0.0) * nfull / max(ks, 1))
+        ks_used, kmax_used = ks, kmax_s
+    t_full = float(np.mean(times))
+    value = 1.0 / t_full
+    sample = ("each step: one execute of the CPU reference with kmax=%s (%d of %d k-vectors), k part scaled by %d/%d, "
+              "non-k part %.2f s measured once; single thread" % (tuple(kmax_used), ks_used, nfull, nfull, ks_used, t_nonk))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_full, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload, "atoms": n, "kvectors": int(nfull)},
+            "ns_per_day": ns_per_day(value),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------
+# the CUDA path
+# --------------------------------------------------------------------------------------------------
+def algorithmic_flops(n_atoms, n_k, pairs, n_terms, n_rows, n_excl):
+    """FMA = 2 FLOP."""
+    return {"structure_factor": 4.0 * n_atoms * n_k, "kspace_gather": 8.0 * n_atoms * n_k, "direct_pairs": 80.0 * pairs,
+            "total": 12.0 * n_atoms * n_k + 80.0 * pairs + 150.0 * n_terms + 6.0 * n_rows + 40.0 * n_excl + 4.0 * n_atoms}
+
+
+def run_ours(args, pos, box, force, workload):
+    import torch
+    import torch.distributed as dist
+    from openmm_chargeflux_b200 import runtime
+    from openmm_chargeflux_b200.parallel import ShardedCoulContext
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n = len(pos)
+    ctx = ShardedCoulContext(force, box, rank=rank, world=world, device=local)
+    ctx.d_pos.copy_(torch.from_numpy(pos.reshape(-1)))
+    torch.cuda.synchronize()
+    flush = torch.empty(384 << 20, dtype=torch.uint8, device="cuda")        # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        ctx.evaluate_device()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    barrier()
+    t_start = time.perf_counter()
+    for i in range(args.steps):
+        with torch.cuda.stream(ctx.stream):
+            flush.zero_()
+            ev0[i].record(ctx.stream)
+        ctx.evaluate_device()
+        ev1[i].record(ctx.stream)
+    barrier()
+    t_end = time.perf_counter()
+    ms = torch.tensor([sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(ms.item()) / args.steps
+    clocks = sampler.stop(t_start, t_end) if sampler else None
+    launches_per_eval = ctx.kernel.stats().kernel_launches
+
+    # end to end through the reference-facing call (host buffers in, host buffers out)
+    e2e_times = []
+    forces_host = np.zeros_like(pos)
+    for i in range(args.steps + 3):
+        flush.zero_()
+        barrier()
+        t = time.perf_counter()
+        if world == 1:
+            forces_host[:] = 0.0
+            if i == 0:
+                k1 = runtime.CalcCoulForceKernel(device=local)
+                k1.initialize(box, force)
+            k1.execute(pos, box, forces_host)
+        else:
+            ctx.evaluate(pos)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t
+        if i >= 3:
+            e2e_times.append(dt)
+    e2e_t = torch.tensor([float(np.mean(e2e_times))], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_s = float(e2e_t.item())
+
+    line = None
+    if rank == 0:
+        alpha, kmax, nk = ctx.kernel.ewald_params()
+        st = ctx.kernel.stats()
+        pairs = st.pairs_in_cutoff if world == 1 else None
+        value = 1e3 / ms_per_step
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32 (f64 energies/accumulation, int64 fixed-point forces)", "data": "synthetic",
+                "config": {"workload": workload, "atoms": n, "kmax": list(kmax), "kvectors": int(nk), "alpha": alpha,
+                           "l2": "384 MiB buffer written between timed steps (L2 flush); working set < L2",
+                           "parallelism": "k-vector rows + direct-space i-tiles sharded x%d, NCCL all-reduce of int64 forces" % world
+                           if world > 1 else "single GPU"},
+                "ns_per_day": ns_per_day(value),
+                "e2e": {"value": 1.0 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 24 * n, "d2h_bytes_per_step": 24 * n + 40,
+                        "ns_per_day": ns_per_day(1.0 / e2e_s)},
+                "gpu_launches": int(launches_per_eval) * args.steps,
+                "clocks": clocks}
+    if world == 1:
+        # per-kernel durations (CUDA events on the launching stream) and the roofline of the dominant one
+        tf_peak, _ = runtime.measure_fp32_peak(local, 5)
+        kt = ctx.kernel.time_kernels(ctx.d_pos.data_ptr(), box, 10)
+        ctx.evaluate_device()
+        torch.cuda.synchronize()
+        pairs = ctx.kernel.stats().pairs_in_cutoff
+        fl = algorithmic_flops(n, nk, pairs, force.getNumFluxBonds() + force.getNumFluxAngles() + force.getNumFluxWaters(),
+                               4 * force.getNumFluxBonds() + 9 * force.getNumFluxAngles() + 9 * force.getNumFluxWaters(),
+                               force.getNumExceptions())
+        top = max(kt, key=kt.get)
+        total_kernel_ms = sum(kt.values())
+        achieved = fl.get(top, 0.0) / (kt[top] * 1e-3) / 1e12
+        line["roofline"] = {"bound": "fp32", "kernel": top, "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
+                            "frac": achieved / tf_peak, "traffic": None,
+                            "peak_source": "FP32 FMA microbenchmark run in this process (cfx_measure_fp32_peak); "
+                                           "theoretical 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
+                            "kernel_ms": kt[top], "kernel_share_of_step": kt[top] / total_kernel_ms,
+                            "algorithmic_flop_per_launch": fl.get(top, 0.0),
+                            "whole_step": {"achieved": fl["total"] / (ms_per_step * 1e-3) / 1e12,
+                                           "frac": fl["total"] / (ms_per_step * 1e-3) / 1e12 / tf_peak,
+                                           "algorithmic_flop": fl["total"]}}
+        line["kernels_ms"] = {k: round(v, 5) for k, v in kt.items()}
+        line["kernel_fp32_frac"] = {k: fl[k] / (kt[k] * 1e-3) / 1e12 / tf_peak for k in ("structure_factor", "kspace_gather", "direct_pairs")
+                                    if k in kt}
+        line["config"]["pairs_in_cutoff"] = int(pairs)
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(pos, box, force)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    from openmm_chargeflux_b200 import synthetic
+    pos, box, force = synthetic.config(args.workload)
+    if args.impl == "reference":
+        run_reference_arm(args, pos, box, force, WORKLOADS[args.workload])
+    else:
+        run_ours(args, pos, box, force, WORKLOADS[args.workload])
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,63 @@
+"""Build recipes for the native code (run by __graft_entry__.build()).
+
+* libcfx_b200.so       -- the product: hand-written CUDA for sm_100a + the C ABI (nvcc, in-tree).
+* libOpenMMCoulB200.so -- the OpenMM plugin adapter (g++), needs the plugin's API headers from
+                          /root/reference and the OpenMM stand-in; skipped when those are absent.
+"""
+import os
+import shutil
+import subprocess
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+LIB = os.path.join(PKG, "libcfx_b200.so")
+PLUGIN_LIB = os.path.join(PKG, "plugin", "libOpenMMCoulB200.so")
+REF = os.environ.get("CFX_REFERENCE_DIR", "/root/reference")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+if os.environ.get("CFX_PTXAS_V"):
+    NVCC_FLAGS += ["-Xptxas", "-v"]
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def build_cuda(force=False, verbose=False):
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    sources = [os.path.join(CSRC, f) for f in ("api.cu", "flux.cu", "kspace.cu", "direct.cu")]
+    deps = sources + [os.path.join(CSRC, "cfx_internal.cuh"), os.path.join(ROOT, "include", "cfx_b200.h")]
+    if not force and not _newer(LIB, deps):
+        return LIB
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + sources
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.run(cmd, check=True)
+    return LIB
+
+
+def build_plugin(force=False, verbose=False):
+    """The KernelFactory-registered adapter; needs the plugin's own openmmapi headers."""
+    api_inc = os.path.join(REF, "openmmapi", "include")
+    ref_out = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.isdir(api_inc) or not os.path.exists(os.path.join(ref_out, "libOpenMMCoul.so")):
+        return PLUGIN_LIB if os.path.exists(PLUGIN_LIB) else None
+    src_dir = os.path.join(PKG, "plugin")
+    sources = [os.path.join(src_dir, f) for f in ("B200CoulKernels.cpp", "B200CoulKernelFactory.cpp")]
+    deps = sources + [os.path.join(src_dir, "B200CoulKernels.h"), os.path.join(src_dir, "B200CoulKernelFactory.h"),
+                      os.path.join(ROOT, "include", "cfx_b200.h")]
+    if not force and not _newer(PLUGIN_LIB, deps):
+        return PLUGIN_LIB
+    cmd = ["g++", "-O2", "-fPIC", "-std=c++17", "-shared", "-I" + os.path.join(ROOT, "shim"), "-I" + api_inc,
+           "-I" + os.path.join(ROOT, "include"), "-o", PLUGIN_LIB] + sources + [
+           "-L" + ref_out, "-lOpenMMCoul", "-lOpenMMShim", "-L" + PKG, "-lcfx_b200",
+           "-Wl,-rpath,$ORIGIN/../../oracle/_ref", "-Wl,-rpath,$ORIGIN/.."]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.run(cmd, check=True)
+    return PLUGIN_LIB

@@ -1,0 +1,184 @@
+// cfx_internal.cuh -- shared declarations of the B200 charge-flux Ewald library.
+//
+// Data layout in HBM (all owned by the handle, see DESIGN.md section "HBM layout"):
+//   user order : pos (double[3N]), q (double[N] + float[Npad]), Jacobian rows (double[3P]),
+//                fixed-point accumulators force[3][Npad], dedq[Npad] (int64, value*2^32),
+//   k-space    : per-atom phase rows, atom-major   rowS[atom] = {q*Ex[0..Kx), Ey[0..Ky), Ez[0..Kz)} (float2)
+//                per-index phase columns, n-major  Ex/Ey[n][Npad], Z4[l][Npad] = (c, s, l*c, l*s)
+//                structure-factor partials         part[split][row][col][8] (float)
+//                gather coefficients               coef[signedRow][Kz] (float4: Ar, Ai, Br, Bi)
+//   direct     : atoms sorted by cell: sortedLocal (float4: local xyz in cell, q), sortedCell (packed
+//                cell coordinates), sortedLJ (float2), sortedUser (user index), cellStart[ncell+1]
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/cfx_b200.h"
+
+#define CFX_FIXED_SCALE 4294967296.0            /* 2^32, OpenMM CUDA platform force convention */
+#define CFX_ENERGY_SCALE 16777216.0             /* 2^24: |E| < 5.4e11 kJ/mol, 6e-8 resolution   */
+
+namespace cfx {
+
+// ---------------------------------------------------------------------------------------------
+// error handling
+// ---------------------------------------------------------------------------------------------
+struct CudaError { cudaError_t code; const char* what; const char* file; int line; };
+void throwCuda(cudaError_t code, const char* what, const char* file, int line);
+#define CFX_CUDA(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) ::cfx::throwCuda(e__, #expr, __FILE__, __LINE__); } while (0)
+#define CFX_LAUNCH_CHECK() CFX_CUDA(cudaGetLastError())
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ long long toFixed(double v) { return __double2ll_rn(v*CFX_FIXED_SCALE); }
+__device__ __forceinline__ long long toFixedF(float v) { return __double2ll_rn((double) v*CFX_FIXED_SCALE); }
+__device__ __forceinline__ void atomicAddFixed(long long* addr, double v) {
+    atomicAdd(reinterpret_cast<unsigned long long*>(addr), static_cast<unsigned long long>(toFixed(v)));
+}
+__device__ __forceinline__ void atomicAddEnergy(long long* addr, double v) {
+    atomicAdd(reinterpret_cast<unsigned long long*>(addr), static_cast<unsigned long long>(__double2ll_rn(v*CFX_ENERGY_SCALE)));
+}
+__device__ __forceinline__ double warpSum(double v) {
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warpSumF(float v) {
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// Block-wide sum of a double; result valid in thread 0. `scratch` must hold 32 doubles.
+__device__ __forceinline__ double blockSum(double v, double* scratch) {
+    v = warpSum(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    v = (threadIdx.x < nw) ? scratch[threadIdx.x] : 0.0;
+    if (warp == 0) v = warpSum(v);
+    return v;
+}
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// per-handle state
+// ---------------------------------------------------------------------------------------------
+struct Box { double L[3]; double invL[3]; };
+
+struct KSpacePlan {
+    int K[3] = {0, 0, 0};        // kmax per axis (reference: nk in [0,K) / (-K,K))
+    int rowPitch = 0;            // float2 per atom row in rowS: Kx + Ky + KzPad
+    int kzPad = 0;               // Kz rounded up to the S kernel's column tile
+    int numRows = 0;             // unsigned rows (nx, |ny|): Kx*Ky
+    int numSignedRows = 0;       // gather rows (nx, ny): Ky + (Kx-1)*(2Ky-1)
+    // S kernel geometry
+    int sThreads = 256, sTN = 4, sTM = 2, sNC = 0, sTR = 0, sBM = 0, sRowTiles = 0, sSplits = 0, sAtomsPerSplit = 0;
+    int sStages = 3;
+    size_t sSmem = 0;
+    // shard of the unsigned rows this rank owns [rowLo, rowHi) (k-vector sharding)
+    int rowLo = 0, rowHi = 0;
+    int signedLo = 0, signedHi = 0;
+    // gather geometry
+    int gThreads = 512, gAtoms = 128, gRowsPerTile = 64, gRowSplits = 1;
+    size_t gSmem = 0;
+};
+
+struct CellPlan {
+    int nc[3] = {1, 1, 1};
+    int ncells = 1;
+    int lo[3] = {0, 0, 0}, nd[3] = {1, 1, 1};   // stencil offsets per axis: lo .. lo+nd-1
+    bool smallBox = false;                      // stencil wraps onto itself: per-pair min image
+    float cs[3] = {1, 1, 1};
+    double csd[3] = {1, 1, 1};
+};
+
+struct State {
+    // sizes
+    int N = 0, Npad = 0;
+    int nb = 0, na = 0, nw = 0, P = 0, numSlots = 0, numTerms = 0;
+    int numExcl = 0;
+    bool pbc = false;
+    double cutoff = 0, tol = 0, alpha = 0;
+    int device = 0, shardRank = 0, shardCount = 1;
+    bool useGraph = true;
+    KSpacePlan ks;
+    CellPlan cells;
+    int64_t numKVectors = 0;
+
+    cudaStream_t stream = nullptr;      // owned stream for the host-buffer path
+    // parameters (device)
+    double* q0 = nullptr;
+    float2* lj = nullptr;               // (sigma/2, 2*sqrt(eps)) per user atom, FP32 pair kernel
+    double2* ljd = nullptr;             // same in FP64 (energy, exclusion and non-periodic kernels)
+    int* termIdx = nullptr;             // [3*numTerms] particle indices (bond: p1,p2,-1)
+    double* termPar = nullptr;          // [5*numTerms]
+    int* qcsrPtr = nullptr; int* qcsrSlot = nullptr; double* qcsrCoef = nullptr;
+    int* rowDq = nullptr; int* rowDx = nullptr;
+    int2* exclPairs = nullptr;          // unique (p1<p2)
+    int* exclPtr = nullptr; int* exclCols = nullptr;   // symmetric CSR, sorted
+    // per-evaluation (device)
+    double* pos = nullptr;              // [3N] staging for the host path
+    double* dqSlot = nullptr;           // [numSlots]
+    double* rowVal = nullptr;           // [3P]
+    double* q = nullptr; float* qf = nullptr;
+    long long* forceFixed = nullptr;    // [3*Npad] internal accumulator (host path)
+    long long* dedqFixed = nullptr;     // [Npad]
+    long long* energyFixed = nullptr;   // [8]
+    double* forceOut = nullptr;         // [3N] double, user order (host path)
+    double* energyOut = nullptr;        // [CFX_E_COUNT]
+    // k-space
+    float2* rowS = nullptr;             // [Npad][rowPitch]
+    float2* colX = nullptr; float2* colY = nullptr;   // [Kx][Npad], [Ky][Npad]
+    float4* colZ4 = nullptr;            // [Kz][Npad]
+    float* sPart = nullptr;             // [splits][rowsPad][kzPad][8]
+    float4* gCoef = nullptr;            // [numSignedRows][Kz]
+    int2* gRowInfo = nullptr;           // [numSignedRows] (nx, ny)
+    int* ks_signedStart = nullptr;      // [numRows+1] first signed row of each unsigned row
+    // direct space
+    int* cellOfAtom = nullptr; int* cellCount = nullptr; int* cellStart = nullptr; int* cellFill = nullptr;
+    float4* userLocal = nullptr;        // [N] local xyz in own cell + q, user order (scratch of the cell build)
+    float4* sortedLocal = nullptr; int* sortedCell = nullptr; float2* sortedLJ = nullptr; int* sortedUser = nullptr;
+    int* sortedExclLo = nullptr; int* sortedExclHi = nullptr;
+    unsigned long long* pairCounters = nullptr;   // [4]: pairs in cutoff, candidates, emitted, overflow
+    int2* pairBuffer = nullptr; int64_t pairCapacity = 0;
+    // pinned host staging
+    double* hPos = nullptr; double* hForce = nullptr; double* hEnergy = nullptr;
+    // graphs, one per (includeForces, includeEnergy)
+    cudaGraphExec_t graphs[4] = {nullptr, nullptr, nullptr, nullptr};
+    int64_t launchesPerGraph[4] = {0, 0, 0, 0};
+    // cached graph of the device-pointer entry (cfx_execute_device), keyed by its arguments
+    struct DeviceGraphKey { const void* pos; void* force; void* dedq; void* energy; int flags; double L[3]; };
+    cudaGraphExec_t devGraph = nullptr;
+    DeviceGraphKey devKey = {nullptr, nullptr, nullptr, nullptr, -1, {0, 0, 0}};
+    int64_t devGraphLaunches = 0;
+    bool evaluated = false;
+    int64_t launches = 0;
+    Box box;
+    // host copies for getters
+    std::vector<int> hRowDq, hRowDx, hExclPtr, hExclCols;
+    // per-kernel timing (cfx_time_kernels)
+    bool timing = false;
+    std::vector<std::string> timeNames;
+    std::vector<cudaEvent_t> timeEvents;
+};
+
+// kernel launchers (each enqueues on `s`; no synchronisation)
+void launchFluxAssembly(State& st, const double* dPos, cudaStream_t s);                 // piece (1) + (4)
+void launchChainRule(State& st, long long* dForce, const long long* dDedq, cudaStream_t s);   // piece (5)
+void launchExclusionCorrection(State& st, const double* dPos, bool forces, long long* dForce, long long* dDedq, cudaStream_t s);
+void launchNoCutoff(State& st, const double* dPos, bool forces, bool energy, long long* dForce, long long* dDedq, cudaStream_t s);
+void launchFinalize(State& st, const long long* dForce, cudaStream_t s);
+void planKSpace(State& st);
+void launchKSpace(State& st, const double* dPos, bool forces, bool energy, long long* dForce, long long* dDedq, cudaStream_t s);  // piece (3)
+void planCells(State& st);
+void launchDirect(State& st, const double* dPos, bool forces, bool energy, bool emitPairs, long long* dForce, long long* dDedq, cudaStream_t s); // piece (2)
+void mark(State& st, const char* name, cudaStream_t s);   // per-kernel timing marker (no-op unless st.timing)
+
+} // namespace cfx

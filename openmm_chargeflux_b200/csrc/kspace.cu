@@ -1,0 +1,612 @@
+// kspace.cu -- piece (3): explicit-k reciprocal space (ReferenceCoulKernels.cpp:513-556).
+//
+// The reference evaluates, for every half-space k = 2*pi*(nx/Lx, ny/Ly, nz/Lz) with nx in [0,Kx),
+// ny,nz in (-K,K), the structure factor S(k) = sum_j q_j exp(i k.r_j) and then
+//   E += C a_k |S|^2,  F_i -= 2 C a_k q_i (S_s cos - S_c sin) k,  dE/dq_i += 2 C a_k (S_c cos + S_s sin)
+// with 4 libm trig calls per (atom,k). Here exp(i k.r) = Ex(nx) Ey(ny) Ez(nz) is factorised:
+//
+//  phaseTableKernel   per-atom, per-axis phases exp(2 pi i n u), FP64 sincospi of the wrapped
+//                     fractional coordinate + FP64 recurrence, stored as float2.
+//  structureFactorKernel  (S) rows = (nx,|ny|), cols = |nz|. Per (row,col) the eight real sums
+//                     P[a][b][c] = sum_j (q X)_a Y_b Z_c  (a: re/im of q*Ex, b: cos/sin of Ey, c: cos/sin of Ez)
+//                     give S at all four sign combinations (+-ny, +-nz): 8 FMA per 4 k-vectors
+//                     = 2 FMA per (atom,k). Register tile TM rows x TN cols per thread; per-atom phase
+//                     rows are streamed into shared memory with bulk-TMA (cp.async.bulk + mbarrier).
+//  coefficientKernel  sums the per-split partials in FP64, a_k = exp(-k^2/4alpha^2)/k^2 once per k,
+//                     E_recip in FP64, and gather coefficients A,B per (signed row, |nz|).
+//  gatherKernel       per atom: U = sum_l A_l c_l + B_l s_l, U' = sum_l l(-iB_l c_l + iA_l s_l) over |nz|
+//                     (4 FMA per (atom,k)), then T = Ex(nx)Ey(ny): dE/dq += Re(T U),
+//                     F += q (2pi/L) (nx Im(T U), ny Im(T U), Im(T U')).
+//
+// All main loops are FP32 FMA; cross-CTA reductions, a_k and energies are FP64 / fixed point.
+#include "cfx_internal.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+
+namespace cfx {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + bulk TMA (global -> shared, completion on an mbarrier)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smemU32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbarInit(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smemU32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbarFenceInit() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbarExpectTx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smemU32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarWait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smemU32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulkLoad(void* dstSmem, const void* srcGlobal, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smemU32(dstSmem)), "l"(srcGlobal), "r"(bytes), "r"(smemU32(bar)) : "memory");
+}
+__device__ __forceinline__ void cpAsync16(void* dstSmem, const void* srcGlobal) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smemU32(dstSmem)), "l"(srcGlobal) : "memory");
+}
+__device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cpAsyncWait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+// ------------------------------------------------------------------------------------------------
+// phase tables
+// ------------------------------------------------------------------------------------------------
+struct TableParams {
+    int N, Npad, Kx, Ky, Kz, kzPad, zOff, rowPitch;
+    double invLx, invLy, invLz;
+};
+
+// One thread per (atom, axis). Writes the atom-major rows used by the S kernel and the n-major
+// columns used by the gather kernel. Padded atoms (>= N) get all-zero phases.
+__global__ void __launch_bounds__(128) phaseTableKernel(TableParams p, const double* __restrict__ pos, const float* __restrict__ qf,
+        float2* __restrict__ rowS, float2* __restrict__ colX, float2* __restrict__ colY, float4* __restrict__ colZ4) {
+    const int t = blockIdx.x*blockDim.x + threadIdx.x;
+    const int atom = t % p.Npad, axis = t / p.Npad;
+    if (axis >= 3) return;
+    const int K = axis == 0 ? p.Kx : (axis == 1 ? p.Ky : p.Kz);
+    float2* row = rowS + (size_t) atom*p.rowPitch + (axis == 0 ? 0 : (axis == 1 ? p.Kx : p.zOff));
+    if (atom >= p.N) {
+        for (int n = 0; n < K; n++) {
+            row[n] = make_float2(0.f, 0.f);
+            if (axis == 0) colX[(size_t) n*p.Npad + atom] = make_float2(0.f, 0.f);
+            else if (axis == 1) colY[(size_t) n*p.Npad + atom] = make_float2(0.f, 0.f);
+            else colZ4[(size_t) n*p.Npad + atom] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    else {
+        const double invL = axis == 0 ? p.invLx : (axis == 1 ? p.invLy : p.invLz);
+        double u = pos[3*(size_t) atom + axis]*invL;
+        u -= floor(u);
+        double s1, c1;
+        sincospi(2.0*u, &s1, &c1);
+        const float scale = axis == 0 ? qf[atom] : 1.0f;
+        double c = 1.0, s = 0.0;
+        for (int n = 0; n < K; n++) {
+            const float cf = (float) c, sf = (float) s;
+            row[n] = make_float2(scale*cf, scale*sf);
+            if (axis == 0) colX[(size_t) n*p.Npad + atom] = make_float2(cf, sf);
+            else if (axis == 1) colY[(size_t) n*p.Npad + atom] = make_float2(cf, sf);
+            else colZ4[(size_t) n*p.Npad + atom] = make_float4(cf, sf, (float) n*cf, (float) n*sf);
+            const double cn = c*c1 - s*s1;
+            s = c*s1 + s*c1;
+            c = cn;
+        }
+    }
+    if (axis == 2)
+        for (int n = p.Kz; n < p.kzPad; n++) row[n] = make_float2(0.f, 0.f);
+    if (axis == 1)
+        for (int n = p.Kx + p.Ky; n < p.zOff; n++) rowS[(size_t) atom*p.rowPitch + n] = make_float2(0.f, 0.f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// structure factors
+// ------------------------------------------------------------------------------------------------
+#define S_ATOMS_PER_STAGE 32
+#define S_MAX_THREADS 288
+#define S_MAX_ROW_ITERS 4          // BM <= 128
+
+struct SParams {
+    const float2* rowS; float* part;
+    int rowPitch, Kx, Ky, zOff, kzPad;
+    int NC, TR, BM, asPitch, stages;
+    int rowLo, rowHi, numRows;
+    int atomsPerSplit, Npad;
+};
+
+template <int TM, int TN>
+__global__ void __launch_bounds__(S_MAX_THREADS, 2) structureFactorKernel(SParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem);
+    float2* raw = reinterpret_cast<float2*>(smem + 128);
+    const int stageElems = S_ATOMS_PER_STAGE*p.rowPitch;
+    float4* As = reinterpret_cast<float4*>(smem + 128 + (size_t) p.stages*stageElems*sizeof(float2));
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int rowBase = p.rowLo + blockIdx.x*p.BM;
+    const int rowEnd = min(rowBase + p.BM, p.rowHi);
+    const int atomBegin = blockIdx.y*p.atomsPerSplit;
+    const int atomEnd = min(atomBegin + p.atomsPerSplit, p.Npad);
+    const int numStages = (atomEnd - atomBegin)/S_ATOMS_PER_STAGE;
+    const uint32_t stageBytes = (uint32_t) (stageElems*sizeof(float2));
+
+    // rows this lane produces (fixed across stages): row = rowBase + lane + 32*it
+    int offX[S_MAX_ROW_ITERS], offY[S_MAX_ROW_ITERS];
+    #pragma unroll
+    for (int it = 0; it < S_MAX_ROW_ITERS; it++) {
+        const int row = rowBase + lane + 32*it;
+        if (lane + 32*it < p.BM && row < rowEnd) {
+            const int nx = row/p.Ky;
+            offX[it] = nx;
+            offY[it] = p.Kx + (row - nx*p.Ky);
+        }
+        else {
+            offX[it] = (lane + 32*it < p.BM) ? -1 : -2;       // -1: zero-fill, -2: outside the tile
+            offY[it] = 0;
+        }
+    }
+    const bool active = tid < p.TR*p.NC;
+    const int tc = tid % p.NC, tr = tid / p.NC;
+
+    float acc[TM][TN][8];
+    #pragma unroll
+    for (int i = 0; i < TM; i++)
+        #pragma unroll
+        for (int c = 0; c < TN; c++)
+            #pragma unroll
+            for (int k = 0; k < 8; k++) acc[i][c][k] = 0.f;
+
+    if (tid == 0) {
+        for (int s = 0; s < p.stages; s++) mbarInit(mbar + s, 1);
+        mbarFenceInit();
+    }
+    __syncthreads();
+    if (tid == 0)
+        for (int s = 0; s < p.stages && s < numStages; s++) {
+            mbarExpectTx(mbar + s, stageBytes);
+            bulkLoad(raw + (size_t) s*stageElems, p.rowS + (size_t) (atomBegin + s*S_ATOMS_PER_STAGE)*p.rowPitch, stageBytes, mbar + s);
+        }
+
+    for (int st = 0; st < numStages; st++) {
+        const int slot = st % p.stages;
+        mbarWait(mbar + slot, (uint32_t) ((st/p.stages) & 1));
+        const float2* rw = raw + (size_t) slot*stageElems;
+        // produce the row operand a = (xr*yc, xr*ys, xi*yc, xi*ys) with x = q*Ex(nx), y = Ey(|ny|)
+        for (int j = warp; j < S_ATOMS_PER_STAGE; j += nwarps) {
+            const float2* r = rw + j*p.rowPitch;
+            #pragma unroll
+            for (int it = 0; it < S_MAX_ROW_ITERS; it++) {
+                if (offX[it] >= 0) {
+                    const float2 x = r[offX[it]], y = r[offY[it]];
+                    As[j*p.asPitch + lane + 32*it] = make_float4(x.x*y.x, x.x*y.y, x.y*y.x, x.y*y.y);
+                }
+                else if (offX[it] == -1)
+                    As[j*p.asPitch + lane + 32*it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        __syncthreads();
+        if (active) {
+            const float4* aPtr = As + tr*TM;
+            const float4* bPtr = reinterpret_cast<const float4*>(rw + p.zOff + tc*TN);
+            const int bPitch4 = p.rowPitch/2;
+            #pragma unroll 4
+            for (int j = 0; j < S_ATOMS_PER_STAGE; j++) {
+                float4 a[TM];
+                float4 b[TN/2];
+                #pragma unroll
+                for (int i = 0; i < TM; i++) a[i] = aPtr[j*p.asPitch + i];
+                #pragma unroll
+                for (int c = 0; c < TN/2; c++) b[c] = bPtr[j*bPitch4 + c];
+                #pragma unroll
+                for (int i = 0; i < TM; i++)
+                    #pragma unroll
+                    for (int c = 0; c < TN; c++) {
+                        const float zc = (c & 1) ? b[c/2].z : b[c/2].x;
+                        const float zs = (c & 1) ? b[c/2].w : b[c/2].y;
+                        acc[i][c][0] = fmaf(a[i].x, zc, acc[i][c][0]);
+                        acc[i][c][1] = fmaf(a[i].x, zs, acc[i][c][1]);
+                        acc[i][c][2] = fmaf(a[i].y, zc, acc[i][c][2]);
+                        acc[i][c][3] = fmaf(a[i].y, zs, acc[i][c][3]);
+                        acc[i][c][4] = fmaf(a[i].z, zc, acc[i][c][4]);
+                        acc[i][c][5] = fmaf(a[i].z, zs, acc[i][c][5]);
+                        acc[i][c][6] = fmaf(a[i].w, zc, acc[i][c][6]);
+                        acc[i][c][7] = fmaf(a[i].w, zs, acc[i][c][7]);
+                    }
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && st + p.stages < numStages) {
+            mbarExpectTx(mbar + slot, stageBytes);
+            bulkLoad(raw + (size_t) slot*stageElems, p.rowS + (size_t) (atomBegin + (st + p.stages)*S_ATOMS_PER_STAGE)*p.rowPitch,
+                     stageBytes, mbar + slot);
+        }
+    }
+    if (active) {
+        #pragma unroll
+        for (int i = 0; i < TM; i++) {
+            const int row = rowBase + tr*TM + i;
+            if (row >= rowEnd) continue;
+            #pragma unroll
+            for (int c = 0; c < TN; c++) {
+                const int col = tc*TN + c;
+                float4* out = reinterpret_cast<float4*>(p.part + (((size_t) blockIdx.y*p.numRows + row)*p.kzPad + col)*8);
+                out[0] = make_float4(acc[i][c][0], acc[i][c][1], acc[i][c][2], acc[i][c][3]);
+                out[1] = make_float4(acc[i][c][4], acc[i][c][5], acc[i][c][6], acc[i][c][7]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// coefficients + reciprocal energy
+// ------------------------------------------------------------------------------------------------
+struct CoefParams {
+    const float* part; float4* coef; const int* signedStart;
+    int Kx, Ky, Kz, kzPad, numRows, splits, rowLo, rowHi;
+    double gx, gy, gz;          // 2 pi / L
+    double C;                   // 4 pi ke / V
+    double invFourAlpha2;
+    bool energy, forces;
+};
+
+__global__ void __launch_bounds__(128) coefficientKernel(CoefParams p, long long* __restrict__ energyFixed) {
+    __shared__ double scratch[32];
+    const int t = blockIdx.x*blockDim.x + threadIdx.x;
+    const int rowsHere = p.rowHi - p.rowLo;
+    double en = 0.0;
+    if (t < rowsHere*p.Kz) {
+        const int row = p.rowLo + t/p.Kz, l = t % p.Kz;
+        const int nx = row/p.Ky, m = row - nx*p.Ky;
+        double P[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int s = 0; s < p.splits; s++) {
+            const float4* src = reinterpret_cast<const float4*>(p.part + (((size_t) s*p.numRows + row)*p.kzPad + l)*8);
+            const float4 v0 = src[0], v1 = src[1];
+            P[0] += v0.x; P[1] += v0.y; P[2] += v0.z; P[3] += v0.w;
+            P[4] += v1.x; P[5] += v1.y; P[6] += v1.z; P[7] += v1.w;
+        }
+        // P = {rcc, rcs, rsc, rss, icc, ics, isc, iss}
+        const double kx = nx*p.gx, ky = m*p.gy, kz = l*p.gz;
+        const double k2 = kx*kx + ky*ky + kz*kz;
+        const double ak = (nx | m | l) ? exp(-k2*p.invFourAlpha2)/k2 : 0.0;
+        double Gre[2][2], Gim[2][2];     // [sy: 0=+,1=-][sz: 0=+,1=-]
+        #pragma unroll
+        for (int iy = 0; iy < 2; iy++)
+            #pragma unroll
+            for (int iz = 0; iz < 2; iz++) {
+                const double sy = iy ? -1.0 : 1.0, sz = iz ? -1.0 : 1.0;
+                const bool exists = !(iy && m == 0) && !(iz && l == 0);
+                const int ny = iy ? -m : m, nz = iz ? -l : l;
+                const bool inHalf = exists && (nx > 0 || ny > 0 || (ny == 0 && nz > 0));
+                const double re = P[0] - sy*sz*P[3] - sz*P[5] - sy*P[6];
+                const double im = P[4] - sy*sz*P[7] + sz*P[1] + sy*P[2];
+                if (inHalf) {
+                    en += p.C*ak*(re*re + im*im);
+                    Gre[iy][iz] = 2.0*p.C*ak*re;
+                    Gim[iy][iz] = 2.0*p.C*ak*im;
+                }
+                else { Gre[iy][iz] = 0.0; Gim[iy][iz] = 0.0; }
+            }
+        if (p.forces) {
+            // signed rows of this unsigned row: (nx,+m) first, then (nx,-m) when it exists
+            const int sBase = p.signedStart[row];
+            const int nSigned = p.signedStart[row+1] - sBase;
+            for (int iy = 0; iy < nSigned; iy++) {
+                // H+- = conj(G(ny, +-l)); A = H+ + H-, B = i (H+ - H-)
+                const double hpr = Gre[iy][0], hpi = -Gim[iy][0];
+                const double hmr = Gre[iy][1], hmi = -Gim[iy][1];
+                float4 c;
+                c.x = (float) (hpr + hmr);
+                c.y = (float) (hpi + hmi);
+                c.z = (float) (-(hpi - hmi));
+                c.w = (float) (hpr - hmr);
+                p.coef[(size_t) (sBase + iy)*p.Kz + l] = c;
+            }
+        }
+    }
+    if (p.energy) {
+        en = blockSum(en, scratch);
+        if (threadIdx.x == 0) atomicAddEnergy(energyFixed + CFX_E_RECIP, en);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// force / dE/dq gather
+// ------------------------------------------------------------------------------------------------
+#define G_THREADS 256
+#define G_WARPS 8
+#define G_ROWS_PER_WARP 4
+#define G_ROW_TILE (G_WARPS*G_ROWS_PER_WARP)
+
+struct GParams {
+    const float4* coef; const int2* rowInfo; const float2* colX; const float2* colY; const float4* colZ4;
+    const float* qf;
+    int Kx, Ky, Kz, N, Npad;
+    int signedLo, signedHi, rowsPerSplit;
+    float fx, fy, fz;            // 2 pi / L
+    size_t offEy, offCoef, offInfo;     // shared-memory carve-up (bytes)
+};
+
+template <int APT>
+__global__ void __launch_bounds__(G_THREADS, 2) gatherKernel(GParams p, long long* __restrict__ forceFixed, long long* __restrict__ dedqFixed) {
+    constexpr int BA = 32*APT;
+    extern __shared__ __align__(128) unsigned char smem[];
+    float4* Z4s = reinterpret_cast<float4*>(smem);                         // [Kz][BA]
+    float2* Eys = reinterpret_cast<float2*>(smem + p.offEy);               // [Ky][BA]
+    float4* coefS = reinterpret_cast<float4*>(smem + p.offCoef);           // [2][G_ROW_TILE][Kz]
+    int2* infoS = reinterpret_cast<int2*>(smem + p.offInfo);               // [2][G_ROW_TILE]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int atom0 = blockIdx.x*BA;
+    const int r0 = p.signedLo + blockIdx.y*p.rowsPerSplit;
+    const int r1 = min(r0 + p.rowsPerSplit, p.signedHi);
+    if (r0 >= r1) return;
+    const int numTiles = (r1 - r0 + G_ROW_TILE - 1)/G_ROW_TILE;
+    const int tileElems = G_ROW_TILE*p.Kz;
+
+    auto prefetchTile = [&](int tile, int buf) {
+        const float4* src = p.coef + (size_t) (r0 + tile*G_ROW_TILE)*p.Kz;
+        float4* dst = coefS + (size_t) buf*tileElems;
+        for (int e = tid; e < tileElems; e += G_THREADS) cpAsync16(dst + e, src + e);
+        if (tid < G_ROW_TILE) infoS[buf*G_ROW_TILE + tid] = p.rowInfo[r0 + tile*G_ROW_TILE + tid];
+        cpAsyncCommit();
+    };
+    prefetchTile(0, 0);
+    for (int e = tid; e < p.Kz*BA; e += G_THREADS) {
+        const int l = e/BA, a = e - l*BA;
+        Z4s[e] = p.colZ4[(size_t) l*p.Npad + atom0 + a];
+    }
+    for (int e = tid; e < p.Ky*BA; e += G_THREADS) {
+        const int m = e/BA, a = e - m*BA;
+        Eys[e] = p.colY[(size_t) m*p.Npad + atom0 + a];
+    }
+
+    float oD[APT], oX[APT], oY[APT], oZ[APT];
+    #pragma unroll
+    for (int a = 0; a < APT; a++) { oD[a] = 0.f; oX[a] = 0.f; oY[a] = 0.f; oZ[a] = 0.f; }
+    int curNx = -1;
+    float2 ex[APT];
+    #pragma unroll
+    for (int a = 0; a < APT; a++) ex[a] = make_float2(0.f, 0.f);
+
+    for (int tile = 0; tile < numTiles; tile++) {
+        const int buf = tile & 1;
+        if (tile + 1 < numTiles) { prefetchTile(tile + 1, buf ^ 1); cpAsyncWait<1>(); }
+        else cpAsyncWait<0>();
+        __syncthreads();
+        const float4* cT = coefS + (size_t) buf*tileElems + (size_t) warp*G_ROWS_PER_WARP*p.Kz;
+        float2 U[G_ROWS_PER_WARP][APT], V[G_ROWS_PER_WARP][APT];
+        #pragma unroll
+        for (int i = 0; i < G_ROWS_PER_WARP; i++)
+            #pragma unroll
+            for (int a = 0; a < APT; a++) { U[i][a] = make_float2(0.f, 0.f); V[i][a] = make_float2(0.f, 0.f); }
+        #pragma unroll 3
+        for (int l = 0; l < p.Kz; l++) {
+            float4 c[G_ROWS_PER_WARP], z[APT];
+            #pragma unroll
+            for (int i = 0; i < G_ROWS_PER_WARP; i++) c[i] = cT[i*p.Kz + l];
+            #pragma unroll
+            for (int a = 0; a < APT; a++) z[a] = Z4s[l*BA + lane + 32*a];
+            #pragma unroll
+            for (int i = 0; i < G_ROWS_PER_WARP; i++)
+                #pragma unroll
+                for (int a = 0; a < APT; a++) {
+                    U[i][a].x = fmaf(c[i].x, z[a].x, U[i][a].x);  U[i][a].x = fmaf(c[i].z, z[a].y, U[i][a].x);
+                    U[i][a].y = fmaf(c[i].y, z[a].x, U[i][a].y);  U[i][a].y = fmaf(c[i].w, z[a].y, U[i][a].y);
+                    V[i][a].x = fmaf(c[i].w, z[a].z, V[i][a].x);  V[i][a].x = fmaf(-c[i].y, z[a].w, V[i][a].x);
+                    V[i][a].y = fmaf(-c[i].z, z[a].z, V[i][a].y); V[i][a].y = fmaf(c[i].x, z[a].w, V[i][a].y);
+                }
+        }
+        // epilogue: T = Ex(nx) Ey(ny); accumulate Re(T U), nx Im(T U), ny Im(T U), Im(T U')
+        #pragma unroll
+        for (int i = 0; i < G_ROWS_PER_WARP; i++) {
+            const int rloc = warp*G_ROWS_PER_WARP + i;
+            if (r0 + tile*G_ROW_TILE + rloc >= r1) continue;
+            const int2 info = infoS[buf*G_ROW_TILE + rloc];
+            if (info.x != curNx) {
+                curNx = info.x;
+                #pragma unroll
+                for (int a = 0; a < APT; a++) ex[a] = p.colX[(size_t) curNx*p.Npad + atom0 + lane + 32*a];
+            }
+            const int m = abs(info.y);
+            const float sgn = info.y < 0 ? -1.f : 1.f;
+            const float fnx = (float) info.x, fny = (float) info.y;
+            #pragma unroll
+            for (int a = 0; a < APT; a++) {
+                float2 ey = Eys[m*BA + lane + 32*a];
+                ey.y *= sgn;
+                const float tr = ex[a].x*ey.x - ex[a].y*ey.y;
+                const float ti = ex[a].x*ey.y + ex[a].y*ey.x;
+                oD[a] = fmaf(tr, U[i][a].x, oD[a]);  oD[a] = fmaf(-ti, U[i][a].y, oD[a]);
+                const float im = tr*U[i][a].y + ti*U[i][a].x;
+                oX[a] = fmaf(fnx, im, oX[a]);
+                oY[a] = fmaf(fny, im, oY[a]);
+                oZ[a] = fmaf(tr, V[i][a].y, oZ[a]);  oZ[a] = fmaf(ti, V[i][a].x, oZ[a]);
+            }
+        }
+        __syncthreads();
+    }
+    // cross-warp reduction through shared memory (aliases Z4s), then one fixed-point atomic per output
+    float4* red = reinterpret_cast<float4*>(smem);
+    #pragma unroll
+    for (int a = 0; a < APT; a++) red[warp*BA + lane + 32*a] = make_float4(oD[a], oX[a], oY[a], oZ[a]);
+    __syncthreads();
+    if (tid < BA) {
+        float4 s = red[tid];
+        #pragma unroll
+        for (int w = 1; w < G_WARPS; w++) {
+            const float4 v = red[w*BA + tid];
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+        const int atom = atom0 + tid;
+        if (atom < p.N) {
+            const double q = (double) p.qf[atom];
+            atomicAddFixed(dedqFixed + atom, (double) s.x);
+            atomicAddFixed(forceFixed + atom, q*(double) p.fx*(double) s.y);
+            atomicAddFixed(forceFixed + p.Npad + atom, q*(double) p.fy*(double) s.z);
+            atomicAddFixed(forceFixed + 2*(size_t) p.Npad + atom, q*(double) p.fz*(double) s.w);
+        }
+    }
+}
+
+size_t gatherSmem(int Kx, int Ky, int Kz, int BA, size_t* offEy, size_t* offCoef, size_t* offInfo) {
+    size_t z4 = (size_t) Kz*BA*sizeof(float4);
+    size_t red = (size_t) G_WARPS*BA*sizeof(float4);
+    size_t first = std::max(z4, red);
+    first = (first + 127) & ~(size_t) 127;
+    *offEy = first;
+    size_t ey = ((size_t) Ky*BA*sizeof(float2) + 127) & ~(size_t) 127;
+    *offCoef = first + ey;
+    size_t coef = ((size_t) 2*G_ROW_TILE*Kz*sizeof(float4) + 127) & ~(size_t) 127;
+    *offInfo = *offCoef + coef;
+    return *offInfo + 2*G_ROW_TILE*sizeof(int2);
+}
+
+} // namespace
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+void planKSpace(State& st) {
+    KSpacePlan& ks = st.ks;
+    const int Kx = ks.K[0], Ky = ks.K[1], Kz = ks.K[2];
+    ks.sTM = 2; ks.sTN = 4;
+    ks.sNC = (Kz + ks.sTN - 1)/ks.sTN;
+    ks.kzPad = ks.sNC*ks.sTN;
+    const int zOff = (Kx + Ky + 1) & ~1;
+    ks.rowPitch = zOff + ks.kzPad;
+    ks.numRows = Kx*Ky;
+    // shard the unsigned rows over ranks (k-vector sharding)
+    ks.rowLo = (int) ((int64_t) ks.numRows*st.shardRank/st.shardCount);
+    ks.rowHi = (int) ((int64_t) ks.numRows*(st.shardRank + 1)/st.shardCount);
+    const int rowsHere = ks.rowHi - ks.rowLo;
+    // block size / tile: maximise useful-FMA fraction (row padding x idle threads)
+    double best = -1.0;
+    const int candidates[] = {256, 288, 224, 192, 160, 128};
+    for (int threads : candidates) {
+        if (ks.sNC > threads) continue;
+        int TR = threads/ks.sNC;
+        int BM = TR*ks.sTM;
+        if (BM > 32*S_MAX_ROW_ITERS) { TR = 32*S_MAX_ROW_ITERS/ks.sTM; BM = TR*ks.sTM; }
+        int tiles = (std::max(rowsHere, 1) + BM - 1)/BM;
+        double eff = (double) std::max(rowsHere, 1)/(tiles*BM)*((double) TR*ks.sNC/threads);
+        if (eff > best + 1e-9) { best = eff; ks.sThreads = threads; ks.sTR = TR; ks.sBM = BM; ks.sRowTiles = tiles; }
+    }
+    ks.sStages = 2;
+    const size_t stageBytes = (size_t) S_ATOMS_PER_STAGE*ks.rowPitch*sizeof(float2);
+    const size_t asBytes = (size_t) S_ATOMS_PER_STAGE*ks.sBM*sizeof(float4);
+    ks.sSmem = 128 + ks.sStages*stageBytes + asBytes;
+    // atom splits: fill ~2 CTAs per SM
+    int numSM = 148;
+    cudaDeviceGetAttribute(&numSM, cudaDevAttrMultiProcessorCount, st.device);
+    const int slots = 2*numSM;
+    int splits = std::max(1, slots/std::max(1, ks.sRowTiles));
+    const int maxSplits = std::max(1, st.Npad/(4*S_ATOMS_PER_STAGE));       // >= 4 stages per CTA
+    splits = std::min(splits, maxSplits);
+    int aps = (st.Npad + splits - 1)/splits;
+    aps = (aps + S_ATOMS_PER_STAGE - 1)/S_ATOMS_PER_STAGE*S_ATOMS_PER_STAGE;
+    splits = (st.Npad + aps - 1)/aps;
+    ks.sSplits = splits;
+    ks.sAtomsPerSplit = aps;
+    // signed rows
+    std::vector<int> signedStart(ks.numRows + 1, 0);
+    std::vector<int2> rowInfo;
+    for (int row = 0; row < ks.numRows; row++) {
+        const int nx = row/Ky, m = row % Ky;
+        signedStart[row] = (int) rowInfo.size();
+        rowInfo.push_back(make_int2(nx, m));
+        if (nx > 0 && m > 0) rowInfo.push_back(make_int2(nx, -m));
+    }
+    signedStart[ks.numRows] = (int) rowInfo.size();
+    ks.numSignedRows = (int) rowInfo.size();
+    ks.signedLo = signedStart[ks.rowLo];
+    ks.signedHi = signedStart[ks.rowHi];
+    for (int k = 0; k < G_ROW_TILE; k++) rowInfo.push_back(make_int2(0, 0));   // padding rows (zero coefficients)
+
+    CFX_CUDA(cudaMalloc(&st.rowS, (size_t) st.Npad*ks.rowPitch*sizeof(float2)));
+    CFX_CUDA(cudaMalloc(&st.colX, (size_t) Kx*st.Npad*sizeof(float2)));
+    CFX_CUDA(cudaMalloc(&st.colY, (size_t) Ky*st.Npad*sizeof(float2)));
+    CFX_CUDA(cudaMalloc(&st.colZ4, (size_t) Kz*st.Npad*sizeof(float4)));
+    CFX_CUDA(cudaMalloc(&st.sPart, (size_t) ks.sSplits*ks.numRows*ks.kzPad*8*sizeof(float)));
+    const size_t coefElems = (size_t) (ks.numSignedRows + G_ROW_TILE)*Kz;
+    CFX_CUDA(cudaMalloc(&st.gCoef, coefElems*sizeof(float4)));
+    CFX_CUDA(cudaMemset(st.gCoef, 0, coefElems*sizeof(float4)));
+    CFX_CUDA(cudaMalloc(&st.gRowInfo, rowInfo.size()*sizeof(int2)));
+    CFX_CUDA(cudaMemcpy(st.gRowInfo, rowInfo.data(), rowInfo.size()*sizeof(int2), cudaMemcpyHostToDevice));
+    int* dSigned = nullptr;
+    CFX_CUDA(cudaMalloc(&dSigned, signedStart.size()*sizeof(int)));
+    CFX_CUDA(cudaMemcpy(dSigned, signedStart.data(), signedStart.size()*sizeof(int), cudaMemcpyHostToDevice));
+    st.ks_signedStart = dSigned;
+
+    // gather geometry
+    ks.gAtoms = 128;
+    size_t o1, o2, o3;
+    ks.gSmem = gatherSmem(Kx, Ky, Kz, ks.gAtoms, &o1, &o2, &o3);
+    const int signedHere = ks.signedHi - ks.signedLo;
+    const int atomTiles = st.Npad/ks.gAtoms;
+    int rowSplits = std::max(1, (2*numSM + atomTiles - 1)/atomTiles);
+    rowSplits = std::min(rowSplits, std::max(1, signedHere/(4*G_ROW_TILE)));
+    int rps = (std::max(signedHere, 1) + rowSplits - 1)/rowSplits;
+    rps = (rps + G_ROW_TILE - 1)/G_ROW_TILE*G_ROW_TILE;
+    ks.gRowSplits = (std::max(signedHere, 1) + rps - 1)/rps;
+    ks.gRowsPerTile = rps;      // rows per split
+
+    CFX_CUDA(cudaFuncSetAttribute(structureFactorKernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ks.sSmem));
+    CFX_CUDA(cudaFuncSetAttribute(gatherKernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ks.gSmem));
+}
+
+void launchKSpace(State& st, const double* dPos, bool forces, bool energy, long long* dForce, long long* dDedq, cudaStream_t s) {
+    KSpacePlan& ks = st.ks;
+    if (!forces && !energy) return;
+    const int Kx = ks.K[0], Ky = ks.K[1], Kz = ks.K[2];
+    const int zOff = ks.rowPitch - ks.kzPad;
+    TableParams tp{st.N, st.Npad, Kx, Ky, Kz, ks.kzPad, zOff, ks.rowPitch, 1.0/st.box.L[0], 1.0/st.box.L[1], 1.0/st.box.L[2]};
+    phaseTableKernel<<<(3*st.Npad + 127)/128, 128, 0, s>>>(tp, dPos, st.qf, st.rowS, st.colX, st.colY, st.colZ4);
+    CFX_LAUNCH_CHECK(); st.launches++;
+    mark(st, "phase_tables", s);
+    if (ks.rowHi <= ks.rowLo) return;
+
+    SParams sp;
+    sp.rowS = st.rowS; sp.part = st.sPart;
+    sp.rowPitch = ks.rowPitch; sp.Kx = Kx; sp.Ky = Ky; sp.zOff = zOff; sp.kzPad = ks.kzPad;
+    sp.NC = ks.sNC; sp.TR = ks.sTR; sp.BM = ks.sBM; sp.asPitch = ks.sBM; sp.stages = ks.sStages;
+    sp.rowLo = ks.rowLo; sp.rowHi = ks.rowHi; sp.numRows = ks.numRows;
+    sp.atomsPerSplit = ks.sAtomsPerSplit; sp.Npad = st.Npad;
+    structureFactorKernel<2, 4><<<dim3(ks.sRowTiles, ks.sSplits), ks.sThreads, ks.sSmem, s>>>(sp);
+    CFX_LAUNCH_CHECK(); st.launches++;
+    mark(st, "structure_factor", s);
+
+    CoefParams cp;
+    cp.part = st.sPart; cp.coef = st.gCoef; cp.signedStart = st.ks_signedStart;
+    cp.Kx = Kx; cp.Ky = Ky; cp.Kz = Kz; cp.kzPad = ks.kzPad; cp.numRows = ks.numRows; cp.splits = ks.sSplits;
+    cp.rowLo = ks.rowLo; cp.rowHi = ks.rowHi;
+    cp.gx = 2*M_PI/st.box.L[0]; cp.gy = 2*M_PI/st.box.L[1]; cp.gz = 2*M_PI/st.box.L[2];
+    cp.C = 4.0/st.box.L[0]/st.box.L[1]/st.box.L[2]*M_PI*CFX_ONE_4PI_EPS0;
+    cp.invFourAlpha2 = 0.25/(st.alpha*st.alpha);
+    cp.energy = energy; cp.forces = forces;
+    const int items = (ks.rowHi - ks.rowLo)*Kz;
+    coefficientKernel<<<(items + 127)/128, 128, 0, s>>>(cp, st.energyFixed);
+    CFX_LAUNCH_CHECK(); st.launches++;
+    mark(st, "kspace_coef", s);
+
+    if (forces && ks.signedHi > ks.signedLo) {
+        GParams gp;
+        gp.coef = st.gCoef; gp.rowInfo = st.gRowInfo; gp.colX = st.colX; gp.colY = st.colY; gp.colZ4 = st.colZ4; gp.qf = st.qf;
+        gp.Kx = Kx; gp.Ky = Ky; gp.Kz = Kz; gp.N = st.N; gp.Npad = st.Npad;
+        gp.signedLo = ks.signedLo; gp.signedHi = ks.signedHi; gp.rowsPerSplit = ks.gRowsPerTile;
+        gp.fx = (float) cp.gx; gp.fy = (float) cp.gy; gp.fz = (float) cp.gz;
+        gatherSmem(Kx, Ky, Kz, ks.gAtoms, &gp.offEy, &gp.offCoef, &gp.offInfo);
+        gatherKernel<4><<<dim3(st.Npad/ks.gAtoms, ks.gRowSplits), G_THREADS, ks.gSmem, s>>>(gp, dForce, dDedq);
+        CFX_LAUNCH_CHECK(); st.launches++;
+        mark(st, "kspace_gather", s);
+    }
+}
+
+} // namespace cfx

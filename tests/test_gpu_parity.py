@@ -1,0 +1,173 @@
+"""GPU: the CUDA path (through the C ABI) against the CPU oracle and the golden vectors.
+
+Tolerances are those of BASELINE.json's north_star: neighbour and exclusion lists bit-exact, energies
+1e-6 relative, forces 1e-5 relative RMS (mixed precision)."""
+import numpy as np
+import pytest
+
+from conftest import E_RTOL, F_RTOL, GOLDEN_NAMES, golden_case, rel_rms
+from openmm_chargeflux_b200 import _abi, runtime, synthetic
+from openmm_chargeflux_b200.force import CoulForce
+from oracle import Oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _compare(pos, box, force, check_pairs=True, flags=((True, True), (True, False), (False, True), (False, False))):
+    o = Oracle(force, box)
+    ctx = runtime.CoulContext(force, box)
+    for inc_f, inc_e in flags:
+        eo, fo = o.execute(pos, box, inc_f, inc_e)
+        e, f, comps = ctx.evaluate(pos, inc_f, inc_e)
+        scale = max(abs(eo[4]), 1e-3 * np.abs(eo[:4]).max())
+        assert abs(e - eo[4]) <= E_RTOL * abs(eo[4]) or abs(e - eo[4]) <= 1e-9 * np.abs(eo[:4]).max(), (inc_f, inc_e, e, eo)
+        assert np.abs(comps[:4] - eo[:4]).max() <= E_RTOL * scale
+        if inc_f:
+            assert rel_rms(f, fo) <= F_RTOL, (inc_f, inc_e)
+        else:
+            # without includeForces only the self-term chain rule reaches the forces (reference quirk)
+            assert np.abs(f - fo).max() <= 1e-9 * max(1.0, np.abs(fo).max())
+    eo, fo = o.execute(pos, box)
+    ctx.evaluate(pos)
+    assert np.abs(ctx.kernel.charges() - o.charges()).max() <= 1e-14
+    assert rel_rms(ctx.kernel.dedq(), o.dedq()) <= F_RTOL
+    dq, dx, val = ctx.kernel.jacobian()
+    odq, odx, oval = o.jacobian()
+    assert np.array_equal(dq, odq) and np.array_equal(dx, odx)
+    if len(oval):
+        assert np.abs(val - oval).max() <= 1e-12 * max(1.0, np.abs(oval).max())
+    if force.usesPeriodicBoundaryConditions() and check_pairs:
+        assert np.array_equal(ctx.kernel.neighbor_pairs(), o.neighbor_pairs())
+        assert ctx.kernel.stats().pairs_in_cutoff == len(o.neighbor_pairs())
+        assert ctx.kernel.ewald_params() == o.ewald_params()
+    return ctx, o
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_golden_vectors(name, build_native):
+    data, pos, box, force = golden_case(name)
+    ctx = runtime.CoulContext(force, box)
+    for inc_f in (1, 0):
+        for inc_e in (1, 0):
+            e, f, _ = ctx.evaluate(pos, bool(inc_f), bool(inc_e))
+            e_ref = float(data["energy_f%d_e%d" % (inc_f, inc_e)])
+            f_ref = data["forces_f%d_e%d" % (inc_f, inc_e)]
+            assert abs(e - e_ref) <= E_RTOL * abs(e_ref)
+            if inc_f and np.abs(f_ref).max() > 1e-6:
+                assert rel_rms(f, f_ref) <= F_RTOL
+            elif inc_f:
+                assert np.abs(f - f_ref).max() <= 1e-2          # rock salt: forces vanish by symmetry
+    ctx.evaluate(pos)
+    assert np.abs(ctx.kernel.charges() - data["charges"]).max() <= 1e-14
+    if len(data["jac_val"]):
+        assert np.abs(ctx.kernel.jacobian()[2] - data["jac_val"]).max() <= 1e-12 * max(1.0, np.abs(data["jac_val"]).max())
+    if force.usesPeriodicBoundaryConditions():
+        assert np.array_equal(ctx.kernel.neighbor_pairs(), data["pairs"])          # bit-exact neighbour list
+
+
+def test_config1_64_waters_nonperiodic(build_native):
+    _compare(*synthetic.config("c1"))
+
+
+def test_config2_4k_water_box(build_native):
+    _compare(*synthetic.config("c2"), flags=((True, True), (True, False)))
+
+
+def test_config5_methanol_water(build_native):
+    _compare(*synthetic.config("c5"))
+
+
+@pytest.mark.parametrize("flux", ["bond+angle", "water", "none"])
+def test_small_periodic_boxes(flux, build_native):
+    _compare(*synthetic.water_box(125, seed=21, cutoff=0.75, ewald_tol=3e-5, flux=flux))
+
+
+def test_exclusion_lists_match_reference_sets(build_native):
+    pos, box, force = synthetic.methanol_water(10, 30, seed=1, cutoff=0.55, ewald_tol=1e-4)
+    force.addException(3, 0)       # duplicate of an existing pair, reversed
+    force.addException(7, 7)       # self pair: never evaluated by the reference (p1 < p2 test)
+    ctx, o = _compare(pos, box, force)
+    ptr, cols = ctx.kernel.exclusions()
+    sets = [set() for _ in range(force.getNumParticles())]
+    for k in range(force.getNumExceptions()):
+        a, b = force.getExceptionParameters(k)
+        sets[a].add(b); sets[b].add(a)
+    for i, s in enumerate(sets):
+        assert list(cols[ptr[i]:ptr[i + 1]]) == sorted(s)
+
+
+def test_edge_cases(build_native):
+    # no flux terms, no exclusions, atoms far outside the box, non-cubic box, tiny system
+    rng = np.random.default_rng(5)
+    n = 37
+    box = np.diag([2.3, 2.9, 2.1])
+    pos = rng.uniform(-7, 9, size=(n, 3))
+    q = rng.normal(size=n); q -= q.mean()
+    f = CoulForce()
+    f._bulk(q, rng.uniform(0.2, 0.3, n), rng.uniform(0.0, 0.5, n))
+    f.setUsesPeriodicBoundaryConditions(True); f.setCutoffDistance(1.0); f.setEwaldErrorTolerance(1e-5)
+    _compare(pos, box, f)
+    # two particles
+    f2 = CoulForce(); f2.addParticle(1.0, 0.3, 0.2); f2.addParticle(-1.0, 0.3, 0.2)
+    f2.setUsesPeriodicBoundaryConditions(True); f2.setCutoffDistance(0.9)
+    _compare(np.array([[0.1, 0.2, 0.3], [0.5, 0.6, 0.2]]), np.diag([2.0, 2.0, 2.0]), f2)
+    # empty system
+    f0 = CoulForce(); f0.setUsesPeriodicBoundaryConditions(True)
+    ctx = runtime.CoulContext(f0, np.diag([3.0] * 3))
+    assert ctx.evaluate(np.zeros((0, 3)))[0] == 0.0
+
+
+def test_errors_are_reported_not_swallowed(build_native):
+    pos, box, force = synthetic.water_box(27, seed=5, cutoff=0.45)
+    ctx = runtime.CoulContext(force, box)
+    with pytest.raises(runtime.CfxError, match="rectangular"):
+        ctx.kernel.execute(pos, np.array([[1.5, 0, 0], [0.2, 1.5, 0], [0, 0, 1.5]]))
+    with pytest.raises(runtime.CfxError, match="twice the cutoff"):
+        ctx.kernel.execute(pos, np.diag([0.8, 2.0, 2.0]))
+    with pytest.raises(runtime.CfxError):
+        ctx.kernel.execute(pos[:-1], box)
+    bad = CoulForce(); bad.addParticle(0, 0, 0); bad.addFluxBond(0, 5, 1.0, 0.1)
+    with pytest.raises(runtime.CfxError, match="out of range"):
+        runtime.CoulContext(bad, box)
+
+
+def test_forces_accumulate_and_box_can_change(build_native):
+    pos, box, force = synthetic.water_box(64, seed=3, cutoff=0.6, ewald_tol=1e-5)
+    ctx = runtime.CoulContext(force, box)
+    base = np.random.default_rng(0).normal(size=pos.shape)
+    forces = base.copy()
+    ctx.kernel.execute(pos, box, forces)
+    _, f0, _ = ctx.evaluate(pos)
+    assert rel_rms(forces - base, f0) < 1e-12
+    # a different box at execute time: kmax/alpha stay those of the default box (reference semantics)
+    box2 = box * 1.07
+    o = Oracle(force, box)
+    eo, fo = o.execute(pos * 1.07, box2)
+    ctx.box = box2
+    e, f, _ = ctx.evaluate(pos * 1.07)
+    assert abs(e - eo[4]) <= E_RTOL * abs(eo[4]) and rel_rms(f, fo) <= F_RTOL
+
+
+def test_results_are_bitwise_reproducible(build_native):
+    pos, box, force = synthetic.config("c2")
+    ctx = runtime.CoulContext(force, box)
+    e1, f1, c1 = ctx.evaluate(pos)
+    e2, f2, c2 = ctx.evaluate(pos)
+    ctx2 = runtime.CoulContext(force, box)
+    e3, f3, c3 = ctx2.evaluate(pos)
+    assert e1 == e2 == e3 and np.array_equal(f1, f2) and np.array_equal(f1, f3)
+
+
+def test_finite_difference_of_gpu_energy(build_native):
+    # chain rule on the GPU: central differences of the GPU energy vs the GPU forces
+    pos, box, force = synthetic.methanol_water(8, 24, seed=5, cutoff=0.5, ewald_tol=1e-6)
+    ctx = runtime.CoulContext(force, box)
+    _, f, _ = ctx.evaluate(pos)
+    h = 2e-4
+    for a in (0, 4, 5, 50):
+        for c in range(3):
+            p = pos.copy(); p[a, c] += h
+            ep = ctx.evaluate(p, False, True)[0]
+            p[a, c] -= 2 * h
+            em = ctx.evaluate(p, False, True)[0]
+            assert abs(-(ep - em) / (2 * h) - f[a, c]) <= 2e-3 * np.abs(f).max()
