@@ -64,7 +64,7 @@ void setBox(State& st, const double* box) {
 void freeCells(State& st) {
     cudaFree(st.cellOfAtom); cudaFree(st.cellCount); cudaFree(st.cellStart); cudaFree(st.cellFill);
     cudaFree(st.userLocal); cudaFree(st.sortedLocal); cudaFree(st.sortedCell); cudaFree(st.sortedLJ); cudaFree(st.sortedUser);
-    cudaFree(st.pairCounters);
+    cudaFree(st.pairCounters); cudaFree(st.filledUser); st.filledUser = nullptr;
     st.cellOfAtom = st.cellCount = st.cellStart = st.cellFill = st.sortedCell = st.sortedUser = nullptr;
     st.userLocal = st.sortedLocal = nullptr; st.sortedLJ = nullptr; st.pairCounters = nullptr;
 }
@@ -104,7 +104,7 @@ void enqueueEvaluation(State& st, const double* dPos, bool includeForces, bool i
         // reference quirks mirrored: reciprocal energy only with includeEnergy; direct,
         // self and exclusion energies always; pair/recip forces and dE/dq only with includeForces
         launchKSpace(st, dPos, includeForces, includeEnergy, dForce, st.dedqFixed, s);
-        launchDirect(st, dPos, includeForces, true, false, dForce, st.dedqFixed, s);
+        launchDirect(st, dPos, includeForces, includeEnergy, false, dForce, st.dedqFixed, s);
         launchExclusionCorrection(st, dPos, includeForces, dForce, st.dedqFixed, s);
     }
     else

@@ -145,7 +145,7 @@ struct State {
     int* cellOfAtom = nullptr; int* cellCount = nullptr; int* cellStart = nullptr; int* cellFill = nullptr;
     float4* userLocal = nullptr;        // [N] local xyz in own cell + q, user order (scratch of the cell build)
     float4* sortedLocal = nullptr; int* sortedCell = nullptr; float2* sortedLJ = nullptr; int* sortedUser = nullptr;
-    int* sortedExclLo = nullptr; int* sortedExclHi = nullptr;
+    int* filledUser = nullptr;          // cell fill in arrival order (input of the rank pass)
     unsigned long long* pairCounters = nullptr;   // [4]: pairs in cutoff, candidates, emitted, overflow
     int2* pairBuffer = nullptr; int64_t pairCapacity = 0;
     // pinned host staging

@@ -110,31 +110,26 @@ __global__ void __launch_bounds__(256) cellFillKernel(int N, const int* __restri
     sortedUser[slot] = i;
 }
 
-// one thread per cell: sort the cell's user indices ascending (insertion sort; ~15 entries) so the
-// sorted order -- and with it every FP32 accumulation order downstream -- is deterministic
-__global__ void __launch_bounds__(128) cellSortKernel(int ncells, const int* __restrict__ cellStart, int* __restrict__ sortedUser) {
-    const int c = blockIdx.x*blockDim.x + threadIdx.x;
-    if (c >= ncells) return;
-    const int s0 = cellStart[c], s1 = cellStart[c+1];
-    for (int a = s0 + 1; a < s1; a++) {
-        const int v = sortedUser[a];
-        int b = a - 1;
-        while (b >= s0 && sortedUser[b] > v) { sortedUser[b+1] = sortedUser[b]; b--; }
-        sortedUser[b+1] = v;
-    }
-}
-
-__global__ void __launch_bounds__(256) cellGatherKernel(int N, int ncy, int ncz, const int* __restrict__ sortedUser,
-        const int* __restrict__ cellOfAtom, const float4* __restrict__ userLocal, const float2* __restrict__ lj,
-        float4* __restrict__ sortedLocal, int* __restrict__ sortedCell, float2* __restrict__ sortedLJ) {
+// One thread per slot of the (arbitrarily ordered) cell fill: the atom's final slot is the start of
+// its cell plus its rank among the cell's atoms by user index, so the sorted order -- and with it every
+// FP32 accumulation order downstream -- is deterministic. Writes all sorted arrays in one pass.
+__global__ void __launch_bounds__(256) cellRankGatherKernel(int N, int ncy, int ncz, const int* __restrict__ filledUser,
+        const int* __restrict__ cellOfAtom, const int* __restrict__ cellStart, const float4* __restrict__ userLocal,
+        const float2* __restrict__ lj, int* __restrict__ sortedUser, float4* __restrict__ sortedLocal,
+        int* __restrict__ sortedCell, float2* __restrict__ sortedLJ) {
     const int s = blockIdx.x*blockDim.x + threadIdx.x;
     if (s >= N) return;
-    const int u = sortedUser[s];
+    const int u = filledUser[s];
     const int cell = cellOfAtom[u];
+    const int s0 = cellStart[cell], s1 = cellStart[cell+1];
+    int rank = 0;
+    for (int t = s0; t < s1; t++) rank += (filledUser[t] < u) ? 1 : 0;
+    const int dst = s0 + rank;
     const int cz = cell % ncz, cy = (cell/ncz) % ncy, cx = cell/(ncz*ncy);
-    sortedLocal[s] = userLocal[u];
-    sortedCell[s] = cx | (cy << CELL_BITS) | (cz << (2*CELL_BITS));
-    sortedLJ[s] = lj[u];
+    sortedUser[dst] = u;
+    sortedLocal[dst] = userLocal[u];
+    sortedCell[dst] = cx | (cy << CELL_BITS) | (cz << (2*CELL_BITS));
+    sortedLJ[dst] = lj[u];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -165,6 +160,22 @@ __device__ __forceinline__ int wrapNearest(int d, int nc) {
     if (d > half) d -= nc;
     if (d < -(nc >> 1)) d += nc;
     return d;
+}
+
+// erfc(x), x >= 0, relative error ~1.2e-7 (Chebyshev fit in t = 1/(1 + x/2), Numerical Recipes erfcc):
+// one MUFU.RCP, nine FFMA and one MUFU.EX2 instead of the ~40-instruction erfcf().
+__device__ __forceinline__ float erfcFast(float x, float x2) {
+    const float t = __fdividef(1.f, fmaf(0.5f, x, 1.f));
+    float p = fmaf(t, 0.17087277f, -0.82215223f);
+    p = fmaf(t, p, 1.48851587f);
+    p = fmaf(t, p, -1.13520398f);
+    p = fmaf(t, p, 0.27886807f);
+    p = fmaf(t, p, -0.18628806f);
+    p = fmaf(t, p, 0.09678418f);
+    p = fmaf(t, p, 0.37409196f);
+    p = fmaf(t, p, 1.00002368f);
+    p = fmaf(t, p, -1.26551223f);
+    return t*__expf(p - x2);
 }
 
 // exact FP64 predicate with the reference's operation order (J - I with I the lower user index;
@@ -288,13 +299,14 @@ __global__ void __launch_bounds__(P_WARPS*32) pairKernel(PairParams p) {
                     const float invR = rsqrtf(r2);
                     const float r = r2*invR;
                     const float ar = p.alpha*r;
-                    const float erfcv = erfcf(ar);
+                    const float ar2 = ar*ar;
+                    const float erfcv = erfcFast(ar, ar2);
                     const float coul = keqi*pj.w*invR;
                     const float sig = lji.x + ljj.x;
                     float s2 = sig*invR; s2 *= s2;
                     const float s6 = s2*s2*s2;
                     const float es6 = s6*(lji.y*ljj.y);
-                    const float ex = __expf(-ar*ar);
+                    const float ex = __expf(-ar2);
                     const float invR2 = invR*invR;
                     const float dEdR = (coul*(erfcv + ar*ex*1.1283791671f) + es6*(12.f*s6 - 6.f))*invR2;
                     fx = fmaf(dEdR, dx, fx); fy = fmaf(dEdR, dy, fy); fz = fmaf(dEdR, dz, fz);
@@ -445,10 +457,12 @@ void planCells(State& st) {
     CFX_CUDA(cudaMalloc(&st.sortedCell, sizeof(int)*st.Npad));
     CFX_CUDA(cudaMalloc(&st.sortedLJ, sizeof(float2)*st.Npad));
     CFX_CUDA(cudaMalloc(&st.sortedUser, sizeof(int)*st.Npad));
+    CFX_CUDA(cudaMalloc(&st.filledUser, sizeof(int)*st.Npad));
     CFX_CUDA(cudaMalloc(&st.pairCounters, sizeof(unsigned long long)*4));
 }
 
 void launchDirect(State& st, const double* dPos, bool forces, bool energy, bool emitPairs, long long* dForce, long long* dDedq, cudaStream_t s) {
+    if (!forces && !energy && !emitPairs) return;
     CellPlan& c = st.cells;
     CellParams cp{st.N, c.nc[0], c.nc[1], c.nc[2], c.ncells, 1.0/st.box.L[0], 1.0/st.box.L[1], 1.0/st.box.L[2], c.csd[0], c.csd[1], c.csd[2]};
     CFX_CUDA(cudaMemsetAsync(st.cellCount, 0, sizeof(int)*(c.ncells + 1), s));
@@ -456,12 +470,10 @@ void launchDirect(State& st, const double* dPos, bool forces, bool energy, bool 
     CFX_LAUNCH_CHECK(); st.launches++;
     cellScanKernel<<<1, 1024, 0, s>>>(c.ncells, st.cellCount, st.cellStart, st.cellFill);
     CFX_LAUNCH_CHECK(); st.launches++;
-    cellFillKernel<<<(st.N + 255)/256, 256, 0, s>>>(st.N, st.cellOfAtom, st.cellFill, st.sortedUser);
+    cellFillKernel<<<(st.N + 255)/256, 256, 0, s>>>(st.N, st.cellOfAtom, st.cellFill, st.filledUser);
     CFX_LAUNCH_CHECK(); st.launches++;
-    cellSortKernel<<<(c.ncells + 127)/128, 128, 0, s>>>(c.ncells, st.cellStart, st.sortedUser);
-    CFX_LAUNCH_CHECK(); st.launches++;
-    cellGatherKernel<<<(st.N + 255)/256, 256, 0, s>>>(st.N, c.nc[1], c.nc[2], st.sortedUser, st.cellOfAtom, st.userLocal, st.lj,
-            st.sortedLocal, st.sortedCell, st.sortedLJ);
+    cellRankGatherKernel<<<(st.N + 255)/256, 256, 0, s>>>(st.N, c.nc[1], c.nc[2], st.filledUser, st.cellOfAtom, st.cellStart,
+            st.userLocal, st.lj, st.sortedUser, st.sortedLocal, st.sortedCell, st.sortedLJ);
     CFX_LAUNCH_CHECK(); st.launches++;
     mark(st, "cell_build", s);
 

@@ -24,6 +24,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <stdexcept>
 
 namespace cfx {
 
@@ -62,6 +63,7 @@ template <int N> __device__ __forceinline__ void cpAsyncWait() { asm volatile("c
 // ------------------------------------------------------------------------------------------------
 struct TableParams {
     int N, Npad, Kx, Ky, Kz, kzPad, zOff, rowPitch;
+    int TN, TNP;                 // S-kernel column grouping: |nz| = l lives in slot (l/TN)*TNP + l%TN
     double invLx, invLy, invLz;
 };
 
@@ -74,9 +76,11 @@ __global__ void __launch_bounds__(128) phaseTableKernel(TableParams p, const dou
     if (axis >= 3) return;
     const int K = axis == 0 ? p.Kx : (axis == 1 ? p.Ky : p.Kz);
     float2* row = rowS + (size_t) atom*p.rowPitch + (axis == 0 ? 0 : (axis == 1 ? p.Kx : p.zOff));
+    if (axis == 2)
+        for (int n = 0; n < p.kzPad; n++) row[n] = make_float2(0.f, 0.f);       // includes the padding slots
     if (atom >= p.N) {
         for (int n = 0; n < K; n++) {
-            row[n] = make_float2(0.f, 0.f);
+            if (axis != 2) row[n] = make_float2(0.f, 0.f);
             if (axis == 0) colX[(size_t) n*p.Npad + atom] = make_float2(0.f, 0.f);
             else if (axis == 1) colY[(size_t) n*p.Npad + atom] = make_float2(0.f, 0.f);
             else colZ4[(size_t) n*p.Npad + atom] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -92,7 +96,7 @@ __global__ void __launch_bounds__(128) phaseTableKernel(TableParams p, const dou
         double c = 1.0, s = 0.0;
         for (int n = 0; n < K; n++) {
             const float cf = (float) c, sf = (float) s;
-            row[n] = make_float2(scale*cf, scale*sf);
+            row[axis == 2 ? (n/p.TN)*p.TNP + n % p.TN : n] = make_float2(scale*cf, scale*sf);
             if (axis == 0) colX[(size_t) n*p.Npad + atom] = make_float2(cf, sf);
             else if (axis == 1) colY[(size_t) n*p.Npad + atom] = make_float2(cf, sf);
             else colZ4[(size_t) n*p.Npad + atom] = make_float4(cf, sf, (float) n*cf, (float) n*sf);
@@ -101,8 +105,6 @@ __global__ void __launch_bounds__(128) phaseTableKernel(TableParams p, const dou
             c = cn;
         }
     }
-    if (axis == 2)
-        for (int n = p.Kz; n < p.kzPad; n++) row[n] = make_float2(0.f, 0.f);
     if (axis == 1)
         for (int n = p.Kx + p.Ky; n < p.zOff; n++) rowS[(size_t) atom*p.rowPitch + n] = make_float2(0.f, 0.f);
 }
@@ -111,54 +113,54 @@ __global__ void __launch_bounds__(128) phaseTableKernel(TableParams p, const dou
 // structure factors
 // ------------------------------------------------------------------------------------------------
 #define S_ATOMS_PER_STAGE 32
-#define S_MAX_THREADS 288
-#define S_MAX_ROW_ITERS 4          // BM <= 128
+#define S_BM 64                    // rows per CTA: lane + 32*i, i < 2
+#define S_MAX_WARPS 8
 
 struct SParams {
     const float2* rowS; float* part;
     int rowPitch, Kx, Ky, zOff, kzPad;
-    int NC, TR, BM, asPitch, stages;
+    int stages;
     int rowLo, rowHi, numRows;
     int atomsPerSplit, Npad;
 };
 
-template <int TM, int TN>
-__global__ void __launch_bounds__(S_MAX_THREADS, 2) structureFactorKernel(SParams p) {
+// One CTA = 64 rows x all |nz| columns over one split of the atoms. Warp g owns column group g (TN
+// columns, padded to TNP float2 so the group is 16-byte aligned) for all 64 rows; lane owns rows
+// lane and lane+32. Per atom a warp issues 2 lane-distinct LDS.128 (row operand, conflict-free, 4
+// wavefronts each) and TNP/2 warp-UNIFORM LDS.128 (column operand, 1 wavefront each) for 16*TN FFMA.
+template <int TN>
+__global__ void __launch_bounds__(32*S_MAX_WARPS, 1) structureFactorKernel(SParams p) {
+    constexpr int TNP = (TN + 1) & ~1;
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem);
     float2* raw = reinterpret_cast<float2*>(smem + 128);
     const int stageElems = S_ATOMS_PER_STAGE*p.rowPitch;
-    float4* As = reinterpret_cast<float4*>(smem + 128 + (size_t) p.stages*stageElems*sizeof(float2));
+    float4* As = reinterpret_cast<float4*>(smem + 128 + (size_t) p.stages*stageElems*sizeof(float2));   // [32][S_BM]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    const int rowBase = p.rowLo + blockIdx.x*p.BM;
-    const int rowEnd = min(rowBase + p.BM, p.rowHi);
+    const int rowBase = p.rowLo + blockIdx.x*S_BM;
+    const int rowEnd = min(rowBase + S_BM, p.rowHi);
     const int atomBegin = blockIdx.y*p.atomsPerSplit;
     const int atomEnd = min(atomBegin + p.atomsPerSplit, p.Npad);
     const int numStages = (atomEnd - atomBegin)/S_ATOMS_PER_STAGE;
     const uint32_t stageBytes = (uint32_t) (stageElems*sizeof(float2));
 
-    // rows this lane produces (fixed across stages): row = rowBase + lane + 32*it
-    int offX[S_MAX_ROW_ITERS], offY[S_MAX_ROW_ITERS];
+    // rows this lane produces and consumes (fixed across stages)
+    int offX[2], offY[2];
     #pragma unroll
-    for (int it = 0; it < S_MAX_ROW_ITERS; it++) {
+    for (int it = 0; it < 2; it++) {
         const int row = rowBase + lane + 32*it;
-        if (lane + 32*it < p.BM && row < rowEnd) {
+        if (row < rowEnd) {
             const int nx = row/p.Ky;
             offX[it] = nx;
             offY[it] = p.Kx + (row - nx*p.Ky);
         }
-        else {
-            offX[it] = (lane + 32*it < p.BM) ? -1 : -2;       // -1: zero-fill, -2: outside the tile
-            offY[it] = 0;
-        }
+        else { offX[it] = -1; offY[it] = 0; }
     }
-    const bool active = tid < p.TR*p.NC;
-    const int tc = tid % p.NC, tr = tid / p.NC;
 
-    float acc[TM][TN][8];
+    float acc[2][TN][8];
     #pragma unroll
-    for (int i = 0; i < TM; i++)
+    for (int i = 0; i < 2; i++)
         #pragma unroll
         for (int c = 0; c < TN; c++)
             #pragma unroll
@@ -179,47 +181,43 @@ __global__ void __launch_bounds__(S_MAX_THREADS, 2) structureFactorKernel(SParam
         const int slot = st % p.stages;
         mbarWait(mbar + slot, (uint32_t) ((st/p.stages) & 1));
         const float2* rw = raw + (size_t) slot*stageElems;
-        // produce the row operand a = (xr*yc, xr*ys, xi*yc, xi*ys) with x = q*Ex(nx), y = Ey(|ny|)
+        // row operand a = (xr*yc, xr*ys, xi*yc, xi*ys) with x = q*Ex(nx), y = Ey(|ny|)
         for (int j = warp; j < S_ATOMS_PER_STAGE; j += nwarps) {
             const float2* r = rw + j*p.rowPitch;
             #pragma unroll
-            for (int it = 0; it < S_MAX_ROW_ITERS; it++) {
+            for (int it = 0; it < 2; it++) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (offX[it] >= 0) {
                     const float2 x = r[offX[it]], y = r[offY[it]];
-                    As[j*p.asPitch + lane + 32*it] = make_float4(x.x*y.x, x.x*y.y, x.y*y.x, x.y*y.y);
+                    v = make_float4(x.x*y.x, x.x*y.y, x.y*y.x, x.y*y.y);
                 }
-                else if (offX[it] == -1)
-                    As[j*p.asPitch + lane + 32*it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                As[j*S_BM + lane + 32*it] = v;
             }
         }
         __syncthreads();
-        if (active) {
-            const float4* aPtr = As + tr*TM;
-            const float4* bPtr = reinterpret_cast<const float4*>(rw + p.zOff + tc*TN);
+        {
+            const float4* aPtr = As + lane;
+            const float4* bPtr = reinterpret_cast<const float4*>(rw + p.zOff + warp*TNP);
             const int bPitch4 = p.rowPitch/2;
-            #pragma unroll 4
+            #pragma unroll 2
             for (int j = 0; j < S_ATOMS_PER_STAGE; j++) {
-                float4 a[TM];
-                float4 b[TN/2];
+                const float4 a0 = aPtr[j*S_BM], a1 = aPtr[j*S_BM + 32];
+                float4 b[TNP/2];
                 #pragma unroll
-                for (int i = 0; i < TM; i++) a[i] = aPtr[j*p.asPitch + i];
+                for (int c = 0; c < TNP/2; c++) b[c] = bPtr[j*bPitch4 + c];
                 #pragma unroll
-                for (int c = 0; c < TN/2; c++) b[c] = bPtr[j*bPitch4 + c];
-                #pragma unroll
-                for (int i = 0; i < TM; i++)
-                    #pragma unroll
-                    for (int c = 0; c < TN; c++) {
-                        const float zc = (c & 1) ? b[c/2].z : b[c/2].x;
-                        const float zs = (c & 1) ? b[c/2].w : b[c/2].y;
-                        acc[i][c][0] = fmaf(a[i].x, zc, acc[i][c][0]);
-                        acc[i][c][1] = fmaf(a[i].x, zs, acc[i][c][1]);
-                        acc[i][c][2] = fmaf(a[i].y, zc, acc[i][c][2]);
-                        acc[i][c][3] = fmaf(a[i].y, zs, acc[i][c][3]);
-                        acc[i][c][4] = fmaf(a[i].z, zc, acc[i][c][4]);
-                        acc[i][c][5] = fmaf(a[i].z, zs, acc[i][c][5]);
-                        acc[i][c][6] = fmaf(a[i].w, zc, acc[i][c][6]);
-                        acc[i][c][7] = fmaf(a[i].w, zs, acc[i][c][7]);
-                    }
+                for (int c = 0; c < TN; c++) {
+                    const float zc = (c & 1) ? b[c/2].z : b[c/2].x;
+                    const float zs = (c & 1) ? b[c/2].w : b[c/2].y;
+                    acc[0][c][0] = fmaf(a0.x, zc, acc[0][c][0]);  acc[0][c][1] = fmaf(a0.x, zs, acc[0][c][1]);
+                    acc[0][c][2] = fmaf(a0.y, zc, acc[0][c][2]);  acc[0][c][3] = fmaf(a0.y, zs, acc[0][c][3]);
+                    acc[0][c][4] = fmaf(a0.z, zc, acc[0][c][4]);  acc[0][c][5] = fmaf(a0.z, zs, acc[0][c][5]);
+                    acc[0][c][6] = fmaf(a0.w, zc, acc[0][c][6]);  acc[0][c][7] = fmaf(a0.w, zs, acc[0][c][7]);
+                    acc[1][c][0] = fmaf(a1.x, zc, acc[1][c][0]);  acc[1][c][1] = fmaf(a1.x, zs, acc[1][c][1]);
+                    acc[1][c][2] = fmaf(a1.y, zc, acc[1][c][2]);  acc[1][c][3] = fmaf(a1.y, zs, acc[1][c][3]);
+                    acc[1][c][4] = fmaf(a1.z, zc, acc[1][c][4]);  acc[1][c][5] = fmaf(a1.z, zs, acc[1][c][5]);
+                    acc[1][c][6] = fmaf(a1.w, zc, acc[1][c][6]);  acc[1][c][7] = fmaf(a1.w, zs, acc[1][c][7]);
+                }
             }
         }
         __syncthreads();
@@ -229,18 +227,16 @@ __global__ void __launch_bounds__(S_MAX_THREADS, 2) structureFactorKernel(SParam
                      stageBytes, mbar + slot);
         }
     }
-    if (active) {
+    #pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const int row = rowBase + lane + 32*i;
+        if (row >= rowEnd) continue;
         #pragma unroll
-        for (int i = 0; i < TM; i++) {
-            const int row = rowBase + tr*TM + i;
-            if (row >= rowEnd) continue;
-            #pragma unroll
-            for (int c = 0; c < TN; c++) {
-                const int col = tc*TN + c;
-                float4* out = reinterpret_cast<float4*>(p.part + (((size_t) blockIdx.y*p.numRows + row)*p.kzPad + col)*8);
-                out[0] = make_float4(acc[i][c][0], acc[i][c][1], acc[i][c][2], acc[i][c][3]);
-                out[1] = make_float4(acc[i][c][4], acc[i][c][5], acc[i][c][6], acc[i][c][7]);
-            }
+        for (int c = 0; c < TN; c++) {
+            const int col = warp*TNP + c;
+            float4* out = reinterpret_cast<float4*>(p.part + (((size_t) blockIdx.y*p.numRows + row)*p.kzPad + col)*8);
+            out[0] = make_float4(acc[i][c][0], acc[i][c][1], acc[i][c][2], acc[i][c][3]);
+            out[1] = make_float4(acc[i][c][4], acc[i][c][5], acc[i][c][6], acc[i][c][7]);
         }
     }
 }
@@ -250,7 +246,7 @@ __global__ void __launch_bounds__(S_MAX_THREADS, 2) structureFactorKernel(SParam
 // ------------------------------------------------------------------------------------------------
 struct CoefParams {
     const float* part; float4* coef; const int* signedStart;
-    int Kx, Ky, Kz, kzPad, numRows, splits, rowLo, rowHi;
+    int Kx, Ky, Kz, kzPad, numRows, splits, rowLo, rowHi, TN, TNP;
     double gx, gy, gz;          // 2 pi / L
     double C;                   // 4 pi ke / V
     double invFourAlpha2;
@@ -267,7 +263,8 @@ __global__ void __launch_bounds__(128) coefficientKernel(CoefParams p, long long
         const int nx = row/p.Ky, m = row - nx*p.Ky;
         double P[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         for (int s = 0; s < p.splits; s++) {
-            const float4* src = reinterpret_cast<const float4*>(p.part + (((size_t) s*p.numRows + row)*p.kzPad + l)*8);
+            const int slotL = (l/p.TN)*p.TNP + l % p.TN;
+            const float4* src = reinterpret_cast<const float4*>(p.part + (((size_t) s*p.numRows + row)*p.kzPad + slotL)*8);
             const float4 v0 = src[0], v1 = src[1];
             P[0] += v0.x; P[1] += v0.y; P[2] += v0.z; P[3] += v0.w;
             P[4] += v1.x; P[5] += v1.y; P[6] += v1.z; P[7] += v1.w;
@@ -320,8 +317,8 @@ __global__ void __launch_bounds__(128) coefficientKernel(CoefParams p, long long
 // ------------------------------------------------------------------------------------------------
 // force / dE/dq gather
 // ------------------------------------------------------------------------------------------------
-#define G_THREADS 256
-#define G_WARPS 8
+#define G_THREADS 384
+#define G_WARPS 12
 #define G_ROWS_PER_WARP 4
 #define G_ROW_TILE (G_WARPS*G_ROWS_PER_WARP)
 
@@ -329,13 +326,16 @@ struct GParams {
     const float4* coef; const int2* rowInfo; const float2* colX; const float2* colY; const float4* colZ4;
     const float* qf;
     int Kx, Ky, Kz, N, Npad;
-    int signedLo, signedHi, rowsPerSplit;
+    int signedLo, signedHi, numRowTiles, numAtomTiles;
     float fx, fy, fz;            // 2 pi / L
     size_t offEy, offCoef, offInfo;     // shared-memory carve-up (bytes)
 };
 
+// Persistent kernel: one CTA per SM walks a contiguous range of work units (atom tile, row tile),
+// atom-tile major, so every SM gets the same amount of work to within one row tile (no wave tail) and
+// reloads the per-atom-tile phase columns only when the atom tile changes.
 template <int APT>
-__global__ void __launch_bounds__(G_THREADS, 2) gatherKernel(GParams p, long long* __restrict__ forceFixed, long long* __restrict__ dedqFixed) {
+__global__ void __launch_bounds__(G_THREADS, 1) gatherKernel(GParams p, long long* __restrict__ forceFixed, long long* __restrict__ dedqFixed) {
     constexpr int BA = 32*APT;
     extern __shared__ __align__(128) unsigned char smem[];
     float4* Z4s = reinterpret_cast<float4*>(smem);                         // [Kz][BA]
@@ -344,41 +344,73 @@ __global__ void __launch_bounds__(G_THREADS, 2) gatherKernel(GParams p, long lon
     int2* infoS = reinterpret_cast<int2*>(smem + p.offInfo);               // [2][G_ROW_TILE]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int atom0 = blockIdx.x*BA;
-    const int r0 = p.signedLo + blockIdx.y*p.rowsPerSplit;
-    const int r1 = min(r0 + p.rowsPerSplit, p.signedHi);
-    if (r0 >= r1) return;
-    const int numTiles = (r1 - r0 + G_ROW_TILE - 1)/G_ROW_TILE;
+    const int numRowTiles = p.numRowTiles;
+    const long long totalUnits = (long long) p.numAtomTiles*numRowTiles;
+    const int u0 = (int) (totalUnits*blockIdx.x/gridDim.x), u1 = (int) (totalUnits*(blockIdx.x + 1)/gridDim.x);
+    if (u0 >= u1) return;
     const int tileElems = G_ROW_TILE*p.Kz;
 
-    auto prefetchTile = [&](int tile, int buf) {
-        const float4* src = p.coef + (size_t) (r0 + tile*G_ROW_TILE)*p.Kz;
+    auto prefetchTile = [&](int unit, int buf) {
+        const int rt = unit % numRowTiles;
+        const size_t row0 = (size_t) p.signedLo + (size_t) rt*G_ROW_TILE;
+        const float4* src = p.coef + row0*p.Kz;
         float4* dst = coefS + (size_t) buf*tileElems;
         for (int e = tid; e < tileElems; e += G_THREADS) cpAsync16(dst + e, src + e);
-        if (tid < G_ROW_TILE) infoS[buf*G_ROW_TILE + tid] = p.rowInfo[r0 + tile*G_ROW_TILE + tid];
+        if (tid < G_ROW_TILE) infoS[buf*G_ROW_TILE + tid] = p.rowInfo[row0 + tid];
         cpAsyncCommit();
     };
-    prefetchTile(0, 0);
-    for (int e = tid; e < p.Kz*BA; e += G_THREADS) {
-        const int l = e/BA, a = e - l*BA;
-        Z4s[e] = p.colZ4[(size_t) l*p.Npad + atom0 + a];
-    }
-    for (int e = tid; e < p.Ky*BA; e += G_THREADS) {
-        const int m = e/BA, a = e - m*BA;
-        Eys[e] = p.colY[(size_t) m*p.Npad + atom0 + a];
-    }
 
     float oD[APT], oX[APT], oY[APT], oZ[APT];
-    #pragma unroll
-    for (int a = 0; a < APT; a++) { oD[a] = 0.f; oX[a] = 0.f; oY[a] = 0.f; oZ[a] = 0.f; }
-    int curNx = -1;
     float2 ex[APT];
-    #pragma unroll
-    for (int a = 0; a < APT; a++) ex[a] = make_float2(0.f, 0.f);
+    int curNx = -1, curAtomTile = -1, atom0 = 0;
 
-    for (int tile = 0; tile < numTiles; tile++) {
-        const int buf = tile & 1;
-        if (tile + 1 < numTiles) { prefetchTile(tile + 1, buf ^ 1); cpAsyncWait<1>(); }
+    // cross-warp reduction through shared memory (aliases Z4s), then one fixed-point atomic per output
+    auto flush = [&]() {
+        __syncthreads();
+        float4* red = reinterpret_cast<float4*>(smem);
+        #pragma unroll
+        for (int a = 0; a < APT; a++) red[warp*BA + lane + 32*a] = make_float4(oD[a], oX[a], oY[a], oZ[a]);
+        __syncthreads();
+        if (tid < BA) {
+            float4 s = red[tid];
+            #pragma unroll
+            for (int w = 1; w < G_WARPS; w++) {
+                const float4 v = red[w*BA + tid];
+                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            }
+            const int atom = atom0 + tid;
+            if (atom < p.N) {
+                const double q = (double) p.qf[atom];
+                atomicAddFixed(dedqFixed + atom, (double) s.x);
+                atomicAddFixed(forceFixed + atom, q*(double) p.fx*(double) s.y);
+                atomicAddFixed(forceFixed + p.Npad + atom, q*(double) p.fy*(double) s.z);
+                atomicAddFixed(forceFixed + 2*(size_t) p.Npad + atom, q*(double) p.fz*(double) s.w);
+            }
+        }
+        __syncthreads();
+    };
+
+    prefetchTile(u0, 0);
+    for (int unit = u0; unit < u1; unit++) {
+        const int buf = (unit - u0) & 1;
+        const int atomTile = unit/numRowTiles, rowTile = unit - atomTile*numRowTiles;
+        if (atomTile != curAtomTile) {
+            if (curAtomTile >= 0) flush();
+            curAtomTile = atomTile;
+            atom0 = atomTile*BA;
+            for (int e = tid; e < p.Kz*BA; e += G_THREADS) {
+                const int l = e/BA, a = e - l*BA;
+                Z4s[e] = p.colZ4[(size_t) l*p.Npad + atom0 + a];
+            }
+            for (int e = tid; e < p.Ky*BA; e += G_THREADS) {
+                const int m = e/BA, a = e - m*BA;
+                Eys[e] = p.colY[(size_t) m*p.Npad + atom0 + a];
+            }
+            #pragma unroll
+            for (int a = 0; a < APT; a++) { oD[a] = 0.f; oX[a] = 0.f; oY[a] = 0.f; oZ[a] = 0.f; ex[a] = make_float2(0.f, 0.f); }
+            curNx = -1;
+        }
+        if (unit + 1 < u1) { prefetchTile(unit + 1, buf ^ 1); cpAsyncWait<1>(); }
         else cpAsyncWait<0>();
         __syncthreads();
         const float4* cT = coefS + (size_t) buf*tileElems + (size_t) warp*G_ROWS_PER_WARP*p.Kz;
@@ -405,10 +437,11 @@ __global__ void __launch_bounds__(G_THREADS, 2) gatherKernel(GParams p, long lon
                 }
         }
         // epilogue: T = Ex(nx) Ey(ny); accumulate Re(T U), nx Im(T U), ny Im(T U), Im(T U')
+        const int rowBase = p.signedLo + rowTile*G_ROW_TILE;
         #pragma unroll
         for (int i = 0; i < G_ROWS_PER_WARP; i++) {
             const int rloc = warp*G_ROWS_PER_WARP + i;
-            if (r0 + tile*G_ROW_TILE + rloc >= r1) continue;
+            if (rowBase + rloc >= p.signedHi) continue;
             const int2 info = infoS[buf*G_ROW_TILE + rloc];
             if (info.x != curNx) {
                 curNx = info.x;
@@ -433,27 +466,7 @@ __global__ void __launch_bounds__(G_THREADS, 2) gatherKernel(GParams p, long lon
         }
         __syncthreads();
     }
-    // cross-warp reduction through shared memory (aliases Z4s), then one fixed-point atomic per output
-    float4* red = reinterpret_cast<float4*>(smem);
-    #pragma unroll
-    for (int a = 0; a < APT; a++) red[warp*BA + lane + 32*a] = make_float4(oD[a], oX[a], oY[a], oZ[a]);
-    __syncthreads();
-    if (tid < BA) {
-        float4 s = red[tid];
-        #pragma unroll
-        for (int w = 1; w < G_WARPS; w++) {
-            const float4 v = red[w*BA + tid];
-            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-        }
-        const int atom = atom0 + tid;
-        if (atom < p.N) {
-            const double q = (double) p.qf[atom];
-            atomicAddFixed(dedqFixed + atom, (double) s.x);
-            atomicAddFixed(forceFixed + atom, q*(double) p.fx*(double) s.y);
-            atomicAddFixed(forceFixed + p.Npad + atom, q*(double) p.fy*(double) s.z);
-            atomicAddFixed(forceFixed + 2*(size_t) p.Npad + atom, q*(double) p.fz*(double) s.w);
-        }
-    }
+    flush();
 }
 
 size_t gatherSmem(int Kx, int Ky, int Kz, int BA, size_t* offEy, size_t* offCoef, size_t* offInfo) {
@@ -477,9 +490,18 @@ size_t gatherSmem(int Kx, int Ky, int Kz, int BA, size_t* offEy, size_t* offCoef
 void planKSpace(State& st) {
     KSpacePlan& ks = st.ks;
     const int Kx = ks.K[0], Ky = ks.K[1], Kz = ks.K[2];
-    ks.sTM = 2; ks.sTN = 4;
-    ks.sNC = (Kz + ks.sTN - 1)/ks.sTN;
-    ks.kzPad = ks.sNC*ks.sTN;
+    // S kernel: TM = 2 rows per lane, TN in {6,7,8} columns per warp; pick the TN with the least column
+    // padding (ties -> larger TN), at most S_MAX_WARPS column groups per CTA
+    ks.sTM = 2;
+    int bestPad = 1 << 30;
+    for (int tn = 6; tn <= 8; tn++) {
+        const int g = (Kz + tn - 1)/tn;
+        const int pad = g*tn - Kz;
+        if (pad <= bestPad) { bestPad = pad; ks.sTN = tn; ks.sNC = g; }
+    }
+    if (ks.sNC > S_MAX_WARPS) throw std::runtime_error("kmax along z too large for the structure-factor kernel (|nz| <= 64)");
+    const int TNP = (ks.sTN + 1) & ~1;
+    ks.kzPad = ks.sNC*TNP;
     const int zOff = (Kx + Ky + 1) & ~1;
     ks.rowPitch = zOff + ks.kzPad;
     ks.numRows = Kx*Ky;
@@ -487,26 +509,18 @@ void planKSpace(State& st) {
     ks.rowLo = (int) ((int64_t) ks.numRows*st.shardRank/st.shardCount);
     ks.rowHi = (int) ((int64_t) ks.numRows*(st.shardRank + 1)/st.shardCount);
     const int rowsHere = ks.rowHi - ks.rowLo;
-    // block size / tile: maximise useful-FMA fraction (row padding x idle threads)
-    double best = -1.0;
-    const int candidates[] = {256, 288, 224, 192, 160, 128};
-    for (int threads : candidates) {
-        if (ks.sNC > threads) continue;
-        int TR = threads/ks.sNC;
-        int BM = TR*ks.sTM;
-        if (BM > 32*S_MAX_ROW_ITERS) { TR = 32*S_MAX_ROW_ITERS/ks.sTM; BM = TR*ks.sTM; }
-        int tiles = (std::max(rowsHere, 1) + BM - 1)/BM;
-        double eff = (double) std::max(rowsHere, 1)/(tiles*BM)*((double) TR*ks.sNC/threads);
-        if (eff > best + 1e-9) { best = eff; ks.sThreads = threads; ks.sTR = TR; ks.sBM = BM; ks.sRowTiles = tiles; }
-    }
+    ks.sThreads = 32*ks.sNC;
+    ks.sBM = S_BM;
+    ks.sRowTiles = (std::max(rowsHere, 1) + S_BM - 1)/S_BM;
     ks.sStages = 2;
     const size_t stageBytes = (size_t) S_ATOMS_PER_STAGE*ks.rowPitch*sizeof(float2);
-    const size_t asBytes = (size_t) S_ATOMS_PER_STAGE*ks.sBM*sizeof(float4);
+    const size_t asBytes = (size_t) S_ATOMS_PER_STAGE*S_BM*sizeof(float4);
     ks.sSmem = 128 + ks.sStages*stageBytes + asBytes;
-    // atom splits: fill ~2 CTAs per SM
+    // atom splits: fill the resident CTA slots (shared memory allows 2-3 CTAs per SM)
     int numSM = 148;
     cudaDeviceGetAttribute(&numSM, cudaDevAttrMultiProcessorCount, st.device);
-    const int slots = 2*numSM;
+    const int ctasPerSM = std::max(1, std::min(4, (int) ((size_t) 220*1024/(ks.sSmem + 1024))));
+    const int slots = ctasPerSM*numSM;
     int splits = std::max(1, slots/std::max(1, ks.sRowTiles));
     const int maxSplits = std::max(1, st.Npad/(4*S_ATOMS_PER_STAGE));       // >= 4 stages per CTA
     splits = std::min(splits, maxSplits);
@@ -550,15 +564,12 @@ void planKSpace(State& st) {
     size_t o1, o2, o3;
     ks.gSmem = gatherSmem(Kx, Ky, Kz, ks.gAtoms, &o1, &o2, &o3);
     const int signedHere = ks.signedHi - ks.signedLo;
-    const int atomTiles = st.Npad/ks.gAtoms;
-    int rowSplits = std::max(1, (2*numSM + atomTiles - 1)/atomTiles);
-    rowSplits = std::min(rowSplits, std::max(1, signedHere/(4*G_ROW_TILE)));
-    int rps = (std::max(signedHere, 1) + rowSplits - 1)/rowSplits;
-    rps = (rps + G_ROW_TILE - 1)/G_ROW_TILE*G_ROW_TILE;
-    ks.gRowSplits = (std::max(signedHere, 1) + rps - 1)/rps;
-    ks.gRowsPerTile = rps;      // rows per split
+    ks.gRowsPerTile = (std::max(signedHere, 1) + G_ROW_TILE - 1)/G_ROW_TILE;      // row tiles per atom tile
+    ks.gRowSplits = numSM;                                                        // persistent grid size
 
-    CFX_CUDA(cudaFuncSetAttribute(structureFactorKernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ks.sSmem));
+    CFX_CUDA(cudaFuncSetAttribute(structureFactorKernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ks.sSmem));
+    CFX_CUDA(cudaFuncSetAttribute(structureFactorKernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ks.sSmem));
+    CFX_CUDA(cudaFuncSetAttribute(structureFactorKernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ks.sSmem));
     CFX_CUDA(cudaFuncSetAttribute(gatherKernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ks.gSmem));
 }
 
@@ -567,7 +578,8 @@ void launchKSpace(State& st, const double* dPos, bool forces, bool energy, long 
     if (!forces && !energy) return;
     const int Kx = ks.K[0], Ky = ks.K[1], Kz = ks.K[2];
     const int zOff = ks.rowPitch - ks.kzPad;
-    TableParams tp{st.N, st.Npad, Kx, Ky, Kz, ks.kzPad, zOff, ks.rowPitch, 1.0/st.box.L[0], 1.0/st.box.L[1], 1.0/st.box.L[2]};
+    const int TNP = (ks.sTN + 1) & ~1;
+    TableParams tp{st.N, st.Npad, Kx, Ky, Kz, ks.kzPad, zOff, ks.rowPitch, ks.sTN, TNP, 1.0/st.box.L[0], 1.0/st.box.L[1], 1.0/st.box.L[2]};
     phaseTableKernel<<<(3*st.Npad + 127)/128, 128, 0, s>>>(tp, dPos, st.qf, st.rowS, st.colX, st.colY, st.colZ4);
     CFX_LAUNCH_CHECK(); st.launches++;
     mark(st, "phase_tables", s);
@@ -576,17 +588,20 @@ void launchKSpace(State& st, const double* dPos, bool forces, bool energy, long 
     SParams sp;
     sp.rowS = st.rowS; sp.part = st.sPart;
     sp.rowPitch = ks.rowPitch; sp.Kx = Kx; sp.Ky = Ky; sp.zOff = zOff; sp.kzPad = ks.kzPad;
-    sp.NC = ks.sNC; sp.TR = ks.sTR; sp.BM = ks.sBM; sp.asPitch = ks.sBM; sp.stages = ks.sStages;
+    sp.stages = ks.sStages;
     sp.rowLo = ks.rowLo; sp.rowHi = ks.rowHi; sp.numRows = ks.numRows;
     sp.atomsPerSplit = ks.sAtomsPerSplit; sp.Npad = st.Npad;
-    structureFactorKernel<2, 4><<<dim3(ks.sRowTiles, ks.sSplits), ks.sThreads, ks.sSmem, s>>>(sp);
+    const dim3 sGrid(ks.sRowTiles, ks.sSplits);
+    if (ks.sTN == 6)      structureFactorKernel<6><<<sGrid, ks.sThreads, ks.sSmem, s>>>(sp);
+    else if (ks.sTN == 7) structureFactorKernel<7><<<sGrid, ks.sThreads, ks.sSmem, s>>>(sp);
+    else                  structureFactorKernel<8><<<sGrid, ks.sThreads, ks.sSmem, s>>>(sp);
     CFX_LAUNCH_CHECK(); st.launches++;
     mark(st, "structure_factor", s);
 
     CoefParams cp;
     cp.part = st.sPart; cp.coef = st.gCoef; cp.signedStart = st.ks_signedStart;
     cp.Kx = Kx; cp.Ky = Ky; cp.Kz = Kz; cp.kzPad = ks.kzPad; cp.numRows = ks.numRows; cp.splits = ks.sSplits;
-    cp.rowLo = ks.rowLo; cp.rowHi = ks.rowHi;
+    cp.rowLo = ks.rowLo; cp.rowHi = ks.rowHi; cp.TN = ks.sTN; cp.TNP = TNP;
     cp.gx = 2*M_PI/st.box.L[0]; cp.gy = 2*M_PI/st.box.L[1]; cp.gz = 2*M_PI/st.box.L[2];
     cp.C = 4.0/st.box.L[0]/st.box.L[1]/st.box.L[2]*M_PI*CFX_ONE_4PI_EPS0;
     cp.invFourAlpha2 = 0.25/(st.alpha*st.alpha);
@@ -600,10 +615,12 @@ void launchKSpace(State& st, const double* dPos, bool forces, bool energy, long 
         GParams gp;
         gp.coef = st.gCoef; gp.rowInfo = st.gRowInfo; gp.colX = st.colX; gp.colY = st.colY; gp.colZ4 = st.colZ4; gp.qf = st.qf;
         gp.Kx = Kx; gp.Ky = Ky; gp.Kz = Kz; gp.N = st.N; gp.Npad = st.Npad;
-        gp.signedLo = ks.signedLo; gp.signedHi = ks.signedHi; gp.rowsPerSplit = ks.gRowsPerTile;
+        gp.signedLo = ks.signedLo; gp.signedHi = ks.signedHi; gp.numRowTiles = ks.gRowsPerTile; gp.numAtomTiles = st.Npad/ks.gAtoms;
         gp.fx = (float) cp.gx; gp.fy = (float) cp.gy; gp.fz = (float) cp.gz;
         gatherSmem(Kx, Ky, Kz, ks.gAtoms, &gp.offEy, &gp.offCoef, &gp.offInfo);
-        gatherKernel<4><<<dim3(st.Npad/ks.gAtoms, ks.gRowSplits), G_THREADS, ks.gSmem, s>>>(gp, dForce, dDedq);
+        const long long units = (long long) gp.numAtomTiles*gp.numRowTiles;
+        const int gGrid = (int) std::min<long long>(ks.gRowSplits, units);
+        gatherKernel<4><<<gGrid, G_THREADS, ks.gSmem, s>>>(gp, dForce, dDedq);
         CFX_LAUNCH_CHECK(); st.launches++;
         mark(st, "kspace_gather", s);
     }
