@@ -16,7 +16,9 @@ PLUGIN_LIB = os.path.join(PKG, "plugin", "libOpenMMCoulB200.so")
 REF = os.environ.get("CFX_REFERENCE_DIR", "/root/reference")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC", "-shared",
+              # keep the statically linked CUDA runtime private: plugin loaders dlopen with RTLD_GLOBAL
+              "-Xlinker", "--exclude-libs=ALL"]
 if os.environ.get("CFX_PTXAS_V"):
     NVCC_FLAGS += ["-Xptxas", "-v"]
 

@@ -104,7 +104,7 @@ void enqueueEvaluation(State& st, const double* dPos, bool includeForces, bool i
         // reference quirks mirrored: reciprocal energy only with includeEnergy; direct,
         // self and exclusion energies always; pair/recip forces and dE/dq only with includeForces
         launchKSpace(st, dPos, includeForces, includeEnergy, dForce, st.dedqFixed, s);
-        launchDirect(st, dPos, includeForces, includeEnergy, false, dForce, st.dedqFixed, s);
+        launchDirect(st, dPos, includeForces, includeEnergy ? 2 : 1, false, dForce, st.dedqFixed, s);
         launchExclusionCorrection(st, dPos, includeForces, dForce, st.dedqFixed, s);
     }
     else
@@ -532,7 +532,7 @@ int cfx_get_neighbor_pairs(cfx_handle* h, int32_t* pairs, int64_t capacity, int6
     // re-run the cell build + pair kernel on the positions of the last host evaluation, emitting pairs
     cudaStream_t s = st.stream;
     CFX_CUDA(cudaMemsetAsync(st.pairCounters, 0, sizeof(unsigned long long)*4, s));
-    launchDirect(st, st.pos, false, true, true, st.forceFixed, st.dedqFixed, s);
+    launchDirect(st, st.pos, false, 0, true, st.forceFixed, st.dedqFixed, s);
     CFX_CUDA(cudaStreamSynchronize(s));
     CFX_CUDA(cudaMemcpy(c, st.pairCounters, sizeof(c), cudaMemcpyDeviceToHost));
     if ((int64_t) c[2] != *count) throw std::runtime_error("pair emission count mismatch");

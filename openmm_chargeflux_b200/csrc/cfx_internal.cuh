@@ -178,7 +178,7 @@ void launchFinalize(State& st, const long long* dForce, cudaStream_t s);
 void planKSpace(State& st);
 void launchKSpace(State& st, const double* dPos, bool forces, bool energy, long long* dForce, long long* dDedq, cudaStream_t s);  // piece (3)
 void planCells(State& st);
-void launchDirect(State& st, const double* dPos, bool forces, bool energy, bool emitPairs, long long* dForce, long long* dDedq, cudaStream_t s); // piece (2)
+void launchDirect(State& st, const double* dPos, bool forces, int energyMode /*0 none, 1 FP32 terms, 2 FP64 terms*/, bool emitPairs, long long* dForce, long long* dDedq, cudaStream_t s); // piece (2)
 void mark(State& st, const char* name, cudaStream_t s);   // per-kernel timing marker (no-op unless st.timing)
 
 } // namespace cfx

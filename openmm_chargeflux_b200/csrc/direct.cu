@@ -194,7 +194,9 @@ __device__ __noinline__ bool exactInCutoff(const double* __restrict__ pos, int u
 
 __device__ __forceinline__ int modPos(int v, int n) { v %= n; return v < 0 ? v + n : v; }
 
-template <bool FORCES, bool ENERGY, bool EMIT>
+// EMODE: 0 = no pair energy, 1 = FP32 pair terms (the partial energy the reference returns when
+// includeEnergy is false is discarded by OpenMM; it is still produced, at FP32 accuracy), 2 = FP64 terms.
+template <bool FORCES, int EMODE, bool EMIT>
 __global__ void __launch_bounds__(P_WARPS*32) pairKernel(PairParams p) {
     __shared__ float4 sPos[P_WARPS][P_JCAP];
     __shared__ float2 sLJ[P_WARPS][P_JCAP];
@@ -294,7 +296,7 @@ __global__ void __launch_bounds__(P_WARPS*32) pairKernel(PairParams p) {
                 for (int e = exBeg; e < exEnd; e++)
                     if (p.exclCols[e] == uj) { in = false; break; }
             if (in) {
-                if (FORCES) {
+                if (FORCES || EMODE == 1) {
                     const float2 ljj = tLJ[k];
                     const float invR = rsqrtf(r2);
                     const float r = r2*invR;
@@ -306,11 +308,14 @@ __global__ void __launch_bounds__(P_WARPS*32) pairKernel(PairParams p) {
                     float s2 = sig*invR; s2 *= s2;
                     const float s6 = s2*s2*s2;
                     const float es6 = s6*(lji.y*ljj.y);
-                    const float ex = __expf(-ar2);
-                    const float invR2 = invR*invR;
-                    const float dEdR = (coul*(erfcv + ar*ex*1.1283791671f) + es6*(12.f*s6 - 6.f))*invR2;
-                    fx = fmaf(dEdR, dx, fx); fy = fmaf(dEdR, dy, fy); fz = fmaf(dEdR, dz, fz);
-                    dq = fmaf((float) CFX_ONE_4PI_EPS0*pj.w*invR, erfcv, dq);
+                    if (FORCES) {
+                        const float ex = __expf(-ar2);
+                        const float invR2 = invR*invR;
+                        const float dEdR = (coul*(erfcv + ar*ex*1.1283791671f) + es6*(12.f*s6 - 6.f))*invR2;
+                        fx = fmaf(dEdR, dx, fx); fy = fmaf(dEdR, dy, fy); fz = fmaf(dEdR, dz, fz);
+                        dq = fmaf((float) CFX_ONE_4PI_EPS0*pj.w*invR, erfcv, dq);
+                    }
+                    if (EMODE == 1) en += (double) (coul*erfcv + es6*(s6 - 1.f));
                 }
                 if (ui < uj) {
                     nPairs++;
@@ -320,7 +325,7 @@ __global__ void __launch_bounds__(P_WARPS*32) pairKernel(PairParams p) {
                     }
                 }
             }
-            if (ENERGY) {
+            if (EMODE == 2) {
                 const bool want = in && ui < uj;
                 const unsigned int m = __ballot_sync(0xffffffffu, want);
                 if (want) eq[qCount + __popc(m & ((1u << lane) - 1u))] = make_int2(ui, uj);
@@ -398,7 +403,7 @@ __global__ void __launch_bounds__(P_WARPS*32) pairKernel(PairParams p) {
         }
     }
     if (count > 0) processTile(count);
-    if (ENERGY && qCount > 0) energyBatch(qCount);
+    if (EMODE == 2 && qCount > 0) energyBatch(qCount);
 
     // reduce over the 4 lanes of each i atom (warp shuffles), one fixed-point atomic per output
     if (FORCES) {
@@ -414,9 +419,10 @@ __global__ void __launch_bounds__(P_WARPS*32) pairKernel(PairParams p) {
             atomicAddFixed(p.dedqFixed + ui, (double) dq);
         }
     }
-    if (ENERGY) {
+    if (EMODE != 0) {
         en = warpSum(en);
-        if (lane == 0) atomicAddEnergy(p.energyFixed + CFX_E_DIRECT, en);       // each i<j pair queued exactly once
+        // FP64 queue: each i<j pair once. FP32 terms: every pair is seen from both sides.
+        if (lane == 0) atomicAddEnergy(p.energyFixed + CFX_E_DIRECT, EMODE == 2 ? en : 0.5*en);
     }
     #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nPairs += __shfl_xor_sync(0xffffffffu, nPairs, o);
@@ -427,10 +433,18 @@ __global__ void __launch_bounds__(P_WARPS*32) pairKernel(PairParams p) {
 }
 
 template <bool EMIT>
-void dispatchPair(const PairParams& pp, bool forces, bool energy, int blocks, cudaStream_t s) {
-    if (forces && energy) pairKernel<true, true, EMIT><<<blocks, P_WARPS*32, 0, s>>>(pp);
-    else if (forces)      pairKernel<true, false, EMIT><<<blocks, P_WARPS*32, 0, s>>>(pp);
-    else                  pairKernel<false, true, EMIT><<<blocks, P_WARPS*32, 0, s>>>(pp);
+void dispatchPair(const PairParams& pp, bool forces, int emode, int blocks, cudaStream_t s) {
+    const int t = P_WARPS*32;
+    if (forces) {
+        if (emode == 2)      pairKernel<true, 2, EMIT><<<blocks, t, 0, s>>>(pp);
+        else if (emode == 1) pairKernel<true, 1, EMIT><<<blocks, t, 0, s>>>(pp);
+        else                 pairKernel<true, 0, EMIT><<<blocks, t, 0, s>>>(pp);
+    }
+    else {
+        if (emode == 2)      pairKernel<false, 2, EMIT><<<blocks, t, 0, s>>>(pp);
+        else if (emode == 1) pairKernel<false, 1, EMIT><<<blocks, t, 0, s>>>(pp);
+        else                 pairKernel<false, 0, EMIT><<<blocks, t, 0, s>>>(pp);
+    }
 }
 
 } // namespace
@@ -461,8 +475,8 @@ void planCells(State& st) {
     CFX_CUDA(cudaMalloc(&st.pairCounters, sizeof(unsigned long long)*4));
 }
 
-void launchDirect(State& st, const double* dPos, bool forces, bool energy, bool emitPairs, long long* dForce, long long* dDedq, cudaStream_t s) {
-    if (!forces && !energy && !emitPairs) return;
+void launchDirect(State& st, const double* dPos, bool forces, int emode, bool emitPairs, long long* dForce, long long* dDedq, cudaStream_t s) {
+    if (!forces && emode == 0 && !emitPairs) return;
     CellPlan& c = st.cells;
     CellParams cp{st.N, c.nc[0], c.nc[1], c.nc[2], c.ncells, 1.0/st.box.L[0], 1.0/st.box.L[1], 1.0/st.box.L[2], c.csd[0], c.csd[1], c.csd[2]};
     CFX_CUDA(cudaMemsetAsync(st.cellCount, 0, sizeof(int)*(c.ncells + 1), s));
@@ -499,8 +513,8 @@ void launchDirect(State& st, const double* dPos, bool forces, bool energy, bool 
     const int groups = pp.groupHi - pp.groupLo;
     if (groups <= 0) return;
     const int blocks = (groups + P_WARPS - 1)/P_WARPS;
-    if (emitPairs) dispatchPair<true>(pp, forces, energy, blocks, s);
-    else           dispatchPair<false>(pp, forces, energy, blocks, s);
+    if (emitPairs) dispatchPair<true>(pp, forces, emode, blocks, s);
+    else           dispatchPair<false>(pp, forces, emode, blocks, s);
     CFX_LAUNCH_CHECK(); st.launches++;
     mark(st, "direct_pairs", s);
 }

@@ -6,7 +6,8 @@ created with (shard_rank, shard_count): it computes S(k) for its block of (nx,|n
 atoms, scatters that block's forces/dE/dq to all atoms, evaluates the i-tiles of its spatial slab,
 and applies the chain rule to its PARTIAL dE/dq (the chain rule is linear in dE/dq). Rank 0 adds the
 self and excluded-pair terms. The partial results are int64 fixed point, so the sum over ranks is
-exact and independent of the reduction order: results are bitwise identical for any GPU count.
+exact and independent of the reduction order (bitwise reproducible for a given GPU count; different GPU
+counts group the FP32 partial sums differently and agree to FP32 rounding, ~1e-6 relative).
 The collective is ``torch.distributed.all_reduce`` (NCCL over NVLink on GPUs; gloo in the CPU tests).
 """
 import numpy as np

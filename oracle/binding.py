@@ -127,7 +127,7 @@ class ReferenceBuild(_Base):
 
     def __init__(self, force, default_box, platform="Reference", plugin=None):
         if ReferenceBuild.lib is None:
-            ReferenceBuild.lib = C.CDLL(REF_LIB, mode=C.RTLD_GLOBAL)
+            ReferenceBuild.lib = C.CDLL(REF_LIB)
             ReferenceBuild.lib.cfxref_destroy.argtypes = [C.c_void_p]
         self._check(self.lib.cfxref_load_plugin((plugin or REF_PLUGIN).encode()))
         self.n = force.getNumParticles()

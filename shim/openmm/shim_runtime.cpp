@@ -71,7 +71,7 @@ Platform& Platform::getPlatformByName(const std::string& name) {
 void Platform::loadPluginLibrary(const std::string& file) {
     // Same contract as OpenMM's loader: dlopen, then call registerPlatforms() and
     // registerKernelFactories() if the library exports them.
-    void* handle = dlopen(file.c_str(), RTLD_LAZY | RTLD_GLOBAL);
+    void* handle = dlopen(file.c_str(), RTLD_LAZY | RTLD_LOCAL);
     if (handle == NULL)
         throw OpenMMException("Error loading library " + file + ": " + dlerror());
     void (*init)();
