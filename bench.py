@@ -162,6 +162,23 @@ def cpu_baseline(pos, box, force, budget_s=25.0):
             "seconds_per_eval_extrapolated": t_full}
 
 
+def existing_cuda_baseline(workload, our_ms):
+    """The reference's own platforms/cuda kernels (prebuilt cubins in oracle/_ref, see oracle/refcuda/) timed here."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "oracle", "refcuda"))
+        import run_baseline
+        if not run_baseline.available(workload):
+            return {"unavailable": "oracle/_ref/refcuda_%s_*.cubin not built (needs /root/reference at build time)" % workload}
+        r = run_baseline.run(workload, iters=3)
+        return {"ms_per_eval_lower_bound": r["ms_per_eval_lower_bound"], "value_upper_bound": r["evals_per_s_upper_bound"], "unit": UNIT,
+                "kernels_ms": {k: round(v, 4) for k, v in r["kernels_ms"].items()},
+                "speedup_vs_lower_bound": r["ms_per_eval_lower_bound"] / our_ms,
+                "note": "8 of the existing platform's 9 launches, reference launch geometry, mixed precision; computeNonbonded needs "
+                        "OpenMM's tile list and is not launched, so this is a lower bound on its time"}
+    except Exception as e:                                   # a baseline must never break the bench line
+        return {"unavailable": "%s: %s" % (type(e).__name__, e)}
+
+
 def run_reference_arm(args, pos, box, force, workload):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -323,6 +340,8 @@ def run_ours(args, pos, box, force, workload):
         line["config"]["pairs_in_cutoff"] = int(pairs)
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(pos, box, force)
+        # second reported baseline of north_star: the plugin's EXISTING CUDA kernels on this GPU
+        line["existing_cuda_baseline"] = existing_cuda_baseline(args.workload, ms_per_step)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
