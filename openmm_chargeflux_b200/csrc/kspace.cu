@@ -126,18 +126,19 @@ struct SParams {
 
 // One CTA = 64 rows x all |nz| columns over one split of the atoms. Warp g owns column group g (TN
 // columns, padded to TNP float2 so the group is 16-byte aligned) for all 64 rows; lane owns rows
-// lane and lane+32. Per atom a warp issues 2 lane-distinct LDS.128 (row operand, conflict-free, 4
-// wavefronts each) and TNP/2 warp-UNIFORM LDS.128 (column operand, 1 wavefront each) for 16*TN FFMA.
-template <int TN>
-__global__ void __launch_bounds__(32*S_MAX_WARPS, 1) structureFactorKernel(SParams p) {
+// lane and lane+32. Per atom a warp reads the row phases q*Ex(nx), Ey(|ny|) of its two rows (4 LDS.64)
+// and forms the row operand a = (xr*yc, xr*ys, xi*yc, xi*ys) in registers (8 FMUL), reads its TN column
+// phases with warp-UNIFORM LDS.128 (1 wavefront each) and issues 16*TN FFMA. The atom rows arrive by
+// bulk TMA into a ring of stages; there is one CTA barrier per 32 atoms and no staging of the operand.
+template <int TN, int G>
+__global__ void __launch_bounds__(32*G, (G <= 4) ? 3 : 1) structureFactorKernel(SParams p) {
     constexpr int TNP = (TN + 1) & ~1;
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem);
     float2* raw = reinterpret_cast<float2*>(smem + 128);
     const int stageElems = S_ATOMS_PER_STAGE*p.rowPitch;
-    float4* As = reinterpret_cast<float4*>(smem + 128 + (size_t) p.stages*stageElems*sizeof(float2));   // [32][S_BM]
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int rowBase = p.rowLo + blockIdx.x*S_BM;
     const int rowEnd = min(rowBase + S_BM, p.rowHi);
     const int atomBegin = blockIdx.y*p.atomsPerSplit;
@@ -145,17 +146,15 @@ __global__ void __launch_bounds__(32*S_MAX_WARPS, 1) structureFactorKernel(SPara
     const int numStages = (atomEnd - atomBegin)/S_ATOMS_PER_STAGE;
     const uint32_t stageBytes = (uint32_t) (stageElems*sizeof(float2));
 
-    // rows this lane produces and consumes (fixed across stages)
+    // phase slots of my two rows inside an atom row (rows past the end compute on row 0's slots and
+    // are never stored)
     int offX[2], offY[2];
     #pragma unroll
     for (int it = 0; it < 2; it++) {
-        const int row = rowBase + lane + 32*it;
-        if (row < rowEnd) {
-            const int nx = row/p.Ky;
-            offX[it] = nx;
-            offY[it] = p.Kx + (row - nx*p.Ky);
-        }
-        else { offX[it] = -1; offY[it] = 0; }
+        const int row = min(rowBase + lane + 32*it, p.numRows - 1);
+        const int nx = row/p.Ky;
+        offX[it] = nx;
+        offY[it] = p.Kx + (row - nx*p.Ky);
     }
 
     float acc[2][TN][8];
@@ -181,46 +180,34 @@ __global__ void __launch_bounds__(32*S_MAX_WARPS, 1) structureFactorKernel(SPara
         const int slot = st % p.stages;
         mbarWait(mbar + slot, (uint32_t) ((st/p.stages) & 1));
         const float2* rw = raw + (size_t) slot*stageElems;
-        // row operand a = (xr*yc, xr*ys, xi*yc, xi*ys) with x = q*Ex(nx), y = Ey(|ny|)
-        for (int j = warp; j < S_ATOMS_PER_STAGE; j += nwarps) {
-            const float2* r = rw + j*p.rowPitch;
+        const float2* x0p = rw + offX[0]; const float2* y0p = rw + offY[0];
+        const float2* x1p = rw + offX[1]; const float2* y1p = rw + offY[1];
+        const float4* bPtr = reinterpret_cast<const float4*>(rw + p.zOff + warp*TNP);
+        const int bPitch4 = p.rowPitch/2;
+        #pragma unroll 2
+        for (int j = 0; j < S_ATOMS_PER_STAGE; j++) {
+            const float2 x0 = x0p[j*p.rowPitch], y0 = y0p[j*p.rowPitch];
+            const float2 x1 = x1p[j*p.rowPitch], y1 = y1p[j*p.rowPitch];
+            float4 b[TNP/2];
             #pragma unroll
-            for (int it = 0; it < 2; it++) {
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (offX[it] >= 0) {
-                    const float2 x = r[offX[it]], y = r[offY[it]];
-                    v = make_float4(x.x*y.x, x.x*y.y, x.y*y.x, x.y*y.y);
-                }
-                As[j*S_BM + lane + 32*it] = v;
+            for (int c = 0; c < TNP/2; c++) b[c] = bPtr[j*bPitch4 + c];
+            const float4 a0 = make_float4(x0.x*y0.x, x0.x*y0.y, x0.y*y0.x, x0.y*y0.y);
+            const float4 a1 = make_float4(x1.x*y1.x, x1.x*y1.y, x1.y*y1.x, x1.y*y1.y);
+            #pragma unroll
+            for (int c = 0; c < TN; c++) {
+                const float zc = (c & 1) ? b[c/2].z : b[c/2].x;
+                const float zs = (c & 1) ? b[c/2].w : b[c/2].y;
+                acc[0][c][0] = fmaf(a0.x, zc, acc[0][c][0]);  acc[0][c][1] = fmaf(a0.x, zs, acc[0][c][1]);
+                acc[0][c][2] = fmaf(a0.y, zc, acc[0][c][2]);  acc[0][c][3] = fmaf(a0.y, zs, acc[0][c][3]);
+                acc[0][c][4] = fmaf(a0.z, zc, acc[0][c][4]);  acc[0][c][5] = fmaf(a0.z, zs, acc[0][c][5]);
+                acc[0][c][6] = fmaf(a0.w, zc, acc[0][c][6]);  acc[0][c][7] = fmaf(a0.w, zs, acc[0][c][7]);
+                acc[1][c][0] = fmaf(a1.x, zc, acc[1][c][0]);  acc[1][c][1] = fmaf(a1.x, zs, acc[1][c][1]);
+                acc[1][c][2] = fmaf(a1.y, zc, acc[1][c][2]);  acc[1][c][3] = fmaf(a1.y, zs, acc[1][c][3]);
+                acc[1][c][4] = fmaf(a1.z, zc, acc[1][c][4]);  acc[1][c][5] = fmaf(a1.z, zs, acc[1][c][5]);
+                acc[1][c][6] = fmaf(a1.w, zc, acc[1][c][6]);  acc[1][c][7] = fmaf(a1.w, zs, acc[1][c][7]);
             }
         }
-        __syncthreads();
-        {
-            const float4* aPtr = As + lane;
-            const float4* bPtr = reinterpret_cast<const float4*>(rw + p.zOff + warp*TNP);
-            const int bPitch4 = p.rowPitch/2;
-            #pragma unroll 2
-            for (int j = 0; j < S_ATOMS_PER_STAGE; j++) {
-                const float4 a0 = aPtr[j*S_BM], a1 = aPtr[j*S_BM + 32];
-                float4 b[TNP/2];
-                #pragma unroll
-                for (int c = 0; c < TNP/2; c++) b[c] = bPtr[j*bPitch4 + c];
-                #pragma unroll
-                for (int c = 0; c < TN; c++) {
-                    const float zc = (c & 1) ? b[c/2].z : b[c/2].x;
-                    const float zs = (c & 1) ? b[c/2].w : b[c/2].y;
-                    acc[0][c][0] = fmaf(a0.x, zc, acc[0][c][0]);  acc[0][c][1] = fmaf(a0.x, zs, acc[0][c][1]);
-                    acc[0][c][2] = fmaf(a0.y, zc, acc[0][c][2]);  acc[0][c][3] = fmaf(a0.y, zs, acc[0][c][3]);
-                    acc[0][c][4] = fmaf(a0.z, zc, acc[0][c][4]);  acc[0][c][5] = fmaf(a0.z, zs, acc[0][c][5]);
-                    acc[0][c][6] = fmaf(a0.w, zc, acc[0][c][6]);  acc[0][c][7] = fmaf(a0.w, zs, acc[0][c][7]);
-                    acc[1][c][0] = fmaf(a1.x, zc, acc[1][c][0]);  acc[1][c][1] = fmaf(a1.x, zs, acc[1][c][1]);
-                    acc[1][c][2] = fmaf(a1.y, zc, acc[1][c][2]);  acc[1][c][3] = fmaf(a1.y, zs, acc[1][c][3]);
-                    acc[1][c][4] = fmaf(a1.z, zc, acc[1][c][4]);  acc[1][c][5] = fmaf(a1.z, zs, acc[1][c][5]);
-                    acc[1][c][6] = fmaf(a1.w, zc, acc[1][c][6]);  acc[1][c][7] = fmaf(a1.w, zs, acc[1][c][7]);
-                }
-            }
-        }
-        __syncthreads();
+        __syncthreads();                                     // every warp is done with this slot
         if (tid == 0 && st + p.stages < numStages) {
             mbarExpectTx(mbar + slot, stageBytes);
             bulkLoad(raw + (size_t) slot*stageElems, p.rowS + (size_t) (atomBegin + (st + p.stages)*S_ATOMS_PER_STAGE)*p.rowPitch,
@@ -512,10 +499,9 @@ void planKSpace(State& st) {
     ks.sThreads = 32*ks.sNC;
     ks.sBM = S_BM;
     ks.sRowTiles = (std::max(rowsHere, 1) + S_BM - 1)/S_BM;
-    ks.sStages = 2;
+    ks.sStages = 3;
     const size_t stageBytes = (size_t) S_ATOMS_PER_STAGE*ks.rowPitch*sizeof(float2);
-    const size_t asBytes = (size_t) S_ATOMS_PER_STAGE*S_BM*sizeof(float4);
-    ks.sSmem = 128 + ks.sStages*stageBytes + asBytes;
+    ks.sSmem = 128 + ks.sStages*stageBytes;
     // atom splits: fill the resident CTA slots (shared memory allows 2-3 CTAs per SM)
     int numSM = 148;
     cudaDeviceGetAttribute(&numSM, cudaDevAttrMultiProcessorCount, st.device);
@@ -567,9 +553,12 @@ void planKSpace(State& st) {
     ks.gRowsPerTile = (std::max(signedHere, 1) + G_ROW_TILE - 1)/G_ROW_TILE;      // row tiles per atom tile
     ks.gRowSplits = numSM;                                                        // persistent grid size
 
-    CFX_CUDA(cudaFuncSetAttribute(structureFactorKernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ks.sSmem));
-    CFX_CUDA(cudaFuncSetAttribute(structureFactorKernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ks.sSmem));
-    CFX_CUDA(cudaFuncSetAttribute(structureFactorKernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ks.sSmem));
+    CFX_CUDA(cudaFuncSetAttribute(structureFactorKernel<6, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ks.sSmem));
+    CFX_CUDA(cudaFuncSetAttribute(structureFactorKernel<7, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ks.sSmem));
+    CFX_CUDA(cudaFuncSetAttribute(structureFactorKernel<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ks.sSmem));
+    CFX_CUDA(cudaFuncSetAttribute(structureFactorKernel<6, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ks.sSmem));
+    CFX_CUDA(cudaFuncSetAttribute(structureFactorKernel<7, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ks.sSmem));
+    CFX_CUDA(cudaFuncSetAttribute(structureFactorKernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ks.sSmem));
     CFX_CUDA(cudaFuncSetAttribute(gatherKernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ks.gSmem));
 }
 
@@ -592,9 +581,16 @@ void launchKSpace(State& st, const double* dPos, bool forces, bool energy, long 
     sp.rowLo = ks.rowLo; sp.rowHi = ks.rowHi; sp.numRows = ks.numRows;
     sp.atomsPerSplit = ks.sAtomsPerSplit; sp.Npad = st.Npad;
     const dim3 sGrid(ks.sRowTiles, ks.sSplits);
-    if (ks.sTN == 6)      structureFactorKernel<6><<<sGrid, ks.sThreads, ks.sSmem, s>>>(sp);
-    else if (ks.sTN == 7) structureFactorKernel<7><<<sGrid, ks.sThreads, ks.sSmem, s>>>(sp);
-    else                  structureFactorKernel<8><<<sGrid, ks.sThreads, ks.sSmem, s>>>(sp);
+    if (ks.sNC <= 4) {
+        if (ks.sTN == 6)      structureFactorKernel<6, 4><<<sGrid, ks.sThreads, ks.sSmem, s>>>(sp);
+        else if (ks.sTN == 7) structureFactorKernel<7, 4><<<sGrid, ks.sThreads, ks.sSmem, s>>>(sp);
+        else                  structureFactorKernel<8, 4><<<sGrid, ks.sThreads, ks.sSmem, s>>>(sp);
+    }
+    else {
+        if (ks.sTN == 6)      structureFactorKernel<6, 8><<<sGrid, ks.sThreads, ks.sSmem, s>>>(sp);
+        else if (ks.sTN == 7) structureFactorKernel<7, 8><<<sGrid, ks.sThreads, ks.sSmem, s>>>(sp);
+        else                  structureFactorKernel<8, 8><<<sGrid, ks.sThreads, ks.sSmem, s>>>(sp);
+    }
     CFX_LAUNCH_CHECK(); st.launches++;
     mark(st, "structure_factor", s);
 
