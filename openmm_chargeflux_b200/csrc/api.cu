@@ -175,7 +175,7 @@ int cfx_create(const cfx_system_desc* d, const cfx_options* opts, cfx_handle** o
     if (st.shardRank < 0 || st.shardRank >= st.shardCount) throw ArgError("shard_rank out of range");
     st.useGraph = opts ? (opts->use_graph != 0) : true;
     st.N = N;
-    st.Npad = std::max(128, (N + 127)/128*128);
+    st.Npad = std::max(256, (N + 255)/256*256);
     st.nb = d->num_flux_bonds; st.na = d->num_flux_angles; st.nw = d->num_flux_waters;
     if (st.nb < 0 || st.na < 0 || st.nw < 0 || d->num_exceptions < 0) throw ArgError("negative term count");
     st.numTerms = st.nb + st.na + st.nw;

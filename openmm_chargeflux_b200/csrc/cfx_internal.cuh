@@ -86,7 +86,7 @@ struct KSpacePlan {
     int rowLo = 0, rowHi = 0;
     int signedLo = 0, signedHi = 0;
     // gather geometry
-    int gThreads = 512, gAtoms = 128, gRowsPerTile = 64, gRowSplits = 1;
+    int gThreads = 384, gAtoms = 256, gRowsPerWarp = 2, gBuffers = 2, gRowsPerTile = 64, gRowSplits = 1;
     size_t gSmem = 0;
 };
 

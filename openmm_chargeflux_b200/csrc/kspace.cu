@@ -306,8 +306,7 @@ __global__ void __launch_bounds__(128) coefficientKernel(CoefParams p, long long
 // ------------------------------------------------------------------------------------------------
 #define G_THREADS 384
 #define G_WARPS 12
-#define G_ROWS_PER_WARP 4
-#define G_ROW_TILE (G_WARPS*G_ROWS_PER_WARP)
+#define G_MAX_ROW_TILE (G_WARPS*4)
 
 struct GParams {
     const float4* coef; const int2* rowInfo; const float2* colX; const float2* colY; const float4* colZ4;
@@ -316,14 +315,16 @@ struct GParams {
     int signedLo, signedHi, numRowTiles, numAtomTiles;
     float fx, fy, fz;            // 2 pi / L
     size_t offEy, offCoef, offInfo;     // shared-memory carve-up (bytes)
+    int nbuf;                           // 2: coefficient tiles double-buffered, 1: single buffer (large kmax)
 };
 
 // Persistent kernel: one CTA per SM walks a contiguous range of work units (atom tile, row tile),
 // atom-tile major, so every SM gets the same amount of work to within one row tile (no wave tail) and
 // reloads the per-atom-tile phase columns only when the atom tile changes.
-template <int APT>
+template <int APT, int G_ROWS_PER_WARP>
 __global__ void __launch_bounds__(G_THREADS, 1) gatherKernel(GParams p, long long* __restrict__ forceFixed, long long* __restrict__ dedqFixed) {
     constexpr int BA = 32*APT;
+    constexpr int G_ROW_TILE = G_WARPS*G_ROWS_PER_WARP;
     extern __shared__ __align__(128) unsigned char smem[];
     float4* Z4s = reinterpret_cast<float4*>(smem);                         // [Kz][BA]
     float2* Eys = reinterpret_cast<float2*>(smem + p.offEy);               // [Ky][BA]
@@ -377,9 +378,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) gatherKernel(GParams p, long lon
         __syncthreads();
     };
 
-    prefetchTile(u0, 0);
+    if (p.nbuf == 2) prefetchTile(u0, 0);
     for (int unit = u0; unit < u1; unit++) {
-        const int buf = (unit - u0) & 1;
+        const int buf = (p.nbuf == 2) ? ((unit - u0) & 1) : 0;
         const int atomTile = unit/numRowTiles, rowTile = unit - atomTile*numRowTiles;
         if (atomTile != curAtomTile) {
             if (curAtomTile >= 0) flush();
@@ -397,8 +398,11 @@ __global__ void __launch_bounds__(G_THREADS, 1) gatherKernel(GParams p, long lon
             for (int a = 0; a < APT; a++) { oD[a] = 0.f; oX[a] = 0.f; oY[a] = 0.f; oZ[a] = 0.f; ex[a] = make_float2(0.f, 0.f); }
             curNx = -1;
         }
-        if (unit + 1 < u1) { prefetchTile(unit + 1, buf ^ 1); cpAsyncWait<1>(); }
-        else cpAsyncWait<0>();
+        if (p.nbuf == 2) {
+            if (unit + 1 < u1) { prefetchTile(unit + 1, buf ^ 1); cpAsyncWait<1>(); }
+            else cpAsyncWait<0>();
+        }
+        else { prefetchTile(unit, 0); cpAsyncWait<0>(); }
         __syncthreads();
         const float4* cT = coefS + (size_t) buf*tileElems + (size_t) warp*G_ROWS_PER_WARP*p.Kz;
         float2 U[G_ROWS_PER_WARP][APT], V[G_ROWS_PER_WARP][APT];
@@ -456,7 +460,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gatherKernel(GParams p, long lon
     flush();
 }
 
-size_t gatherSmem(int Kx, int Ky, int Kz, int BA, size_t* offEy, size_t* offCoef, size_t* offInfo) {
+size_t gatherSmem(int Kx, int Ky, int Kz, int BA, int rowTile, int nbuf, size_t* offEy, size_t* offCoef, size_t* offInfo) {
     size_t z4 = (size_t) Kz*BA*sizeof(float4);
     size_t red = (size_t) G_WARPS*BA*sizeof(float4);
     size_t first = std::max(z4, red);
@@ -464,9 +468,9 @@ size_t gatherSmem(int Kx, int Ky, int Kz, int BA, size_t* offEy, size_t* offCoef
     *offEy = first;
     size_t ey = ((size_t) Ky*BA*sizeof(float2) + 127) & ~(size_t) 127;
     *offCoef = first + ey;
-    size_t coef = ((size_t) 2*G_ROW_TILE*Kz*sizeof(float4) + 127) & ~(size_t) 127;
+    size_t coef = ((size_t) nbuf*rowTile*Kz*sizeof(float4) + 127) & ~(size_t) 127;
     *offInfo = *offCoef + coef;
-    return *offInfo + 2*G_ROW_TILE*sizeof(int2);
+    return *offInfo + 2*rowTile*sizeof(int2);
 }
 
 } // namespace
@@ -528,14 +532,14 @@ void planKSpace(State& st) {
     ks.numSignedRows = (int) rowInfo.size();
     ks.signedLo = signedStart[ks.rowLo];
     ks.signedHi = signedStart[ks.rowHi];
-    for (int k = 0; k < G_ROW_TILE; k++) rowInfo.push_back(make_int2(0, 0));   // padding rows (zero coefficients)
+    for (int k = 0; k < G_MAX_ROW_TILE; k++) rowInfo.push_back(make_int2(0, 0));   // padding rows (zero coefficients)
 
     CFX_CUDA(cudaMalloc(&st.rowS, (size_t) st.Npad*ks.rowPitch*sizeof(float2)));
     CFX_CUDA(cudaMalloc(&st.colX, (size_t) Kx*st.Npad*sizeof(float2)));
     CFX_CUDA(cudaMalloc(&st.colY, (size_t) Ky*st.Npad*sizeof(float2)));
     CFX_CUDA(cudaMalloc(&st.colZ4, (size_t) Kz*st.Npad*sizeof(float4)));
     CFX_CUDA(cudaMalloc(&st.sPart, (size_t) ks.sSplits*ks.numRows*ks.kzPad*8*sizeof(float)));
-    const size_t coefElems = (size_t) (ks.numSignedRows + G_ROW_TILE)*Kz;
+    const size_t coefElems = (size_t) (ks.numSignedRows + G_MAX_ROW_TILE)*Kz;
     CFX_CUDA(cudaMalloc(&st.gCoef, coefElems*sizeof(float4)));
     CFX_CUDA(cudaMemset(st.gCoef, 0, coefElems*sizeof(float4)));
     CFX_CUDA(cudaMalloc(&st.gRowInfo, rowInfo.size()*sizeof(int2)));
@@ -545,12 +549,20 @@ void planKSpace(State& st) {
     CFX_CUDA(cudaMemcpy(dSigned, signedStart.data(), signedStart.size()*sizeof(int), cudaMemcpyHostToDevice));
     st.ks_signedStart = dSigned;
 
-    // gather geometry
-    ks.gAtoms = 128;
+    // gather geometry: prefer 2 rows x 8 atoms per thread (fastest inner loop), fall back to 4 x 4 and to
+    // single-buffered coefficient tiles when the per-atom-tile phase columns do not fit in shared memory
+    const size_t smemCap = 220*1024;
     size_t o1, o2, o3;
-    ks.gSmem = gatherSmem(Kx, Ky, Kz, ks.gAtoms, &o1, &o2, &o3);
+    const int shapes[4][3] = {{8, 2, 2}, {4, 4, 2}, {4, 4, 1}, {4, 2, 1}};       // {atoms per lane, rows per warp, buffers}
+    ks.gAtoms = 0;
+    for (const auto& sh : shapes) {
+        const size_t need = gatherSmem(Kx, Ky, Kz, 32*sh[0], G_WARPS*sh[1], sh[2], &o1, &o2, &o3);
+        if (need <= smemCap) { ks.gAtoms = 32*sh[0]; ks.gRowsPerWarp = sh[1]; ks.gBuffers = sh[2]; ks.gSmem = need; break; }
+    }
+    if (ks.gAtoms == 0) throw std::runtime_error("kmax too large for the gather kernel's shared-memory tiles");
     const int signedHere = ks.signedHi - ks.signedLo;
-    ks.gRowsPerTile = (std::max(signedHere, 1) + G_ROW_TILE - 1)/G_ROW_TILE;      // row tiles per atom tile
+    const int gRowTile = G_WARPS*ks.gRowsPerWarp;
+    ks.gRowsPerTile = (std::max(signedHere, 1) + gRowTile - 1)/gRowTile;          // row tiles per atom tile
     ks.gRowSplits = numSM;                                                        // persistent grid size
 
     CFX_CUDA(cudaFuncSetAttribute(structureFactorKernel<6, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ks.sSmem));
@@ -559,7 +571,9 @@ void planKSpace(State& st) {
     CFX_CUDA(cudaFuncSetAttribute(structureFactorKernel<6, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ks.sSmem));
     CFX_CUDA(cudaFuncSetAttribute(structureFactorKernel<7, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ks.sSmem));
     CFX_CUDA(cudaFuncSetAttribute(structureFactorKernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ks.sSmem));
-    CFX_CUDA(cudaFuncSetAttribute(gatherKernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ks.gSmem));
+    CFX_CUDA(cudaFuncSetAttribute(gatherKernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smemCap));
+    CFX_CUDA(cudaFuncSetAttribute(gatherKernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smemCap));
+    CFX_CUDA(cudaFuncSetAttribute(gatherKernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smemCap));
 }
 
 void launchKSpace(State& st, const double* dPos, bool forces, bool energy, long long* dForce, long long* dDedq, cudaStream_t s) {
@@ -613,10 +627,13 @@ void launchKSpace(State& st, const double* dPos, bool forces, bool energy, long 
         gp.Kx = Kx; gp.Ky = Ky; gp.Kz = Kz; gp.N = st.N; gp.Npad = st.Npad;
         gp.signedLo = ks.signedLo; gp.signedHi = ks.signedHi; gp.numRowTiles = ks.gRowsPerTile; gp.numAtomTiles = st.Npad/ks.gAtoms;
         gp.fx = (float) cp.gx; gp.fy = (float) cp.gy; gp.fz = (float) cp.gz;
-        gatherSmem(Kx, Ky, Kz, ks.gAtoms, &gp.offEy, &gp.offCoef, &gp.offInfo);
+        gatherSmem(Kx, Ky, Kz, ks.gAtoms, G_WARPS*ks.gRowsPerWarp, ks.gBuffers, &gp.offEy, &gp.offCoef, &gp.offInfo);
+        gp.nbuf = ks.gBuffers;
         const long long units = (long long) gp.numAtomTiles*gp.numRowTiles;
         const int gGrid = (int) std::min<long long>(ks.gRowSplits, units);
-        gatherKernel<4><<<gGrid, G_THREADS, ks.gSmem, s>>>(gp, dForce, dDedq);
+        if (ks.gAtoms == 256)           gatherKernel<8, 2><<<gGrid, G_THREADS, ks.gSmem, s>>>(gp, dForce, dDedq);
+        else if (ks.gRowsPerWarp == 4)  gatherKernel<4, 4><<<gGrid, G_THREADS, ks.gSmem, s>>>(gp, dForce, dDedq);
+        else                            gatherKernel<4, 2><<<gGrid, G_THREADS, ks.gSmem, s>>>(gp, dForce, dDedq);
         CFX_LAUNCH_CHECK(); st.launches++;
         mark(st, "kspace_gather", s);
     }
