@@ -162,6 +162,28 @@ def cpu_baseline(pos, box, force, budget_s=25.0):
             "seconds_per_eval_extrapolated": t_full}
 
 
+def md_leg(args):
+    """NVE MD of the same box: bonded forces + charge-flux Ewald forces + velocity Verlet, one CUDA graph per step."""
+    try:
+        from openmm_chargeflux_b200 import md, synthetic
+        cfgs = synthetic.CONFIGS[args.workload]
+        sim, pos = md.flexible_water_simulation(cfgs["n_waters"], cfgs["seed"], cutoff=cfgs["cutoff"], ewald_tol=cfgs["ewald_tol"])
+        sim.minimize(200, 0.002)
+        p, _ = sim.get_state()
+        sim.set_state(p, sim.maxwell_boltzmann(300.0, seed=7))
+        dt = TIMESTEP_FS * 1e-3
+        sim.step(50, dt)
+        e0 = sim.energies()
+        ms = sim.step(args.md_steps, dt) / args.md_steps
+        e1 = sim.energies()
+        sim.close()
+        return {"steps": args.md_steps, "dt_fs": TIMESTEP_FS, "ms_per_step": ms, "steps_per_s": 1e3 / ms, "ns_per_day": ns_per_day(1e3 / ms),
+                "energy_drift_over_kinetic": (e1["total"] - e0["total"]) / e0["kinetic"],
+                "note": "forces-only evaluations; profiles/ holds the 10,000-step run"}
+    except Exception as e:
+        return {"unavailable": "%s: %s" % (type(e).__name__, e)}
+
+
 def existing_cuda_baseline(workload, our_ms):
     """The reference's own platforms/cuda kernels (prebuilt cubins in oracle/_ref, see oracle/refcuda/) timed here."""
     try:
@@ -340,6 +362,8 @@ def run_ours(args, pos, box, force, workload):
         line["config"]["pairs_in_cutoff"] = int(pairs)
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(pos, box, force)
+        if args.md_steps > 0:
+            line["md_nve"] = md_leg(args)
         # second reported baseline of north_star: the plugin's EXISTING CUDA kernels on this GPU
         line["existing_cuda_baseline"] = existing_cuda_baseline(args.workload, ms_per_step)
     if rank == 0:
@@ -356,6 +380,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--md-steps", type=int, default=500, help="length of the NVE MD leg (0 = skip)")
     args = ap.parse_args()
     from openmm_chargeflux_b200 import synthetic
     pos, box, force = synthetic.config(args.workload)

@@ -144,6 +144,28 @@ int  cfx_time_kernels(cfx_handle* h, const double* d_positions, const double* bo
  * bounded by (MEASURED_PEAKS.json has no FP32 CUDA-core figure). */
 int  cfx_measure_fp32_peak(int device, int iters, double* tflops, double* sm_clock_mhz_est);
 
+/* ------------------------------------------------------------------------------------------------
+ * MD harness: what sits either side of the path in an OpenMM simulation of
+ * flexible molecules -- harmonic bond/angle forces and a velocity-Verlet integrator -- so that the
+ * "NVE MD" benchmark configuration can be run and energy conservation checked without OpenMM. The whole
+ * step (bonded forces + charge-flux Ewald forces + integration) is device-resident and replayed as one
+ * CUDA graph. Units: amu, nm, ps, kJ/mol. E_bond = k/2 (r-r0)^2, E_angle = k/2 (theta-theta0)^2.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct cfx_md cfx_md;
+int  cfx_md_create(cfx_handle* h, const double* masses /*[N]*/,
+                   int32_t num_bonds, const int32_t* bond_idx /*[2nb]*/, const double* bond_params /*[2nb]: k, r0*/,
+                   int32_t num_angles, const int32_t* angle_idx /*[3na]*/, const double* angle_params /*[2na]: k, theta0*/,
+                   cfx_md** out);
+void cfx_md_destroy(cfx_md* md);
+int  cfx_md_set_state(cfx_md* md, const double* positions /*[3N]*/, const double* velocities /*[3N] or NULL*/, const double* box);
+int  cfx_md_get_state(cfx_md* md, double* positions, double* velocities);
+/* steepest descent with a per-atom displacement cap (nm), to relax the synthetic starting structures */
+int  cfx_md_minimize(cfx_md* md, int32_t steps, double max_displacement);
+/* nsteps of velocity Verlet with time step dt (ps); ms_elapsed (may be NULL) = device time of the steps */
+int  cfx_md_step(cfx_md* md, int32_t nsteps, double dt, float* ms_elapsed);
+/* energies of the current state: [kinetic, bonded, coulomb+LJ (the CoulForce), total] */
+int  cfx_md_energies(cfx_md* md, double* out4);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,6 +21,8 @@ void throwCuda(cudaError_t code, const char* what, const char* file, int line) {
     throw std::runtime_error(buf);
 }
 
+void setLastError(const std::string& msg) { g_lastError = msg; }
+
 void mark(State& st, const char* name, cudaStream_t s) {
     if (!st.timing) return;
     cudaEvent_t ev;
@@ -92,10 +94,12 @@ __global__ void addEnergyKernel(const long long* __restrict__ energyFixed, doubl
     }
 }
 
+} // namespace
+
 // The kernel sequence of one evaluation. Forces are ADDED into dForce (fixed point); dE/dq of this
 // evaluation is built in st.dedqFixed (zeroed here) because the chain rule must see only this
 // evaluation's values.
-void enqueueEvaluation(State& st, const double* dPos, bool includeForces, bool includeEnergy, long long* dForce, cudaStream_t s) {
+void enqueueEvaluation(State& st, const double* dPos, bool includeForces, bool includeEnergy, long long* dForce, cudaStream_t s, bool skipDiscardedEnergy) {
     CFX_CUDA(cudaMemsetAsync(st.dedqFixed, 0, sizeof(long long)*st.Npad, s));
     CFX_CUDA(cudaMemsetAsync(st.energyFixed, 0, sizeof(long long)*8, s));
     launchFluxAssembly(st, dPos, s);
@@ -104,7 +108,7 @@ void enqueueEvaluation(State& st, const double* dPos, bool includeForces, bool i
         // reference quirks mirrored: reciprocal energy only with includeEnergy; direct,
         // self and exclusion energies always; pair/recip forces and dE/dq only with includeForces
         launchKSpace(st, dPos, includeForces, includeEnergy, dForce, st.dedqFixed, s);
-        launchDirect(st, dPos, includeForces, includeEnergy ? 2 : 1, false, dForce, st.dedqFixed, s);
+        launchDirect(st, dPos, includeForces, includeEnergy ? 2 : (skipDiscardedEnergy ? 0 : 1), false, dForce, st.dedqFixed, s);
         launchExclusionCorrection(st, dPos, includeForces, dForce, st.dedqFixed, s);
     }
     else
@@ -125,12 +129,18 @@ void ensureCells(State& st) {
     planCells(st);
 }
 
-} // namespace
+void ensureBox(State& st, const double* box) {
+    checkBox(box);
+    if (box[0] < 2*st.cutoff || box[4] < 2*st.cutoff || box[8] < 2*st.cutoff)
+        throw ArgError("the periodic box must be at least twice the cutoff in every direction");
+    if (st.box.L[0] != box[0] || st.box.L[1] != box[4] || st.box.L[2] != box[8]) { setBox(st, box); dropGraphs(st); }
+    ensureCells(st);
+}
+
 } // namespace cfx
 
 using namespace cfx;
 
-struct cfx_handle { State st; };
 
 #define CFX_TRY try {
 #define CFX_CATCH \
@@ -351,7 +361,7 @@ int cfx_execute(cfx_handle* h, const double* positions, const double* box, int i
     auto enqueueAll = [&]() {
         CFX_CUDA(cudaMemcpyAsync(st.pos, st.hPos, sizeof(double)*3*st.N, cudaMemcpyHostToDevice, s));
         CFX_CUDA(cudaMemsetAsync(st.forceFixed, 0, sizeof(long long)*3*st.Npad, s));
-        enqueueEvaluation(st, st.pos, incF, incE, st.forceFixed, s);
+        enqueueEvaluation(st, st.pos, incF, incE, st.forceFixed, s, false);
         launchFinalize(st, st.forceFixed, s);
         CFX_CUDA(cudaMemcpyAsync(st.hForce, st.forceOut, sizeof(double)*3*st.N, cudaMemcpyDeviceToHost, s));
         CFX_CUDA(cudaMemcpyAsync(st.hEnergy, st.energyOut, sizeof(double)*CFX_E_COUNT, cudaMemcpyDeviceToHost, s));
@@ -399,7 +409,7 @@ int cfx_execute_device(cfx_handle* h, const double* d_positions, const double* b
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     auto enqueueAll = [&]() {
-        enqueueEvaluation(st, d_positions, include_forces != 0, include_energy != 0, d_force_fixed, s);
+        enqueueEvaluation(st, d_positions, include_forces != 0, include_energy != 0, d_force_fixed, s, false);
         if (d_dedq_fixed) {
             addFixedKernel<<<(st.N + 255)/256, 256, 0, s>>>(st.N, st.dedqFixed, d_dedq_fixed);
             CFX_LAUNCH_CHECK(); st.launches++;
@@ -576,7 +586,7 @@ int cfx_time_device(cfx_handle* h, const double* d_positions, const double* box,
     CFX_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
     try {
         CFX_CUDA(cudaMemsetAsync(st.forceFixed, 0, sizeof(long long)*3*st.Npad, s));
-        enqueueEvaluation(st, d_positions, include_forces != 0, include_energy != 0, st.forceFixed, s);
+        enqueueEvaluation(st, d_positions, include_forces != 0, include_energy != 0, st.forceFixed, s, false);
     }
     catch (...) { cudaGraph_t dead; cudaStreamEndCapture(s, &dead); throw; }
     CFX_CUDA(cudaStreamEndCapture(s, &graph));
@@ -619,7 +629,7 @@ int cfx_time_kernels(cfx_handle* h, const double* d_positions, const double* box
         st.timing = true;
         CFX_CUDA(cudaMemsetAsync(st.forceFixed, 0, sizeof(long long)*3*st.Npad, s));
         mark(st, "begin", s);
-        enqueueEvaluation(st, d_positions, true, true, st.forceFixed, s);
+        enqueueEvaluation(st, d_positions, true, true, st.forceFixed, s, false);
         st.timing = false;
         CFX_CUDA(cudaStreamSynchronize(s));
         if (it == 0) { labels.assign(st.timeNames.begin() + 1, st.timeNames.end()); acc.assign(labels.size(), 0.0); continue; }

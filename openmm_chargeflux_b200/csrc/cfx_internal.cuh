@@ -180,5 +180,13 @@ void launchKSpace(State& st, const double* dPos, bool forces, bool energy, long 
 void planCells(State& st);
 void launchDirect(State& st, const double* dPos, bool forces, int energyMode /*0 none, 1 FP32 terms, 2 FP64 terms*/, bool emitPairs, long long* dForce, long long* dDedq, cudaStream_t s); // piece (2)
 void mark(State& st, const char* name, cudaStream_t s);   // per-kernel timing marker (no-op unless st.timing)
+// the kernel sequence of one evaluation (api.cu); skipDiscardedEnergy: do not produce the partial energy the
+// reference returns (and OpenMM discards) when includeEnergy is false -- used by the MD harness
+void enqueueEvaluation(State& st, const double* dPos, bool includeForces, bool includeEnergy, long long* dForce, cudaStream_t s,
+                       bool skipDiscardedEnergy);
+void ensureBox(State& st, const double* box);            // validates the box, re-plans the cell grid if it changed
+void setLastError(const std::string& msg);
 
 } // namespace cfx
+
+struct cfx_handle { cfx::State st; };
