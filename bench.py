@@ -256,6 +256,8 @@ def run_ours(args, pos, box, force, workload):
         raise SystemExit("bench.py needs a B200: there is no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
+        # rank 0 must print exactly one JSON line: keep NCCL's version banner off stdout
+        os.environ["NCCL_DEBUG"] = os.environ.get("CFX_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n = len(pos)
     ctx = ShardedCoulContext(force, box, rank=rank, world=world, device=local)
