@@ -13,6 +13,7 @@ The collective is ``torch.distributed.all_reduce`` (NCCL over NVLink on GPUs; gl
 import numpy as np
 
 FIXED_SCALE = 4294967296.0
+ENERGY_SCALE = 16777216.0
 
 
 def shard_bounds(count, rank, world):
@@ -44,7 +45,10 @@ class ShardedCoulContext:
         self.d_pos = torch.zeros(3 * self.n, dtype=torch.float64, device=self.device)
         # one buffer = forces [3][Npad] followed by the four energy components (fixed point 2^24 as
         # int64 would lose nothing, but energies are kept as doubles in a second tiny buffer)
-        self.d_force = torch.zeros(3 * self.npad, dtype=torch.int64, device=self.device)
+        # one reduction buffer: forces [3][Npad] followed by 8 slots for the energies as 2^24 fixed point,
+        # so a step needs a single all-reduce
+        self.d_buf = torch.zeros(3 * self.npad + 8, dtype=torch.int64, device=self.device)
+        self.d_force = self.d_buf[:3 * self.npad]
         self.d_energy = torch.zeros(8, dtype=torch.float64, device=self.device)
         self.h_pos = torch.zeros(3 * self.n, dtype=torch.float64).pin_memory() if self.device.type == "cuda" else None
         # a dedicated (capturable) stream: the step is replayed as one CUDA graph on it
@@ -63,8 +67,10 @@ class ShardedCoulContext:
             self.kernel.execute_device(self.d_pos.data_ptr(), self.box, self.d_force.data_ptr(), 0, self.d_energy.data_ptr(),
                                        stream, include_forces, include_energy)
             if self.world > 1:
-                self.dist.all_reduce(self.d_force)
-                self.dist.all_reduce(self.d_energy)
+                t = self.torch
+                self.d_buf[3 * self.npad:] = t.round(self.d_energy * ENERGY_SCALE).to(t.int64)
+                self.dist.all_reduce(self.d_buf)
+                self.d_energy.copy_(self.d_buf[3 * self.npad:].to(t.float64) / ENERGY_SCALE)
 
     def evaluate(self, positions, include_forces=True, include_energy=True):
         """Host positions in, (energy, forces[N,3], components[5]) out -- the end-to-end call."""
