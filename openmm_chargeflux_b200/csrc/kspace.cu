@@ -135,6 +135,7 @@ __global__ void __launch_bounds__(32*G, (G <= 4) ? 3 : 1) structureFactorKernel(
     constexpr int TNP = (TN + 1) & ~1;
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem);
+    int* done = reinterpret_cast<int*>(smem + 64);         // per slot: warps that have finished reading it
     float2* raw = reinterpret_cast<float2*>(smem + 128);
     const int stageElems = S_ATOMS_PER_STAGE*p.rowPitch;
 
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(32*G, (G <= 4) ? 3 : 1) structureFactorKernel(
             for (int k = 0; k < 8; k++) acc[i][c][k] = 0.f;
 
     if (tid == 0) {
-        for (int s = 0; s < p.stages; s++) mbarInit(mbar + s, 1);
+        for (int s = 0; s < p.stages; s++) { mbarInit(mbar + s, 1); done[s] = 0; }
         mbarFenceInit();
     }
     __syncthreads();
@@ -176,6 +177,8 @@ __global__ void __launch_bounds__(32*G, (G <= 4) ? 3 : 1) structureFactorKernel(
             bulkLoad(raw + (size_t) s*stageElems, p.rowS + (size_t) (atomBegin + s*S_ATOMS_PER_STAGE)*p.rowPitch, stageBytes, mbar + s);
         }
 
+    // Warps run free of each other: a warp waits only for the TMA of its next stage; the last warp to
+    // finish a stage re-arms the slot's mbarrier and issues the refill (no CTA barrier in the loop).
     for (int st = 0; st < numStages; st++) {
         const int slot = st % p.stages;
         mbarWait(mbar + slot, (uint32_t) ((st/p.stages) & 1));
@@ -207,11 +210,16 @@ __global__ void __launch_bounds__(32*G, (G <= 4) ? 3 : 1) structureFactorKernel(
                 acc[1][c][6] = fmaf(a1.w, zc, acc[1][c][6]);  acc[1][c][7] = fmaf(a1.w, zs, acc[1][c][7]);
             }
         }
-        __syncthreads();                                     // every warp is done with this slot
-        if (tid == 0 && st + p.stages < numStages) {
-            mbarExpectTx(mbar + slot, stageBytes);
-            bulkLoad(raw + (size_t) slot*stageElems, p.rowS + (size_t) (atomBegin + (st + p.stages)*S_ATOMS_PER_STAGE)*p.rowPitch,
-                     stageBytes, mbar + slot);
+        __syncwarp();
+        if (lane == 0 && st + p.stages < numStages) {
+            __threadfence_block();
+            if (atomicAdd(done + slot, 1) == (int) (blockDim.x >> 5) - 1) {   // every warp has read this slot
+                done[slot] = 0;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbarExpectTx(mbar + slot, stageBytes);
+                bulkLoad(raw + (size_t) slot*stageElems, p.rowS + (size_t) (atomBegin + (st + p.stages)*S_ATOMS_PER_STAGE)*p.rowPitch,
+                         stageBytes, mbar + slot);
+            }
         }
     }
     #pragma unroll
@@ -338,13 +346,16 @@ __global__ void __launch_bounds__(G_THREADS, 1) gatherKernel(GParams p, long lon
     if (u0 >= u1) return;
     const int tileElems = G_ROW_TILE*p.Kz;
 
+    // Each warp only ever reads its own G_ROWS_PER_WARP rows of a coefficient tile, so every warp
+    // prefetches (cp.async) and double-buffers its own rows: no block-level barrier in the main loop.
+    const int warpElems = G_ROWS_PER_WARP*p.Kz;
     auto prefetchTile = [&](int unit, int buf) {
         const int rt = unit % numRowTiles;
-        const size_t row0 = (size_t) p.signedLo + (size_t) rt*G_ROW_TILE;
+        const size_t row0 = (size_t) p.signedLo + (size_t) rt*G_ROW_TILE + (size_t) warp*G_ROWS_PER_WARP;
         const float4* src = p.coef + row0*p.Kz;
-        float4* dst = coefS + (size_t) buf*tileElems;
-        for (int e = tid; e < tileElems; e += G_THREADS) cpAsync16(dst + e, src + e);
-        if (tid < G_ROW_TILE) infoS[buf*G_ROW_TILE + tid] = p.rowInfo[row0 + tid];
+        float4* dst = coefS + (size_t) buf*tileElems + (size_t) warp*warpElems;
+        for (int e = lane; e < warpElems; e += 32) cpAsync16(dst + e, src + e);
+        if (lane < G_ROWS_PER_WARP) infoS[buf*G_ROW_TILE + warp*G_ROWS_PER_WARP + lane] = p.rowInfo[row0 + lane];
         cpAsyncCommit();
     };
 
@@ -384,6 +395,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gatherKernel(GParams p, long lon
         const int atomTile = unit/numRowTiles, rowTile = unit - atomTile*numRowTiles;
         if (atomTile != curAtomTile) {
             if (curAtomTile >= 0) flush();
+            else __syncthreads();
             curAtomTile = atomTile;
             atom0 = atomTile*BA;
             for (int e = tid; e < p.Kz*BA; e += G_THREADS) {
@@ -397,13 +409,14 @@ __global__ void __launch_bounds__(G_THREADS, 1) gatherKernel(GParams p, long lon
             #pragma unroll
             for (int a = 0; a < APT; a++) { oD[a] = 0.f; oX[a] = 0.f; oY[a] = 0.f; oZ[a] = 0.f; ex[a] = make_float2(0.f, 0.f); }
             curNx = -1;
+            __syncthreads();                             // phase columns visible to every warp
         }
         if (p.nbuf == 2) {
             if (unit + 1 < u1) { prefetchTile(unit + 1, buf ^ 1); cpAsyncWait<1>(); }
             else cpAsyncWait<0>();
         }
         else { prefetchTile(unit, 0); cpAsyncWait<0>(); }
-        __syncthreads();
+        __syncwarp();
         const float4* cT = coefS + (size_t) buf*tileElems + (size_t) warp*G_ROWS_PER_WARP*p.Kz;
         float2 U[G_ROWS_PER_WARP][APT], V[G_ROWS_PER_WARP][APT];
         #pragma unroll
@@ -455,7 +468,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gatherKernel(GParams p, long lon
                 oZ[a] = fmaf(tr, V[i][a].y, oZ[a]);  oZ[a] = fmaf(ti, V[i][a].x, oZ[a]);
             }
         }
-        __syncthreads();
+        __syncwarp();
     }
     flush();
 }
