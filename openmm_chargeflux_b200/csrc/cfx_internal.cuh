@@ -79,7 +79,7 @@ struct KSpacePlan {
     int numRows = 0;             // unsigned rows (nx, |ny|): Kx*Ky
     int numSignedRows = 0;       // gather rows (nx, ny): Ky + (Kx-1)*(2Ky-1)
     // S kernel geometry
-    int sThreads = 256, sTN = 4, sTM = 2, sNC = 0, sTR = 0, sBM = 0, sRowTiles = 0, sSplits = 0, sAtomsPerSplit = 0;
+    int sThreads = 128, sTN = 7, sNC = 0, sRowTiles = 0, sSplits = 0, sAtomsPerSplit = 0;   // TN columns per warp, NC column groups
     int sStages = 3;
     size_t sSmem = 0;
     // shard of the unsigned rows this rank owns [rowLo, rowHi) (k-vector sharding)
@@ -94,7 +94,7 @@ struct CellPlan {
     int nc[3] = {1, 1, 1};
     int ncells = 1;
     int lo[3] = {0, 0, 0}, nd[3] = {1, 1, 1};   // stencil offsets per axis: lo .. lo+nd-1
-    bool smallBox = false;                      // stencil wraps onto itself: per-pair min image
+    bool smallBox = false;                      // informational: tiles fall back to per-pair min image
     float cs[3] = {1, 1, 1};
     double csd[3] = {1, 1, 1};
 };

@@ -494,9 +494,8 @@ size_t gatherSmem(int Kx, int Ky, int Kz, int BA, int rowTile, int nbuf, size_t*
 void planKSpace(State& st) {
     KSpacePlan& ks = st.ks;
     const int Kx = ks.K[0], Ky = ks.K[1], Kz = ks.K[2];
-    // S kernel: TM = 2 rows per lane, TN in {6,7,8} columns per warp; pick the TN with the least column
+    // S kernel: 2 rows per lane, TN in {6,7,8} columns per warp; pick the TN with the least column
     // padding (ties -> larger TN), at most S_MAX_WARPS column groups per CTA
-    ks.sTM = 2;
     int bestPad = 1 << 30;
     for (int tn = 6; tn <= 8; tn++) {
         const int g = (Kz + tn - 1)/tn;
@@ -514,7 +513,6 @@ void planKSpace(State& st) {
     ks.rowHi = (int) ((int64_t) ks.numRows*(st.shardRank + 1)/st.shardCount);
     const int rowsHere = ks.rowHi - ks.rowLo;
     ks.sThreads = 32*ks.sNC;
-    ks.sBM = S_BM;
     ks.sRowTiles = (std::max(rowsHere, 1) + S_BM - 1)/S_BM;
     ks.sStages = 3;
     const size_t stageBytes = (size_t) S_ATOMS_PER_STAGE*ks.rowPitch*sizeof(float2);
