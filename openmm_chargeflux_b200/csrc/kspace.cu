@@ -67,46 +67,47 @@ struct TableParams {
     double invLx, invLy, invLz;
 };
 
-// One thread per (atom, axis). Writes the atom-major rows used by the S kernel and the n-major
-// columns used by the gather kernel. Padded atoms (>= N) get all-zero phases.
+// One CTA = 32 atoms x 3 axes (96 working threads). Each thread runs the FP64 recurrence of one (atom, axis);
+// the atom-major rows used by the S kernel are assembled in shared memory and written out as one contiguous,
+// fully coalesced block; the n-major columns used by the gather kernel are coalesced over atoms as they are.
+// Padded atoms (>= N) get all-zero phases.
+#define PT_ATOMS 32
 __global__ void __launch_bounds__(128) phaseTableKernel(TableParams p, const double* __restrict__ pos, const float* __restrict__ qf,
         float2* __restrict__ rowS, float2* __restrict__ colX, float2* __restrict__ colY, float4* __restrict__ colZ4) {
-    const int t = blockIdx.x*blockDim.x + threadIdx.x;
-    const int atom = t % p.Npad, axis = t / p.Npad;
-    if (axis >= 3) return;
-    const int K = axis == 0 ? p.Kx : (axis == 1 ? p.Ky : p.Kz);
-    float2* row = rowS + (size_t) atom*p.rowPitch + (axis == 0 ? 0 : (axis == 1 ? p.Kx : p.zOff));
-    if (axis == 2)
-        for (int n = 0; n < p.kzPad; n++) row[n] = make_float2(0.f, 0.f);       // includes the padding slots
-    if (atom >= p.N) {
-        for (int n = 0; n < K; n++) {
-            if (axis != 2) row[n] = make_float2(0.f, 0.f);
-            if (axis == 0) colX[(size_t) n*p.Npad + atom] = make_float2(0.f, 0.f);
-            else if (axis == 1) colY[(size_t) n*p.Npad + atom] = make_float2(0.f, 0.f);
-            else colZ4[(size_t) n*p.Npad + atom] = make_float4(0.f, 0.f, 0.f, 0.f);
+    extern __shared__ float2 rows[];                      // [PT_ATOMS][rowPitch]
+    const int la = threadIdx.x & 31, axis = threadIdx.x >> 5;
+    const int atom = blockIdx.x*PT_ATOMS + la;
+    for (int e = threadIdx.x; e < PT_ATOMS*p.rowPitch; e += blockDim.x) rows[e] = make_float2(0.f, 0.f);   // padding slots stay zero
+    __syncthreads();
+    if (axis < 3) {
+        const int K = axis == 0 ? p.Kx : (axis == 1 ? p.Ky : p.Kz);
+        float2* row = rows + la*p.rowPitch + (axis == 0 ? 0 : (axis == 1 ? p.Kx : p.zOff));
+        const bool real = atom < p.N;
+        double s1 = 0.0, c1 = 0.0;
+        float scale = 0.f;
+        if (real) {
+            const double invL = axis == 0 ? p.invLx : (axis == 1 ? p.invLy : p.invLz);
+            double u = pos[3*(size_t) atom + axis]*invL;
+            u -= floor(u);
+            sincospi(2.0*u, &s1, &c1);
+            scale = axis == 0 ? qf[atom] : 1.0f;
         }
-    }
-    else {
-        const double invL = axis == 0 ? p.invLx : (axis == 1 ? p.invLy : p.invLz);
-        double u = pos[3*(size_t) atom + axis]*invL;
-        u -= floor(u);
-        double s1, c1;
-        sincospi(2.0*u, &s1, &c1);
-        const float scale = axis == 0 ? qf[atom] : 1.0f;
-        double c = 1.0, s = 0.0;
+        double c = real ? 1.0 : 0.0, sn = 0.0;
         for (int n = 0; n < K; n++) {
-            const float cf = (float) c, sf = (float) s;
+            const float cf = (float) c, sf = (float) sn;
             row[axis == 2 ? (n/p.TN)*p.TNP + n % p.TN : n] = make_float2(scale*cf, scale*sf);
             if (axis == 0) colX[(size_t) n*p.Npad + atom] = make_float2(cf, sf);
             else if (axis == 1) colY[(size_t) n*p.Npad + atom] = make_float2(cf, sf);
             else colZ4[(size_t) n*p.Npad + atom] = make_float4(cf, sf, (float) n*cf, (float) n*sf);
-            const double cn = c*c1 - s*s1;
-            s = c*s1 + s*c1;
+            const double cn = c*c1 - sn*s1;
+            sn = c*s1 + sn*c1;
             c = cn;
         }
     }
-    if (axis == 1)
-        for (int n = p.Kx + p.Ky; n < p.zOff; n++) rowS[(size_t) atom*p.rowPitch + n] = make_float2(0.f, 0.f);
+    __syncthreads();
+    float4* dst = reinterpret_cast<float4*>(rowS + (size_t) blockIdx.x*PT_ATOMS*p.rowPitch);
+    const float4* src = reinterpret_cast<const float4*>(rows);
+    for (int e = threadIdx.x; e < PT_ATOMS*p.rowPitch/2; e += blockDim.x) dst[e] = src[e];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -250,19 +251,28 @@ struct CoefParams {
 
 __global__ void __launch_bounds__(128) coefficientKernel(CoefParams p, long long* __restrict__ energyFixed) {
     __shared__ double scratch[32];
-    const int t = blockIdx.x*blockDim.x + threadIdx.x;
+    // 4 lanes share one (row, |nz|): each sums a quarter of the atom splits, then a 2-step shuffle reduction
+    const int gt = blockIdx.x*blockDim.x + threadIdx.x;
+    const int t = gt >> 2, sub = gt & 3;
     const int rowsHere = p.rowHi - p.rowLo;
     double en = 0.0;
-    if (t < rowsHere*p.Kz) {
-        const int row = p.rowLo + t/p.Kz, l = t % p.Kz;
+    const bool valid = t < rowsHere*p.Kz;
+    {
+        const int tt = valid ? t : 0;
+        const int row = p.rowLo + tt/p.Kz, l = tt % p.Kz;
         const int nx = row/p.Ky, m = row - nx*p.Ky;
         double P[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (int s = 0; s < p.splits; s++) {
+        for (int s = sub; s < p.splits; s += 4) {
             const int slotL = (l/p.TN)*p.TNP + l % p.TN;
             const float4* src = reinterpret_cast<const float4*>(p.part + (((size_t) s*p.numRows + row)*p.kzPad + slotL)*8);
             const float4 v0 = src[0], v1 = src[1];
             P[0] += v0.x; P[1] += v0.y; P[2] += v0.z; P[3] += v0.w;
             P[4] += v1.x; P[5] += v1.y; P[6] += v1.z; P[7] += v1.w;
+        }
+        #pragma unroll
+        for (int k = 0; k < 8; k++) {
+            P[k] += __shfl_xor_sync(0xffffffffu, P[k], 1);
+            P[k] += __shfl_xor_sync(0xffffffffu, P[k], 2);
         }
         // P = {rcc, rcs, rsc, rss, icc, ics, isc, iss}
         const double kx = nx*p.gx, ky = m*p.gy, kz = l*p.gz;
@@ -280,13 +290,13 @@ __global__ void __launch_bounds__(128) coefficientKernel(CoefParams p, long long
                 const double re = P[0] - sy*sz*P[3] - sz*P[5] - sy*P[6];
                 const double im = P[4] - sy*sz*P[7] + sz*P[1] + sy*P[2];
                 if (inHalf) {
-                    en += p.C*ak*(re*re + im*im);
+                    if (valid && sub == 0) en += p.C*ak*(re*re + im*im);
                     Gre[iy][iz] = 2.0*p.C*ak*re;
                     Gim[iy][iz] = 2.0*p.C*ak*im;
                 }
                 else { Gre[iy][iz] = 0.0; Gim[iy][iz] = 0.0; }
             }
-        if (p.forces) {
+        if (p.forces && valid && sub == 0) {
             // signed rows of this unsigned row: (nx,+m) first, then (nx,-m) when it exists
             const int sBase = p.signedStart[row];
             const int nSigned = p.signedStart[row+1] - sBase;
@@ -576,6 +586,7 @@ void planKSpace(State& st) {
     ks.gRowsPerTile = (std::max(signedHere, 1) + gRowTile - 1)/gRowTile;          // row tiles per atom tile
     ks.gRowSplits = numSM;                                                        // persistent grid size
 
+    CFX_CUDA(cudaFuncSetAttribute(phaseTableKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (PT_ATOMS*ks.rowPitch*sizeof(float2))));
     CFX_CUDA(cudaFuncSetAttribute(structureFactorKernel<6, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ks.sSmem));
     CFX_CUDA(cudaFuncSetAttribute(structureFactorKernel<7, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ks.sSmem));
     CFX_CUDA(cudaFuncSetAttribute(structureFactorKernel<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ks.sSmem));
@@ -594,7 +605,7 @@ void launchKSpace(State& st, const double* dPos, bool forces, bool energy, long 
     const int zOff = ks.rowPitch - ks.kzPad;
     const int TNP = (ks.sTN + 1) & ~1;
     TableParams tp{st.N, st.Npad, Kx, Ky, Kz, ks.kzPad, zOff, ks.rowPitch, ks.sTN, TNP, 1.0/st.box.L[0], 1.0/st.box.L[1], 1.0/st.box.L[2]};
-    phaseTableKernel<<<(3*st.Npad + 127)/128, 128, 0, s>>>(tp, dPos, st.qf, st.rowS, st.colX, st.colY, st.colZ4);
+    phaseTableKernel<<<st.Npad/PT_ATOMS, 128, PT_ATOMS*ks.rowPitch*sizeof(float2), s>>>(tp, dPos, st.qf, st.rowS, st.colX, st.colY, st.colZ4);
     CFX_LAUNCH_CHECK(); st.launches++;
     mark(st, "phase_tables", s);
     if (ks.rowHi <= ks.rowLo) return;
@@ -628,7 +639,7 @@ void launchKSpace(State& st, const double* dPos, bool forces, bool energy, long 
     cp.invFourAlpha2 = 0.25/(st.alpha*st.alpha);
     cp.energy = energy; cp.forces = forces;
     const int items = (ks.rowHi - ks.rowLo)*Kz;
-    coefficientKernel<<<(items + 127)/128, 128, 0, s>>>(cp, st.energyFixed);
+    coefficientKernel<<<(4*items + 127)/128, 128, 0, s>>>(cp, st.energyFixed);
     CFX_LAUNCH_CHECK(); st.launches++;
     mark(st, "kspace_coef", s);
 
