@@ -107,9 +107,24 @@ void enqueueEvaluation(State& st, const double* dPos, bool includeForces, bool i
         CFX_CUDA(cudaMemsetAsync(st.pairCounters, 0, sizeof(unsigned long long)*4, s));
         // reference quirks mirrored: reciprocal energy only with includeEnergy; direct,
         // self and exclusion energies always; pair/recip forces and dE/dq only with includeForces
-        launchKSpace(st, dPos, includeForces, includeEnergy, dForce, st.dedqFixed, s);
-        launchDirect(st, dPos, includeForces, includeEnergy ? 2 : (skipDiscardedEnergy ? 0 : 1), false, dForce, st.dedqFixed, s);
-        launchExclusionCorrection(st, dPos, includeForces, dForce, st.dedqFixed, s);
+        const int emode = includeEnergy ? 2 : (skipDiscardedEnergy ? 0 : 1);
+        if (st.overlapBranches && !st.timing) {
+            // The reciprocal-space and direct-space branches only meet in the fixed-point accumulators
+            // (atomics), so the direct branch is forked onto a side stream: its small kernels and its tail
+            // overlap with the k-space kernels. Fork/join are captured into the step's CUDA graph.
+            CFX_CUDA(cudaEventRecord(st.evFork, s));
+            CFX_CUDA(cudaStreamWaitEvent(st.sideStream, st.evFork, 0));
+            launchDirect(st, dPos, includeForces, emode, false, dForce, st.dedqFixed, st.sideStream);
+            launchExclusionCorrection(st, dPos, includeForces, dForce, st.dedqFixed, st.sideStream);
+            CFX_CUDA(cudaEventRecord(st.evJoin, st.sideStream));
+            launchKSpace(st, dPos, includeForces, includeEnergy, dForce, st.dedqFixed, s);
+            CFX_CUDA(cudaStreamWaitEvent(s, st.evJoin, 0));
+        }
+        else {
+            launchKSpace(st, dPos, includeForces, includeEnergy, dForce, st.dedqFixed, s);
+            launchDirect(st, dPos, includeForces, emode, false, dForce, st.dedqFixed, s);
+            launchExclusionCorrection(st, dPos, includeForces, dForce, st.dedqFixed, s);
+        }
     }
     else
         launchNoCutoff(st, dPos, includeForces, includeEnergy, dForce, st.dedqFixed, s);
@@ -261,6 +276,9 @@ int cfx_create(const cfx_system_desc* d, const cfx_options* opts, cfx_handle** o
     st.hRowDq = rowDq; st.hRowDx = rowDx;
 
     CFX_CUDA(cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking));
+    CFX_CUDA(cudaStreamCreateWithFlags(&st.sideStream, cudaStreamNonBlocking));
+    CFX_CUDA(cudaEventCreateWithFlags(&st.evFork, cudaEventDisableTiming));
+    CFX_CUDA(cudaEventCreateWithFlags(&st.evJoin, cudaEventDisableTiming));
     st.q0 = upload(q0); st.lj = upload(lj); st.ljd = upload(ljd);
     st.termIdx = upload(termIdx); st.termPar = upload(termPar);
     st.qcsrPtr = upload(csrPtr, 2); st.qcsrSlot = upload(csrSlot); st.qcsrCoef = upload(csrCoef);
@@ -326,6 +344,9 @@ void cfx_destroy(cfx_handle* h) {
     if (st.hForce) cudaFreeHost(st.hForce);
     if (st.hEnergy) cudaFreeHost(st.hEnergy);
     for (cudaEvent_t e : st.timeEvents) cudaEventDestroy(e);
+    if (st.evFork) cudaEventDestroy(st.evFork);
+    if (st.evJoin) cudaEventDestroy(st.evJoin);
+    if (st.sideStream) cudaStreamDestroy(st.sideStream);
     if (st.stream) cudaStreamDestroy(st.stream);
     delete h;
 }

@@ -113,6 +113,9 @@ struct State {
     int64_t numKVectors = 0;
 
     cudaStream_t stream = nullptr;      // owned stream for the host-buffer path
+    cudaStream_t sideStream = nullptr;  // direct-space branch runs here, forked/joined inside the step (and its graph)
+    cudaEvent_t evFork = nullptr, evJoin = nullptr;
+    bool overlapBranches = true;
     // parameters (device)
     double* q0 = nullptr;
     float2* lj = nullptr;               // (sigma/2, 2*sqrt(eps)) per user atom, FP32 pair kernel

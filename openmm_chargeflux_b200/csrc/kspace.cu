@@ -197,18 +197,31 @@ __global__ void __launch_bounds__(32*G, (G <= 4) ? 3 : 1) structureFactorKernel(
             for (int c = 0; c < TNP/2; c++) b[c] = bPtr[j*bPitch4 + c];
             const float4 a0 = make_float4(x0.x*y0.x, x0.x*y0.y, x0.y*y0.x, x0.y*y0.y);
             const float4 a1 = make_float4(x1.x*y1.x, x1.x*y1.y, x1.y*y1.x, x1.y*y1.y);
+            // Register-bank layout: the accumulators live in aligned quads (they are stored as float4), the
+            // column phases in aligned quads (LDS.128): zc in even, zs in odd registers. Storing the zs product
+            // FIRST in each accumulator pair makes the two non-reused operands of every FFMA (phase, accumulator)
+            // opposite-parity, i.e. free of register-bank conflicts: acc[2m] += a_m*zs, acc[2m+1] += a_m*zc.
+            const float av0[4] = {a0.x, a0.y, a0.z, a0.w};
+            const float av1[4] = {a1.x, a1.y, a1.z, a1.w};
             #pragma unroll
-            for (int c = 0; c < TN; c++) {
-                const float zc = (c & 1) ? b[c/2].z : b[c/2].x;
-                const float zs = (c & 1) ? b[c/2].w : b[c/2].y;
-                acc[0][c][0] = fmaf(a0.x, zc, acc[0][c][0]);  acc[0][c][1] = fmaf(a0.x, zs, acc[0][c][1]);
-                acc[0][c][2] = fmaf(a0.y, zc, acc[0][c][2]);  acc[0][c][3] = fmaf(a0.y, zs, acc[0][c][3]);
-                acc[0][c][4] = fmaf(a0.z, zc, acc[0][c][4]);  acc[0][c][5] = fmaf(a0.z, zs, acc[0][c][5]);
-                acc[0][c][6] = fmaf(a0.w, zc, acc[0][c][6]);  acc[0][c][7] = fmaf(a0.w, zs, acc[0][c][7]);
-                acc[1][c][0] = fmaf(a1.x, zc, acc[1][c][0]);  acc[1][c][1] = fmaf(a1.x, zs, acc[1][c][1]);
-                acc[1][c][2] = fmaf(a1.y, zc, acc[1][c][2]);  acc[1][c][3] = fmaf(a1.y, zs, acc[1][c][3]);
-                acc[1][c][4] = fmaf(a1.z, zc, acc[1][c][4]);  acc[1][c][5] = fmaf(a1.z, zs, acc[1][c][5]);
-                acc[1][c][6] = fmaf(a1.w, zc, acc[1][c][6]);  acc[1][c][7] = fmaf(a1.w, zs, acc[1][c][7]);
+            for (int m = 0; m < 4; m++) {
+                #pragma unroll
+                for (int c = 0; c < TN; c++) {
+                    const float zc = (c & 1) ? b[c/2].z : b[c/2].x;
+                    const float zs = (c & 1) ? b[c/2].w : b[c/2].y;
+                    acc[0][c][2*m]     = fmaf(av0[m], zs, acc[0][c][2*m]);
+                    acc[0][c][2*m + 1] = fmaf(av0[m], zc, acc[0][c][2*m + 1]);
+                }
+            }
+            #pragma unroll
+            for (int m = 0; m < 4; m++) {
+                #pragma unroll
+                for (int c = 0; c < TN; c++) {
+                    const float zc = (c & 1) ? b[c/2].z : b[c/2].x;
+                    const float zs = (c & 1) ? b[c/2].w : b[c/2].y;
+                    acc[1][c][2*m]     = fmaf(av1[m], zs, acc[1][c][2*m]);
+                    acc[1][c][2*m + 1] = fmaf(av1[m], zc, acc[1][c][2*m + 1]);
+                }
             }
         }
         __syncwarp();
@@ -274,6 +287,8 @@ __global__ void __launch_bounds__(128) coefficientKernel(CoefParams p, long long
             P[k] += __shfl_xor_sync(0xffffffffu, P[k], 1);
             P[k] += __shfl_xor_sync(0xffffffffu, P[k], 2);
         }
+        // stored order is {rcs, rcc, rss, rsc, ics, icc, iss, isc} (zs product first, see the S kernel)
+        { double t; t = P[0]; P[0] = P[1]; P[1] = t; t = P[2]; P[2] = P[3]; P[3] = t; t = P[4]; P[4] = P[5]; P[5] = t; t = P[6]; P[6] = P[7]; P[7] = t; }
         // P = {rcc, rcs, rsc, rss, icc, ics, isc, iss}
         const double kx = nx*p.gx, ky = m*p.gy, kz = l*p.gz;
         const double k2 = kx*kx + ky*ky + kz*kz;
