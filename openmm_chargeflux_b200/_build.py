@@ -32,7 +32,7 @@ def _newer(target, sources):
 
 def build_cuda(force=False, verbose=False):
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    sources = [os.path.join(CSRC, f) for f in ("api.cu", "flux.cu", "kspace.cu", "direct.cu", "md.cu")]
+    sources = [os.path.join(CSRC, f) for f in ("api.cu", "flux.cu", "kspace.cu", "kspace_tc.cu", "direct.cu", "md.cu")]
     deps = sources + [os.path.join(CSRC, "cfx_internal.cuh"), os.path.join(ROOT, "include", "cfx_b200.h")]
     if not force and not _newer(LIB, deps):
         return LIB

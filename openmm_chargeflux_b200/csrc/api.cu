@@ -338,7 +338,7 @@ void cfx_destroy(cfx_handle* h) {
     void* ptrs[] = {st.q0, st.lj, st.ljd, st.termIdx, st.termPar, st.qcsrPtr, st.qcsrSlot, st.qcsrCoef, st.rowDq, st.rowDx, st.exclPairs,
                     st.exclPtr, st.exclCols, st.pos, st.dqSlot, st.rowVal, st.q, st.qf, st.forceFixed, st.dedqFixed, st.energyFixed,
                     st.forceOut, st.energyOut, st.rowS, st.colX, st.colY, st.colZ4, st.sPart, st.gCoef, st.gRowInfo,
-                    st.ks_signedStart, st.pairBuffer};
+                    st.ks_signedStart, st.pairBuffer, st.zSplit, st.coefT, st.gRowData};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (st.hPos) cudaFreeHost(st.hPos);
     if (st.hForce) cudaFreeHost(st.hForce);

@@ -88,6 +88,11 @@ struct KSpacePlan {
     // gather geometry
     int gThreads = 384, gAtoms = 256, gRowsPerWarp = 2, gBuffers = 2, gRowsPerTile = 64, gRowSplits = 1;
     size_t gSmem = 0;
+    // tensor-core gather (kspace_tc.cu): K padded to 8, atom tiles per work unit, columns per coefficient tile
+    bool tensorGather = false;
+    int tKp = 0, tKC = 0, tMT = 2, tNT = 128, tStages = 0, tColTiles = 0;
+    uint32_t tStageBytes = 0, tOffEy = 0, tOffBar = 0;
+    size_t tSmem = 0;
 };
 
 struct CellPlan {
@@ -144,6 +149,9 @@ struct State {
     float4* gCoef = nullptr;            // [numSignedRows][Kz]
     int2* gRowInfo = nullptr;           // [numSignedRows] (nx, ny)
     int* ks_signedStart = nullptr;      // [numRows+1] first signed row of each unsigned row
+    float4* gRowData = nullptr;         // [numSignedRows + pad] (nx, ny, |ny|*Ey stride, sign) for the tensor gather epilogue
+    float* zSplit = nullptr;            // [Npad/128][hi|lo][Kp/4][128][4]  TF32 split of (cos, sin)(2 pi l z), tensor gather operand
+    float* coefT = nullptr;             // [column tile][hi|lo][Kp/4][NT][4]  TF32 split of the gather coefficients, core-matrix layout
     // direct space
     int* cellOfAtom = nullptr; int* cellCount = nullptr; int* cellStart = nullptr; int* cellFill = nullptr;
     float4* userLocal = nullptr;        // [N] local xyz in own cell + q, user order (scratch of the cell build)
@@ -180,6 +188,8 @@ void launchNoCutoff(State& st, const double* dPos, bool forces, bool energy, lon
 void launchFinalize(State& st, const long long* dForce, cudaStream_t s);
 void planKSpace(State& st);
 void launchKSpace(State& st, const double* dPos, bool forces, bool energy, long long* dForce, long long* dDedq, cudaStream_t s);  // piece (3)
+void planKSpaceTensor(State& st);                                                       // kspace_tc.cu
+void launchGatherTensor(State& st, long long* dForce, long long* dDedq, cudaStream_t s);
 void planCells(State& st);
 void launchDirect(State& st, const double* dPos, bool forces, int energyMode /*0 none, 1 FP32 terms, 2 FP64 terms*/, bool emitPairs, long long* dForce, long long* dDedq, cudaStream_t s); // piece (2)
 void mark(State& st, const char* name, cudaStream_t s);   // per-kernel timing marker (no-op unless st.timing)

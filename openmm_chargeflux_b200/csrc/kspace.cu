@@ -20,6 +20,7 @@
 //
 // All main loops are FP32 FMA; cross-CTA reductions, a_k and energies are FP64 / fixed point.
 #include "cfx_internal.cuh"
+#include "ptx_sm100.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -31,40 +32,13 @@ namespace cfx {
 namespace {
 
 // ------------------------------------------------------------------------------------------------
-// PTX helpers: mbarrier + bulk TMA (global -> shared, completion on an mbarrier)
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smemU32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbarInit(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smemU32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbarFenceInit() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbarExpectTx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smemU32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbarWait(uint64_t* bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(smemU32(bar)), "r"(parity) : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void bulkLoad(void* dstSmem, const void* srcGlobal, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(smemU32(dstSmem)), "l"(srcGlobal), "r"(bytes), "r"(smemU32(bar)) : "memory");
-}
-__device__ __forceinline__ void cpAsync16(void* dstSmem, const void* srcGlobal) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smemU32(dstSmem)), "l"(srcGlobal) : "memory");
-}
-__device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cpAsyncWait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
-
-// ------------------------------------------------------------------------------------------------
 // phase tables
 // ------------------------------------------------------------------------------------------------
 struct TableParams {
     int N, Npad, Kx, Ky, Kz, kzPad, zOff, rowPitch;
     int TN, TNP;                 // S-kernel column grouping: |nz| = l lives in slot (l/TN)*TNP + l%TN
     double invLx, invLy, invLz;
+    float* zSplit; int KC;       // tensor gather operand (kspace_tc.cu), nullptr when the FP32 gather is used
 };
 
 // One CTA = 32 atoms x 3 axes (96 working threads). Each thread runs the FP64 recurrence of one (atom, axis);
@@ -98,7 +72,16 @@ __global__ void __launch_bounds__(128) phaseTableKernel(TableParams p, const dou
             row[axis == 2 ? (n/p.TN)*p.TNP + n % p.TN : n] = make_float2(scale*cf, scale*sf);
             if (axis == 0) colX[(size_t) n*p.Npad + atom] = make_float2(cf, sf);
             else if (axis == 1) colY[(size_t) n*p.Npad + atom] = make_float2(cf, sf);
-            else colZ4[(size_t) n*p.Npad + atom] = make_float4(cf, sf, (float) n*cf, (float) n*sf);
+            else {
+                colZ4[(size_t) n*p.Npad + atom] = make_float4(cf, sf, (float) n*cf, (float) n*sf);
+                if (p.zSplit) {
+                    // k = 2n (cos), 2n+1 (sin): [tile][hi|lo][k/4][128 atoms][4]
+                    const float ch = roundTf32(cf), sh = roundTf32(sf);
+                    float* hi = p.zSplit + (((size_t) (atom >> 7)*2*p.KC + (n >> 1))*128 + (atom & 127))*4 + (n & 1)*2;
+                    *reinterpret_cast<float2*>(hi) = make_float2(ch, sh);
+                    *reinterpret_cast<float2*>(hi + (size_t) p.KC*512) = make_float2(roundTf32(cf - ch), roundTf32(sf - sh));
+                }
+            }
             const double cn = c*c1 - sn*s1;
             sn = c*s1 + sn*c1;
             c = cn;
@@ -260,6 +243,7 @@ struct CoefParams {
     double C;                   // 4 pi ke / V
     double invFourAlpha2;
     bool energy, forces;
+    float* coefT; int KC, NT, signedLo;     // tensor gather operand (kspace_tc.cu) or nullptr
 };
 
 __global__ void __launch_bounds__(128) coefficientKernel(CoefParams p, long long* __restrict__ energyFixed) {
@@ -325,6 +309,21 @@ __global__ void __launch_bounds__(128) coefficientKernel(CoefParams p, long long
                 c.z = (float) (-(hpi - hmi));
                 c.w = (float) (hpr - hmr);
                 p.coef[(size_t) (sBase + iy)*p.Kz + l] = c;
+                if (p.coefT) {
+                    // four GEMM columns (Ur, Ui, Vr, Vi) of this signed row, k = 2l (cos), 2l+1 (sin), TF32 hi/lo planes
+                    const double Ar = hpr + hmr, Ai = hpi + hmi, Br = -(hpi - hmi), Bi = hpr - hmr, dl = (double) l;
+                    const double cv[4][2] = {{Ar, Br}, {Ai, Bi}, {dl*Bi, -dl*Ai}, {-dl*Br, dl*Ar}};
+                    const int rl = sBase + iy - p.signedLo, rows = p.NT >> 2;
+                    const int tile = rl/rows, rr = rl - tile*rows;
+                    float* base = p.coefT + (size_t) tile*2*p.KC*p.NT*4 + ((size_t) (l >> 1)*p.NT + rr*4)*4 + (l & 1)*2;
+                    #pragma unroll
+                    for (int comp = 0; comp < 4; comp++) {
+                        const float h0 = roundTf32((float) cv[comp][0]), h1 = roundTf32((float) cv[comp][1]);
+                        *reinterpret_cast<float2*>(base + comp*4) = make_float2(h0, h1);
+                        *reinterpret_cast<float2*>(base + comp*4 + (size_t) p.KC*p.NT*4) =
+                            make_float2(roundTf32((float) (cv[comp][0] - (double) h0)), roundTf32((float) (cv[comp][1] - (double) h1)));
+                    }
+                }
             }
         }
     }
@@ -611,6 +610,7 @@ void planKSpace(State& st) {
     CFX_CUDA(cudaFuncSetAttribute(gatherKernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smemCap));
     CFX_CUDA(cudaFuncSetAttribute(gatherKernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smemCap));
     CFX_CUDA(cudaFuncSetAttribute(gatherKernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smemCap));
+    planKSpaceTensor(st);
 }
 
 void launchKSpace(State& st, const double* dPos, bool forces, bool energy, long long* dForce, long long* dDedq, cudaStream_t s) {
@@ -619,7 +619,8 @@ void launchKSpace(State& st, const double* dPos, bool forces, bool energy, long 
     const int Kx = ks.K[0], Ky = ks.K[1], Kz = ks.K[2];
     const int zOff = ks.rowPitch - ks.kzPad;
     const int TNP = (ks.sTN + 1) & ~1;
-    TableParams tp{st.N, st.Npad, Kx, Ky, Kz, ks.kzPad, zOff, ks.rowPitch, ks.sTN, TNP, 1.0/st.box.L[0], 1.0/st.box.L[1], 1.0/st.box.L[2]};
+    TableParams tp{st.N, st.Npad, Kx, Ky, Kz, ks.kzPad, zOff, ks.rowPitch, ks.sTN, TNP, 1.0/st.box.L[0], 1.0/st.box.L[1], 1.0/st.box.L[2],
+                   (ks.tensorGather && forces) ? st.zSplit : nullptr, ks.tKC};
     phaseTableKernel<<<st.Npad/PT_ATOMS, 128, PT_ATOMS*ks.rowPitch*sizeof(float2), s>>>(tp, dPos, st.qf, st.rowS, st.colX, st.colY, st.colZ4);
     CFX_LAUNCH_CHECK(); st.launches++;
     mark(st, "phase_tables", s);
@@ -653,12 +654,17 @@ void launchKSpace(State& st, const double* dPos, bool forces, bool energy, long 
     cp.C = 4.0/st.box.L[0]/st.box.L[1]/st.box.L[2]*M_PI*CFX_ONE_4PI_EPS0;
     cp.invFourAlpha2 = 0.25/(st.alpha*st.alpha);
     cp.energy = energy; cp.forces = forces;
+    cp.coefT = ks.tensorGather ? st.coefT : nullptr; cp.KC = ks.tKC; cp.NT = ks.tNT; cp.signedLo = ks.signedLo;
     const int items = (ks.rowHi - ks.rowLo)*Kz;
     coefficientKernel<<<(4*items + 127)/128, 128, 0, s>>>(cp, st.energyFixed);
     CFX_LAUNCH_CHECK(); st.launches++;
     mark(st, "kspace_coef", s);
 
-    if (forces && ks.signedHi > ks.signedLo) {
+    if (forces && ks.signedHi > ks.signedLo && ks.tensorGather) {
+        launchGatherTensor(st, dForce, dDedq, s);
+        mark(st, "kspace_gather", s);
+    }
+    else if (forces && ks.signedHi > ks.signedLo) {
         GParams gp;
         gp.coef = st.gCoef; gp.rowInfo = st.gRowInfo; gp.colX = st.colX; gp.colY = st.colY; gp.colZ4 = st.colZ4; gp.qf = st.qf;
         gp.Kx = Kx; gp.Ky = Ky; gp.Kz = Kz; gp.N = st.N; gp.Npad = st.Npad;
