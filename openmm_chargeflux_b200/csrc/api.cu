@@ -338,7 +338,7 @@ void cfx_destroy(cfx_handle* h) {
     void* ptrs[] = {st.q0, st.lj, st.ljd, st.termIdx, st.termPar, st.qcsrPtr, st.qcsrSlot, st.qcsrCoef, st.rowDq, st.rowDx, st.exclPairs,
                     st.exclPtr, st.exclCols, st.pos, st.dqSlot, st.rowVal, st.q, st.qf, st.forceFixed, st.dedqFixed, st.energyFixed,
                     st.forceOut, st.energyOut, st.rowS, st.colX, st.colY, st.colZ4, st.sPart, st.gCoef, st.gRowInfo,
-                    st.ks_signedStart, st.pairBuffer, st.zSplit, st.coefT, st.gRowData};
+                    st.ks_signedStart, st.pairBuffer, st.zSplit, st.coefT, st.gRowData, st.gGroupInfo, st.gtTrace};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (st.hPos) cudaFreeHost(st.hPos);
     if (st.hForce) cudaFreeHost(st.hForce);
@@ -727,3 +727,11 @@ int cfx_measure_fp32_peak(int device, int iters, double* tflops, double* sm_cloc
 }
 
 } // extern "C"
+
+// debug only (not part of include/cfx_b200.h): phase timestamps of the last tensor-gather launch, [148][32] ns
+extern "C" int cfx_debug_gather_trace(cfx_handle* h, unsigned long long* out) {
+    if (!h || !h->st.gtTrace) return CFX_ERR_STATE;
+    cudaSetDevice(h->st.device);
+    cudaDeviceSynchronize();
+    return cudaMemcpy(out, h->st.gtTrace, 148*32*sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess ? CFX_OK : CFX_ERR_CUDA;
+}

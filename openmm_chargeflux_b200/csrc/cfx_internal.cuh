@@ -149,6 +149,8 @@ struct State {
     float4* gCoef = nullptr;            // [numSignedRows][Kz]
     int2* gRowInfo = nullptr;           // [numSignedRows] (nx, ny)
     int* ks_signedStart = nullptr;      // [numRows+1] first signed row of each unsigned row
+    unsigned long long* gtTrace = nullptr;   // debug: per-CTA phase timestamps of the tensor gather (CFX_GT_TRACE)
+    int4* gGroupInfo = nullptr;         // per 8 signed rows from signedLo: Ex offsets of the first / last nx, rows with the first nx
     float4* gRowData = nullptr;         // [numSignedRows + pad] (nx, ny, |ny|*Ey stride, sign) for the tensor gather epilogue
     float* zSplit = nullptr;            // [Npad/128][hi|lo][Kp/4][128][4]  TF32 split of (cos, sin)(2 pi l z), tensor gather operand
     float* coefT = nullptr;             // [column tile][hi|lo][Kp/4][NT][4]  TF32 split of the gather coefficients, core-matrix layout

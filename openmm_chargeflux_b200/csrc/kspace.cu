@@ -75,11 +75,9 @@ __global__ void __launch_bounds__(128) phaseTableKernel(TableParams p, const dou
             else {
                 colZ4[(size_t) n*p.Npad + atom] = make_float4(cf, sf, (float) n*cf, (float) n*sf);
                 if (p.zSplit) {
-                    // k = 2n (cos), 2n+1 (sin): [tile][hi|lo][k/4][128 atoms][4]
-                    const float ch = roundTf32(cf), sh = roundTf32(sf);
-                    float* hi = p.zSplit + (((size_t) (atom >> 7)*2*p.KC + (n >> 1))*128 + (atom & 127))*4 + (n & 1)*2;
-                    *reinterpret_cast<float2*>(hi) = make_float2(ch, sh);
-                    *reinterpret_cast<float2*>(hi + (size_t) p.KC*512) = make_float2(roundTf32(cf - ch), roundTf32(sf - sh));
+                    // k = 2n (cos), 2n+1 (sin): [tile][k/4][128 atoms][4]
+                    float* dst = p.zSplit + (((size_t) (atom >> 7)*p.KC + (n >> 1))*128 + (atom & 127))*4 + (n & 1)*2;
+                    *reinterpret_cast<float2*>(dst) = make_float2(cf, sf);
                 }
             }
             const double cn = c*c1 - sn*s1;
@@ -310,19 +308,15 @@ __global__ void __launch_bounds__(128) coefficientKernel(CoefParams p, long long
                 c.w = (float) (hpr - hmr);
                 p.coef[(size_t) (sBase + iy)*p.Kz + l] = c;
                 if (p.coefT) {
-                    // four GEMM columns (Ur, Ui, Vr, Vi) of this signed row, k = 2l (cos), 2l+1 (sin), TF32 hi/lo planes
+                    // four GEMM columns (Ur, Ui, Vr, Vi) of this signed row, k = 2l (cos), 2l+1 (sin): [tile][k/4][NT][4]
                     const double Ar = hpr + hmr, Ai = hpi + hmi, Br = -(hpi - hmi), Bi = hpr - hmr, dl = (double) l;
                     const double cv[4][2] = {{Ar, Br}, {Ai, Bi}, {dl*Bi, -dl*Ai}, {-dl*Br, dl*Ar}};
                     const int rl = sBase + iy - p.signedLo, rows = p.NT >> 2;
                     const int tile = rl/rows, rr = rl - tile*rows;
-                    float* base = p.coefT + (size_t) tile*2*p.KC*p.NT*4 + ((size_t) (l >> 1)*p.NT + rr*4)*4 + (l & 1)*2;
+                    float* base = p.coefT + (size_t) tile*p.KC*p.NT*4 + ((size_t) (l >> 1)*p.NT + rr*4)*4 + (l & 1)*2;
                     #pragma unroll
-                    for (int comp = 0; comp < 4; comp++) {
-                        const float h0 = roundTf32((float) cv[comp][0]), h1 = roundTf32((float) cv[comp][1]);
-                        *reinterpret_cast<float2*>(base + comp*4) = make_float2(h0, h1);
-                        *reinterpret_cast<float2*>(base + comp*4 + (size_t) p.KC*p.NT*4) =
-                            make_float2(roundTf32((float) (cv[comp][0] - (double) h0)), roundTf32((float) (cv[comp][1] - (double) h1)));
-                    }
+                    for (int comp = 0; comp < 4; comp++)
+                        *reinterpret_cast<float2*>(base + comp*4) = make_float2((float) cv[comp][0], (float) cv[comp][1]);
                 }
             }
         }

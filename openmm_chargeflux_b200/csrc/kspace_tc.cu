@@ -33,44 +33,54 @@ namespace cfx {
 namespace {
 
 inline float __int_as_float_host(int v) { float f; memcpy(&f, &v, 4); return f; }
+__device__ __forceinline__ unsigned long long globalTimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define GT_STAMP(slot) do { if (p.trace && lane == 0) p.trace[blockIdx.x*32 + (slot)] = globalTimer(); } while (0)
 __device__ __forceinline__ void namedBarrier(int id, int threads) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(threads) : "memory"); }
 
-constexpr int GT_THREADS = 64 + 512;        // producer warp, MMA warp, up to 16 epilogue warps
+constexpr int GT_MMA_WARP = 2;               // warps 2-3: MMA issuers, one per accumulator slot
+constexpr int GT_EPI_WARP0 = 4;              // up to 16 epilogue warps (20 warps: 96 registers per thread)
+constexpr int GT_THREADS = (GT_EPI_WARP0 + 16)*32;
 constexpr int GT_TILE_ATOMS = 128;
 
 struct GTParams {
-    const float* zSplit;        // [atom tile][hi|lo][KC][128][4]
-    const float* coefT;         // [column tile][hi|lo][KC][NT][4]
-    const float4* rowData; const float2* colX; const float2* colY; const float* qf;
+    const float* zSplit;        // [atom tile][KC][128][4]   FP32 (cos, sin)(2 pi l z), split into TF32 hi/lo when loaded
+    const float* coefT;         // [column tile][KC][NT][4]  FP32 coefficients in core-matrix order, split in the kernel
+    const float4* rowData; const int4* groupInfo; const float2* colX; const float2* colY; const float* qf;
     int Ky, Kp, KC, N, Npad;
     int signedLo, signedHi, numColTiles, numAtomGroups;
     float fx, fy, fz;
-    int stages;
-    uint32_t stageBytes, offEy, offBar;
+    int rawStages;              // FP32 coefficient tiles in flight (bulk TMA ring)
+    uint32_t planeBytes, offRaw, offEy, offBar, offRd;
+    int dbg;
+    unsigned long long* trace;      // optional [gridDim][32] globaltimer stamps (CFX_GT_TRACE)
 };
 
 template <int MT, int NT>
 __global__ void __launch_bounds__(GT_THREADS, 1) gatherTensorKernel(GTParams p, long long* __restrict__ forceFixed, long long* __restrict__ dedqFixed) {
     constexpr int ROWS = NT/4;                       // signed rows per column tile
     constexpr int SUBS = ROWS/8;                     // epilogue warps per lane quarter, 8 rows each
-    extern __shared__ __align__(1024) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem[];
     float2* Eys = reinterpret_cast<float2*>(smem + p.offEy);                 // [Ky][MT*128], thread-private columns
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.offBar);
-    uint64_t* coefFull = bars;                       // [stages]
-    uint64_t* coefEmpty = bars + p.stages;           // [stages]
-    uint64_t* dFull = bars + 2*p.stages;             // [2]
-    uint64_t* dEmpty = dFull + 2;                    // [2]
-    uint64_t* aFull = dEmpty + 2;                    // [1]
+    uint64_t* rawFull = bars;                        // [rawStages]  TMA -> splitters (the epilogue warps)
+    uint64_t* rawEmpty = bars + p.rawStages;         // [rawStages]  splitters -> TMA
+    uint64_t* opFull = rawEmpty + p.rawStages;       // [2]          splitters -> MMA
+    uint64_t* opEmpty = opFull + 2;                  // [2]          MMA -> splitter
+    uint64_t* dFull = opEmpty + 2;                   // [2]          MMA -> epilogue
+    uint64_t* dEmpty = dFull + 2;                    // [2]          epilogue -> MMA
+    uint64_t* aFull = dEmpty + 2;                    // [1]          epilogue (phase operand in TMEM) -> MMA
     uint32_t* tmemSlot = reinterpret_cast<uint32_t*>(aFull + 1);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long totalUnits = (long long) p.numAtomGroups*p.numColTiles;
-    const int u0 = (int) (totalUnits*blockIdx.x/gridDim.x), u1 = (int) (totalUnits*(blockIdx.x + 1)/gridDim.x);
+    const int u0 = (int) (totalUnits*blockIdx.x/gridDim.x);
+    const int u1 = (p.dbg & 32) ? u0 : (int) (totalUnits*(blockIdx.x + 1)/gridDim.x);
 
     if (tid == 0) {
-        for (int s = 0; s < p.stages; s++) { mbarInit(&coefFull[s], 1); mbarInit(&coefEmpty[s], 1); }
-        for (int d = 0; d < 2; d++) { mbarInit(&dFull[d], 1); mbarInit(&dEmpty[d], 128*SUBS); }
-        mbarInit(aFull, 128*SUBS);
+        for (int s = 0; s < p.rawStages; s++) { mbarInit(&rawFull[s], 1); mbarInit(&rawEmpty[s], 4*SUBS); }
+        for (int b = 0; b < 2; b++) { mbarInit(&opFull[b], 4*SUBS); mbarInit(&opEmpty[b], (MT == 2 && !(p.dbg & 64)) ? 2 : 1); }
+        for (int d = 0; d < 2; d++) { mbarInit(&dFull[d], 1); mbarInit(&dEmpty[d], 4*SUBS); }      // one arrival per epilogue warp
+        mbarInit(aFull, 4*SUBS);
         mbarFenceInit();
     }
     if (warp == 0) tmemAlloc<512>(tmemSlot);
@@ -81,77 +91,98 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gatherTensorKernel(GTParams p, 
     // tensor-memory map: accumulator slots at columns 0 and 128, phase operand from column 256:
     // tile t: hi at 256 + t*2*Kp, lo at 256 + t*2*Kp + Kp
     const uint32_t tmemA = tmem + 256;
+    if (warp == 0) GT_STAMP(0);
 
     if (warp == 0) {
         // ---------------- producer ----------------
-        if (lane == 0) {
-            int s = 0; uint32_t ph = 0;
+        // one lane keeps rawStages FP32 coefficient tiles in flight (bulk TMA); a stage is refilled as soon as the
+        // epilogue warps have split it into the TF32 operand planes
+        if (lane == 0 && !(p.dbg & 8)) {
+            const uint32_t planeFloats = p.planeBytes/4;
+            unsigned char* raw = smem + p.offRaw;
+            int rs = 0; uint32_t rph = 0;
             for (int unit = u0; unit < u1; unit++) {
-                const int colTile = unit % p.numColTiles;
-                mbarWait(&coefEmpty[s], ph ^ 1);
-                mbarExpectTx(&coefFull[s], p.stageBytes);
-                bulkLoad(smem + (size_t) s*p.stageBytes, p.coefT + (size_t) colTile*(p.stageBytes/4), p.stageBytes, &coefFull[s]);
-                if (++s == p.stages) { s = 0; ph ^= 1; }
+                if (unit - u0 >= p.rawStages) mbarWait(&rawEmpty[rs], rph ^ 1);
+                mbarExpectTx(&rawFull[rs], p.planeBytes);
+                bulkLoad(raw + (size_t) rs*p.planeBytes, p.coefT + (size_t) (unit % p.numColTiles)*planeFloats, p.planeBytes, &rawFull[rs]);
+                if (++rs == p.rawStages) { rs = 0; rph ^= 1; }
             }
         }
         __syncwarp();
     }
-    else if (warp == 1) {
-        // ---------------- MMA issuer ----------------
-        if (lane == 0) {
-            constexpr uint32_t idesc = ummaIdescTf32(128, NT);
-            const uint32_t planeBytes = (uint32_t) p.KC*NT*16;           // one hi or lo plane of a stage
-            int s = 0; uint32_t ph = 0, aPh = 0;
-            int curGroup = -1;
-            uint32_t seq = 0;
-            for (int unit = u0; unit < u1; unit++) {
-                const int group = unit/p.numColTiles;
-                if (group != curGroup) {
-                    curGroup = group;
-                    mbarWait(aFull, aPh); aPh ^= 1;
-                    tcgen05FenceAfter();
-                }
-                mbarWait(&coefFull[s], ph);
+    else if (warp == GT_MMA_WARP || (warp == GT_MMA_WARP + 1 && !(p.dbg & 64))) {
+        // ---------------- MMA issuers ----------------
+        // Two warps, one per accumulator slot (seq parity), so that the per-tile bookkeeping of one overlaps the
+        // issue of the other: the tensor pipe idles whenever nobody is issuing.
+        const uint32_t mySlot = warp - GT_MMA_WARP;
+        // The whole warp runs the (warp-uniform) control flow so that descriptors live in uniform registers;
+        // one elected lane issues the tensor-core instructions.
+        constexpr uint32_t idesc = ummaIdescTf32(128, NT);
+        const uint32_t planeBytes = p.planeBytes;                    // one hi or lo plane of an operand buffer
+        const int k8n = p.Kp >> 3;
+        int ob = 0; uint32_t oph = 0, aPh = 0;
+        int curGroup = -1;
+        uint32_t seq = 0;
+        for (int unit = u0; unit < u1; unit++) {
+            const int group = unit/p.numColTiles;
+            if (p.dbg & 8) continue;
+            if (group != curGroup) {
+                curGroup = group;
+                mbarWait(aFull, aPh); aPh ^= 1;
+                GT_STAMP(aPh ? 20 : 21);
+            }
+            if (seq == 20) GT_STAMP(28);
+            mbarWait(&opFull[ob], oph);
+            if (seq == 20) GT_STAMP(29);
+            tcgen05FenceAfter();
+            const uint32_t stageAddr = smemU32(smem) + (uint32_t) ob*2*planeBytes;
+            const uint64_t bHi = ummaSmemDesc(stageAddr, NT*16, 128), bLo = ummaSmemDesc(stageAddr + planeBytes, NT*16, 128);
+            bool issued = false;
+            #pragma unroll 1
+            for (int t = 0; t < MT; t++, seq++) {
+                const uint32_t d = seq & 1;
+                if (d != mySlot && !(p.dbg & 64)) continue;
+                issued = true;
+                if (seq == 20) GT_STAMP(22);
+                mbarWait(&dEmpty[d], ((seq >> 1) & 1) ^ 1);
+                if (seq == 20) GT_STAMP(23);
                 tcgen05FenceAfter();
-                const uint32_t stageAddr = smemU32(smem + (size_t) s*p.stageBytes);
-                #pragma unroll 1
-                for (int t = 0; t < MT; t++, seq++) {
-                    const uint32_t d = seq & 1;
-                    mbarWait(&dEmpty[d], ((seq >> 1) & 1) ^ 1);
-                    tcgen05FenceAfter();
-                    const uint32_t tD = tmem + d*128;
-                    const uint32_t aHi = tmemA + (uint32_t) t*2*p.Kp, aLo = aHi + p.Kp;
-                    uint32_t acc = 0;
-                    // small products first: Zlo Chi, Zhi Clo, then Zhi Chi
+                const uint32_t tD = tmem + d*128;
+                const uint32_t aHi = tmemA + (uint32_t) t*2*p.Kp, aLo = aHi + p.Kp;
+                if (!(p.dbg & 2) && electOne()) {
+                    // small products first: Zlo Chi, Zhi Clo, then Zhi Chi; one k8 step advances the
+                    // descriptor by two core-matrix columns (2*NT*16 bytes) and the phase operand by 8 columns
                     #pragma unroll 1
-                    for (int pass = 0; pass < 3; pass++) {
-                        const uint32_t a = pass == 0 ? aLo : aHi;
-                        const uint32_t b = stageAddr + (pass == 1 ? planeBytes : 0);
-                        for (int k8 = 0; k8 < p.Kp/8; k8++) {
-                            ummaTf32TS(tD, a + k8*8, ummaSmemDesc(b + (uint32_t) k8*2*NT*16, NT*16, 128), idesc, acc);
-                            acc = 1;
-                        }
-                    }
-                    ummaCommit(&dFull[d]);
+                    for (int k8 = 0; k8 < k8n; k8++) ummaTf32TS(tD, aLo + 8*k8, bHi + (uint64_t) (k8*(2*NT*16 >> 4)), idesc, k8 > 0);
+                    #pragma unroll 1
+                    for (int k8 = 0; k8 < k8n; k8++) ummaTf32TS(tD, aHi + 8*k8, bLo + (uint64_t) (k8*(2*NT*16 >> 4)), idesc, 1);
+                    #pragma unroll 1
+                    for (int k8 = 0; k8 < k8n; k8++) ummaTf32TS(tD, aHi + 8*k8, bHi + (uint64_t) (k8*(2*NT*16 >> 4)), idesc, 1);
                 }
-                ummaCommit(&coefEmpty[s]);            // the stage is free once these MMAs have read it
-                if (++s == p.stages) { s = 0; ph ^= 1; }
+                __syncwarp();
+                if (seq == 18 || seq == 20) GT_STAMP(seq == 18 ? 24 : 25);
+                if (electOne()) ummaCommit(&dFull[d]);
             }
+            if (issued && electOne()) ummaCommit(&opEmpty[ob]);   // the operand buffer is free once these MMAs have read it
+            __syncwarp();
+            if (++ob == 2) { ob = 0; oph ^= 1; }
         }
-        __syncwarp();
     }
-    else if (warp - 2 < 4*SUBS) {
+    else if (warp >= GT_EPI_WARP0 && warp - GT_EPI_WARP0 < 4*SUBS) {
         // ---------------- epilogue: thread = (tensor-memory lane = atom of the tile, group of 8 rows) ----------------
         const int q4 = warp & 3;                                  // lane quarter this warp may access
-        const int sub = (warp - 2) >> 2;                          // which 8 rows (32 accumulator columns) of the tile
+        const int sub = (warp - GT_EPI_WARP0) >> 2;                          // which 8 rows (32 accumulator columns) of the tile
         const int atomInTile = q4*32 + lane;
         const uint32_t laneBase = (uint32_t) (q4*32) << 16;
         constexpr int EPI_THREADS = 128*SUBS;
-        float oD[MT], oX[MT], oY[MT], oZ[MT], nxOf[MT];
-        float2 ex[MT];
+        float oD[MT], oX[MT], oY[MT], oZ[MT];
+        float2 ex0[MT], ex1[MT], ex0n[MT], ex1n[MT];        // Ex of the first / last row of this warp's 8 rows: current unit, next unit
+        float4* rdS = reinterpret_cast<float4*>(smem + p.offRd) + (warp - GT_EPI_WARP0)*16;    // [2][8] row data of this warp's rows
+
         int curGroup = -1;
         uint32_t seq = 0;
         auto flush = [&]() {
+            if (p.dbg & 16) return;
             #pragma unroll
             for (int t = 0; t < MT; t++) {
                 const int atom = (curGroup*MT + t)*GT_TILE_ATOMS + atomInTile;
@@ -164,53 +195,120 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gatherTensorKernel(GTParams p, 
                 }
             }
         };
+        // this warp's share of splitting the coefficient tile of unit v into the TF32 hi / lo operand planes
+        const uint32_t eid = (warp - GT_EPI_WARP0)*32 + lane, planeVec = p.planeBytes/16;
+        auto splitUnit = [&](int v) {
+            const int k = v - u0, rs = k % p.rawStages, ob = k & 1;
+            mbarWait(&rawFull[rs], (k/p.rawStages) & 1);
+            mbarWait(&opEmpty[ob], ((k >> 1) & 1) ^ 1);             // the MMAs that read this operand buffer are complete
+            const float4* src = reinterpret_cast<const float4*>(smem + p.offRaw + (size_t) rs*p.planeBytes);
+            float4* hi = reinterpret_cast<float4*>(smem + (size_t) ob*2*p.planeBytes);
+            float4* lo = hi + planeVec;
+            #pragma unroll 1
+            for (uint32_t e = eid; e < planeVec; e += 2*EPI_THREADS) {          // two independent 16-byte chunks per pass
+                const bool two = e + EPI_THREADS < planeVec;
+                const float4 a = src[e], b = two ? src[e + EPI_THREADS] : a;
+                float4 h, l;
+                splitTf32(a, h, l); hi[e] = h; lo[e] = l;
+                if (two) { splitTf32(b, h, l); hi[e + EPI_THREADS] = h; lo[e + EPI_THREADS] = l; }
+            }
+            fenceProxyAsync();                                    // operand planes visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) { mbarArrive(&opFull[ob]); mbarArrive(&rawEmpty[rs]); }
+        };
+        int buf = 0, cc = 0;
+        if (u0 < u1 && !(p.dbg & 8)) splitUnit(u0);
+        if (u0 < u1) {
+            const int group0 = u0/p.numColTiles, g8 = (u0 - group0*p.numColTiles)*SUBS + sub;
+            const int4 gi = __ldg(p.groupInfo + g8);
+            if (lane < 8) rdS[lane] = __ldg(p.rowData + p.signedLo + 8*g8 + lane);
+            #pragma unroll
+            for (int t = 0; t < MT; t++) {
+                const float2* exCol = p.colX + (group0*MT + t)*GT_TILE_ATOMS + atomInTile;
+                ex0[t] = __ldg(exCol + gi.x); ex1[t] = __ldg(exCol + gi.y);
+            }
+            cc = gi.z;
+            __syncwarp();
+        }
         for (int unit = u0; unit < u1; unit++) {
-            const int group = unit/p.numColTiles, colTile = unit - group*p.numColTiles;
+            const int group = unit/p.numColTiles;
             if (group != curGroup) {
+                const int gs = (curGroup < 0) ? 1 : 8;
+                if (warp == GT_EPI_WARP0) GT_STAMP(gs);
                 if (curGroup >= 0) flush();
-                namedBarrier(1, EPI_THREADS);                     // every epilogue warp is done with the old Ey columns
+                if (warp == GT_EPI_WARP0) GT_STAMP(gs + 1);
+                namedBarrier(1, EPI_THREADS);
+                if (warp == GT_EPI_WARP0) GT_STAMP(gs + 2);                     // every epilogue warp is done with the old Ey columns
                 curGroup = group;
                 // phase operand of the new atom group -> tensor memory (all MMAs that read the old one are
                 // complete: their last accumulator has been consumed), Ey columns -> shared memory
                 #pragma unroll
                 for (int t = 0; t < MT; t++) {
                     const int tile = group*MT + t;
-                    const float4* src = reinterpret_cast<const float4*>(p.zSplit) + (size_t) tile*2*p.KC*GT_TILE_ATOMS + atomInTile;
+                    const float4* src = reinterpret_cast<const float4*>(p.zSplit) + (size_t) tile*p.KC*GT_TILE_ATOMS + atomInTile;
                     const uint32_t dst = tmemA + (uint32_t) t*2*p.Kp + laneBase;
-                    for (int c = sub; c < 2*p.KC; c += SUBS) tmemStore4(dst + 4*c, src[(size_t) c*GT_TILE_ATOMS]);   // hi plane then lo plane
-                    const int atom = tile*GT_TILE_ATOMS + atomInTile;
-                    for (int m = sub; m < p.Ky; m += SUBS) Eys[m*(MT*GT_TILE_ATOMS) + t*GT_TILE_ATOMS + atomInTile] = p.colY[(size_t) m*p.Npad + atom];
-                    oD[t] = 0.f; oX[t] = 0.f; oY[t] = 0.f; oZ[t] = 0.f; ex[t] = make_float2(0.f, 0.f); nxOf[t] = -1.f;
+                    for (int c0 = sub; c0 < p.KC; c0 += 4*SUBS) {               // loads batched ahead of the ordered tensor-memory stores
+                        float4 buf[4];
+                        #pragma unroll
+                        for (int j = 0; j < 4; j++) if (c0 + j*SUBS < p.KC) buf[j] = __ldg(src + (size_t) (c0 + j*SUBS)*GT_TILE_ATOMS);
+                        #pragma unroll
+                        for (int j = 0; j < 4; j++) if (c0 + j*SUBS < p.KC) {
+                            const float4 v = buf[j];
+                            float4 h, l;
+                            splitTf32(v, h, l);
+                            tmemStore4(dst + 4*(c0 + j*SUBS), h);
+                            tmemStore4(dst + p.Kp + 4*(c0 + j*SUBS), l);
+                        }
+                    }
+                    const float2* eySrc = p.colY + tile*GT_TILE_ATOMS + atomInTile;
+                    float2* eyDst = Eys + t*GT_TILE_ATOMS + atomInTile;
+                    #pragma unroll 4
+                    for (int m = sub; m < p.Ky; m += SUBS) eyDst[m*(MT*GT_TILE_ATOMS)] = __ldg(eySrc + (size_t) m*p.Npad);
+                    oD[t] = 0.f; oX[t] = 0.f; oY[t] = 0.f; oZ[t] = 0.f;
                 }
+                if (warp == GT_EPI_WARP0) GT_STAMP(gs + 3);
                 tmemWaitStore();
                 tcgen05FenceBefore();
-                mbarArrive(aFull);
+                __syncwarp();
+                if (lane == 0) mbarArrive(aFull);
+                if (warp == GT_EPI_WARP0) GT_STAMP(gs + 4);
                 namedBarrier(1, EPI_THREADS);                     // Ey columns complete
+                if (warp == GT_EPI_WARP0) GT_STAMP(gs + 5);
             }
-            const float4* rd = p.rowData + p.signedLo + colTile*ROWS + 8*sub;
+            if (p.dbg & 8) continue;
+            if (unit + 1 < u1) splitUnit(unit + 1);
+            // row data / Ex of the NEXT unit are fetched while this one is processed (no exposed global latency)
+            const int unitN = (unit + 1 < u1) ? unit + 1 : unit;
+            const int groupN = unitN/p.numColTiles, g8N = (unitN - groupN*p.numColTiles)*SUBS + sub;
+            const int4 giN = __ldg(p.groupInfo + g8N);
+            float4 rdN = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (lane < 8) rdN = __ldg(p.rowData + p.signedLo + 8*g8N + lane);
             #pragma unroll
             for (int t = 0; t < MT; t++, seq++) {
                 const uint32_t d = seq & 1;
                 mbarWait(&dFull[d], (seq >> 1) & 1);
+                if (warp == GT_EPI_WARP0 && seq == 18) GT_STAMP(26);
+                if (warp == GT_EPI_WARP0 && seq == 19) GT_STAMP(19);
+                if (warp == GT_EPI_WARP0 && seq == 20) GT_STAMP(7);
                 tcgen05FenceAfter();
                 float v[32];
                 tmemLoad32(tmem + d*128 + laneBase + 32*sub, v);
                 tcgen05FenceBefore();
-                mbarArrive(&dEmpty[d]);                           // values are in registers: the slot can be refilled
-                const int atom = (group*MT + t)*GT_TILE_ATOMS + atomInTile;
-                const float2* eyCol = Eys + t*GT_TILE_ATOMS + atomInTile;
+                __syncwarp();
+                if (lane == 0) mbarArrive(&dEmpty[d]);            // values are in registers: the slot can be refilled
+                if (warp == GT_EPI_WARP0 && seq == 18) GT_STAMP(27);
+                const char* eyCol = reinterpret_cast<const char*>(Eys + t*GT_TILE_ATOMS + atomInTile);
+                if (p.dbg & 1) { oD[t] += v[0] + v[31]; continue; }
+                const float4* rd = rdS + buf*8;
                 #pragma unroll
                 for (int i = 0; i < 8; i++) {
-                    // padding rows beyond signedHi have zero coefficients (U = V = 0) and row data (0,0,0,1)
-                    const float4 r = __ldg(rd + i);               // (nx, ny, |ny|*stride as int bits, sign of ny)
-                    if (r.x != nxOf[t]) {
-                        nxOf[t] = r.x;
-                        ex[t] = p.colX[(size_t) ((int) r.x)*p.Npad + atom];
-                    }
-                    float2 ey = eyCol[__float_as_int(r.z)];
-                    ey.y *= r.w;
-                    const float tr = ex[t].x*ey.x - ex[t].y*ey.y;
-                    const float ti = ex[t].x*ey.y + ex[t].y*ey.x;
+                    // padding rows beyond signedHi have zero coefficients (U = V = 0) and zero row data
+                    const float4 r = rd[i];                       // (nx, ny, byte offset of Ey(|ny|), -)
+                    const float exx = (i < cc) ? ex0[t].x : ex1[t].x, exy = (i < cc) ? ex0[t].y : ex1[t].y;
+                    float2 ey = *reinterpret_cast<const float2*>(eyCol + __float_as_uint(r.z));
+                    ey.y = __uint_as_float(__float_as_uint(ey.y) ^ (__float_as_uint(r.y) & 0x80000000u));     // Ey(-m) = conj Ey(m)
+                    const float tr = exx*ey.x - exy*ey.y;
+                    const float ti = exx*ey.y + exy*ey.x;
                     const float ur = v[4*i], ui = v[4*i+1], vr = v[4*i+2], vi = v[4*i+3];
                     oD[t] = fmaf(tr, ur, oD[t]);  oD[t] = fmaf(-ti, ui, oD[t]);
                     const float im = tr*ui + ti*ur;
@@ -218,12 +316,30 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gatherTensorKernel(GTParams p, 
                     oY[t] = fmaf(r.y, im, oY[t]);
                     oZ[t] = fmaf(tr, vi, oZ[t]);  oZ[t] = fmaf(ti, vr, oZ[t]);
                 }
+                if (warp == GT_EPI_WARP0 && (seq == 18 || seq == 19)) GT_STAMP(seq == 18 ? 8 : 9);
+                if (t == 0) {
+                    #pragma unroll
+                    for (int tt = 0; tt < MT; tt++) {
+                        const float2* exCol = p.colX + (groupN*MT + tt)*GT_TILE_ATOMS + atomInTile;
+                        ex0n[tt] = __ldg(exCol + giN.x);
+                        ex1n[tt] = __ldg(exCol + giN.y);
+                    }
+                }
             }
+            buf ^= 1;
+            if (lane < 8) rdS[buf*8 + lane] = rdN;
+            __syncwarp();
+            cc = giN.z;
+            #pragma unroll
+            for (int t = 0; t < MT; t++) { ex0[t] = ex0n[t]; ex1[t] = ex1n[t]; }
         }
+        if (warp == GT_EPI_WARP0) GT_STAMP(16);
         if (curGroup >= 0) flush();
+        if (warp == GT_EPI_WARP0) GT_STAMP(17);
     }
     tcgen05FenceBefore();
     __syncthreads();
+    if (warp == 0) GT_STAMP(18);
     if (warp == 0) tmemFree<512>(tmem);
 }
 
@@ -239,57 +355,75 @@ void planKSpaceTensor(State& st) {
     if (mode && !strcmp(mode, "fp32")) return;
     const int Kz = ks.K[2], Ky = ks.K[1];
     const int Kp = (2*Kz + 7)/8*8;
-    if (Kp > 112) return;                                        // phase operand must fit 2 x 224 tensor-memory columns
+    if (Kp > 112 || Ky < 8) return;                              // (a group of 8 rows must not span three nx values)                                        // phase operand must fit 2 x 224 tensor-memory columns
     ks.tKp = Kp; ks.tKC = Kp/4;
     ks.tMT = (Kp <= 56) ? 2 : 1;
     ks.tNT = (Kp <= 56) ? 128 : 64;
-    const size_t stageBytes = (size_t) 2*ks.tKC*ks.tNT*16;
+    const size_t planeBytes = (size_t) ks.tKC*ks.tNT*16;         // one FP32 / TF32-hi / TF32-lo plane of a coefficient tile
     const size_t eyBytes = ((size_t) Ky*ks.tMT*GT_TILE_ATOMS*sizeof(float2) + 127) & ~(size_t) 127;
-    const size_t cap = 227*1024 - 1024;                          // alignment slack of the dynamic shared-memory base
-    int stages = (int) std::min<size_t>(4, (cap - eyBytes - 256)/stageBytes);
-    if (stages < 2) return;
-    ks.tStages = stages;
-    ks.tStageBytes = (uint32_t) stageBytes;
-    ks.tOffEy = (uint32_t) (stages*stageBytes);
+    const size_t tailBytes = 256 + 16*16*sizeof(float4);          // barriers + per-warp row-data slots
+    const size_t cap = 227*1024 - 256;
+    if (4*planeBytes + eyBytes + tailBytes > cap) return;         // operand double buffer (hi+lo) needs 4 planes
+    const int rawStages = (int) std::min<size_t>(4, (cap - 4*planeBytes - eyBytes - tailBytes)/planeBytes);
+    if (rawStages < 2) return;
+    ks.tStages = rawStages;
+    ks.tStageBytes = (uint32_t) planeBytes;
+    ks.tOffEy = (uint32_t) ((4 + rawStages)*planeBytes);
     ks.tOffBar = (uint32_t) (ks.tOffEy + eyBytes);
-    ks.tSmem = ks.tOffBar + 256;
+    ks.tSmem = ks.tOffBar + tailBytes;
     const int rows = ks.tNT/4;
     const int signedHere = std::max(ks.signedHi - ks.signedLo, 1);
     ks.tColTiles = (signedHere + rows - 1)/rows;
-    const size_t zFloats = (size_t) (st.Npad/GT_TILE_ATOMS)*2*ks.tKC*GT_TILE_ATOMS*4;
-    const size_t cFloats = (size_t) ks.tColTiles*2*ks.tKC*ks.tNT*4;
+    const size_t zFloats = (size_t) (st.Npad/GT_TILE_ATOMS)*ks.tKC*GT_TILE_ATOMS*4;
+    const size_t cFloats = (size_t) ks.tColTiles*ks.tKC*ks.tNT*4;
     CFX_CUDA(cudaMalloc(&st.zSplit, zFloats*sizeof(float)));
     CFX_CUDA(cudaMemset(st.zSplit, 0, zFloats*sizeof(float)));
     CFX_CUDA(cudaMalloc(&st.coefT, cFloats*sizeof(float)));
     CFX_CUDA(cudaMemset(st.coefT, 0, cFloats*sizeof(float)));
-    // per signed row: (nx, ny, |ny| * Ey column stride, sign of ny), same order as gRowInfo, zero-padded
+    // per signed row: (nx, ny, byte offset of Ey(|ny|) in the shared columns, -), gRowInfo order, zero-padded; and per
+    // group of 8 rows counted from signedLo: (Ex offset of the first row's nx, of the last real row's nx, rows with the first nx)
     {
         const int Kx = ks.K[0];
         std::vector<float4> rd;
+        std::vector<int> rowNx;
         const int stride = ks.tMT*GT_TILE_ATOMS;
         for (int row = 0; row < Kx*Ky; row++) {
             const int nx = row/Ky, m = row % Ky;
-            rd.push_back(make_float4((float) nx, (float) m, __int_as_float_host(m*stride), 1.f));
-            if (nx > 0 && m > 0) rd.push_back(make_float4((float) nx, (float) -m, __int_as_float_host(m*stride), -1.f));
+            rd.push_back(make_float4((float) nx, (float) m, __int_as_float_host(m*stride*8), 0.f)); rowNx.push_back(nx);
+            if (nx > 0 && m > 0) { rd.push_back(make_float4((float) nx, (float) -m, __int_as_float_host(m*stride*8), 0.f)); rowNx.push_back(nx); }
         }
-        for (int k = 0; k < 64; k++) rd.push_back(make_float4(0.f, 0.f, __int_as_float_host(0), 1.f));
+        for (int k = 0; k < 64; k++) rd.push_back(make_float4(0.f, 0.f, 0.f, 0.f));
+        std::vector<int4> gi((size_t) ks.tColTiles*(ks.tNT/32) + 1);
+        for (size_t g = 0; g < gi.size(); g++) {
+            const int r0 = std::min(ks.signedLo + 8*(int) g, std::max(ks.signedHi - 1, 0));
+            const int r7 = std::min(ks.signedLo + 8*(int) g + 7, std::max(ks.signedHi - 1, 0));
+            int c = 0;
+            for (int r = ks.signedLo + 8*(int) g; r < ks.signedLo + 8*(int) g + 8; r++) if (r >= ks.signedHi || rowNx[std::min(r, (int) rowNx.size() - 1)] == rowNx[r0]) c++; else break;
+            gi[g] = make_int4(rowNx[r0]*st.Npad, rowNx[r7]*st.Npad, c, 0);
+        }
         CFX_CUDA(cudaMalloc(&st.gRowData, rd.size()*sizeof(float4)));
         CFX_CUDA(cudaMemcpy(st.gRowData, rd.data(), rd.size()*sizeof(float4), cudaMemcpyHostToDevice));
+        CFX_CUDA(cudaMalloc(&st.gGroupInfo, gi.size()*sizeof(int4)));
+        CFX_CUDA(cudaMemcpy(st.gGroupInfo, gi.data(), gi.size()*sizeof(int4), cudaMemcpyHostToDevice));
     }
     CFX_CUDA(cudaFuncSetAttribute(gatherTensorKernel<2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024));
     CFX_CUDA(cudaFuncSetAttribute(gatherTensorKernel<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024));
+    if (getenv("CFX_GT_TRACE")) { CFX_CUDA(cudaMalloc(&st.gtTrace, 148*32*8)); CFX_CUDA(cudaMemset(st.gtTrace, 0, 148*32*8)); }
     ks.tensorGather = true;
 }
 
 void launchGatherTensor(State& st, long long* dForce, long long* dDedq, cudaStream_t s) {
     KSpacePlan& ks = st.ks;
     GTParams gp;
-    gp.zSplit = st.zSplit; gp.coefT = st.coefT; gp.rowData = st.gRowData; gp.colX = st.colX; gp.colY = st.colY; gp.qf = st.qf;
+    gp.zSplit = st.zSplit; gp.coefT = st.coefT; gp.rowData = st.gRowData; gp.groupInfo = st.gGroupInfo; gp.colX = st.colX; gp.colY = st.colY; gp.qf = st.qf;
     gp.Ky = ks.K[1]; gp.Kp = ks.tKp; gp.KC = ks.tKC; gp.N = st.N; gp.Npad = st.Npad;
     gp.signedLo = ks.signedLo; gp.signedHi = ks.signedHi; gp.numColTiles = ks.tColTiles;
     gp.numAtomGroups = st.Npad/(GT_TILE_ATOMS*ks.tMT);
     gp.fx = (float) (2*M_PI/st.box.L[0]); gp.fy = (float) (2*M_PI/st.box.L[1]); gp.fz = (float) (2*M_PI/st.box.L[2]);
-    gp.stages = ks.tStages; gp.stageBytes = ks.tStageBytes; gp.offEy = ks.tOffEy; gp.offBar = ks.tOffBar;
+    gp.dbg = getenv("CFX_GT_DEBUG") ? atoi(getenv("CFX_GT_DEBUG")) : 0;
+    gp.trace = nullptr;
+    gp.trace = st.gtTrace;
+    gp.rawStages = ks.tStages; gp.planeBytes = ks.tStageBytes; gp.offRaw = 4*ks.tStageBytes; gp.offEy = ks.tOffEy; gp.offBar = ks.tOffBar; gp.offRd = ks.tOffBar + 256;
     int numSM = 148;
     cudaDeviceGetAttribute(&numSM, cudaDevAttrMultiProcessorCount, st.device);
     const long long units = (long long) gp.numAtomGroups*gp.numColTiles;

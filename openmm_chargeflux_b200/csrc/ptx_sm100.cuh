@@ -42,6 +42,17 @@ __device__ __forceinline__ void fenceProxyAsync() { asm volatile("fence.proxy.as
 // ---- TF32 split ----
 __device__ __forceinline__ float roundTf32(float x) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return __uint_as_float(r); }
 
+// x = hi + lo with hi, lo representable in TF32 (round to nearest, ties away, finite inputs): the integer form of
+// cvt.rna.tf32.f32 without its inf/nan handling
+__device__ __forceinline__ void splitTf32(float x, float& hi, float& lo) {
+    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+    const float r = x - hi;
+    lo = __uint_as_float((__float_as_uint(r) + 0x1000u) & 0xFFFFE000u);
+}
+__device__ __forceinline__ void splitTf32(const float4& v, float4& h, float4& l) {
+    splitTf32(v.x, h.x, l.x); splitTf32(v.y, h.y, l.y); splitTf32(v.z, h.z, l.z); splitTf32(v.w, h.w, l.w);
+}
+
 // ---- tcgen05: tensor memory ----
 template <int COLS> __device__ __forceinline__ void tmemAlloc(uint32_t* slotInSmem) {       // whole warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smemU32(slotInSmem)), "n"(COLS) : "memory");
@@ -71,6 +82,13 @@ __device__ __forceinline__ void tmemStore4(uint32_t taddr, float4 v) {
                  :: "r"(taddr), "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)), "r"(__float_as_uint(v.w)) : "memory");
 }
 __device__ __forceinline__ void tmemWaitStore() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// one lane of a converged warp
+__device__ __forceinline__ bool electOne() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 
 // ---- tcgen05: MMA ----
 // Shared-memory operand descriptor, K-major, no swizzle: core matrix = 8 rows x 16 bytes, contiguous (128 B).

@@ -197,8 +197,9 @@ __global__ void __launch_bounds__(128) gemmTestTS(const float* __restrict__ A, c
 }
 
 // throughput: every CTA issues `iters` MMAs of 128 x 256 x 8 on the same operands
+template <int N, bool TS>
 __global__ void __launch_bounds__(128) peakTest(int iters, float* sink) {
-    constexpr int M = 128, N = 256;
+    constexpr int M = 128;
     extern __shared__ __align__(128) unsigned char smem[];
     float* a = reinterpret_cast<float*>(smem);        // [2][M][4]
     float* b = a + 2*M*4;                              // [2][N][4]
@@ -206,6 +207,7 @@ __global__ void __launch_bounds__(128) peakTest(int iters, float* sink) {
     __shared__ uint32_t tmemBase;
     const int tid = threadIdx.x, warp = tid >> 5;
     for (int e = tid; e < 2*M*4 + 2*N*4; e += 128) a[e] = toTf32(0.001f*(e % 97));
+    // (the TS variant reads whatever is in tensor-memory columns 256..263: timing only)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (tid == 0) { mbarInit(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     if (warp == 0) {
@@ -219,7 +221,10 @@ __global__ void __launch_bounds__(128) peakTest(int iters, float* sink) {
     if (tid == 0) {
         constexpr uint32_t idesc = makeIdescTf32(M, N);
         const uint64_t ad = makeDesc(smemAddr(a), M*16, 128), bd = makeDesc(smemAddr(b), N*16, 128);
-        for (int i = 0; i < iters; i++) ummaTf32(tmem + (i & 1)*256, ad, bd, idesc, i > 1);
+        for (int i = 0; i < iters; i++) {
+            if (TS) ummaTf32TS(tmem + (i & 1)*N, tmem + 256 + 8*(i % 7), bd, idesc, i > 1);
+            else ummaTf32(tmem + (i & 1)*N, ad, bd, idesc, i > 1);
+        }
         ummaCommit(&bar);
     }
     mbarWait(&bar, 0);
@@ -303,13 +308,15 @@ int main() {
     const size_t smem = (2*128*4 + 2*256*4)*4;
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     const int iters = 20000;
-    for (int rep = 0; rep < 3; rep++) {
-        CK(cudaEventRecord(e0));
-        peakTest<<<prop.multiProcessorCount, 128, smem>>>(iters, sink);
-        CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
-        float ms; cudaEventElapsedTime(&ms, e0, e1);
-        printf("tcgen05.mma kind::tf32 128x256x8, %d CTAs x %d MMAs: %.3f ms = %.1f TFLOP/s\n", prop.multiProcessorCount, iters, ms,
-               2.0*128*256*8*(double) iters*prop.multiProcessorCount/ms*1e-9);
+#define PEAK(NN, TSV) \
+    for (int rep = 0; rep < 2; rep++) { \
+        CK(cudaEventRecord(e0)); \
+        peakTest<NN, TSV><<<prop.multiProcessorCount, 128, smem>>>(iters, sink); \
+        CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); \
+        float ms; cudaEventElapsedTime(&ms, e0, e1); \
+        if (rep) printf("tcgen05.mma kind::tf32 128x%dx8 %s: %.3f ms, %.1f ns per MMA, %.1f TFLOP/s\n", NN, TSV ? "A in TMEM" : "A in smem", ms, \
+               ms*1e6/iters, 2.0*128*NN*8*(double) iters*prop.multiProcessorCount/ms*1e-9); \
     }
+    PEAK(256, false) PEAK(256, true) PEAK(128, false) PEAK(128, true) PEAK(64, false) PEAK(64, true)
     return 0;
 }
