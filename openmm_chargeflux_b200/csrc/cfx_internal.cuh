@@ -72,22 +72,32 @@ __device__ __forceinline__ double blockSum(double v, double* scratch) {
 // ---------------------------------------------------------------------------------------------
 struct Box { double L[3]; double invL[3]; };
 
+// geometry of one structure-factor kernel: |nz| slot layout of the per-atom phase rows, grid, shared memory
+struct SGeom {
+    int TN = 7, NC = 0;          // TN columns per warp, NC column groups (FP32 kernel); |nz| = l lives in slot (l/TN)*TNP + l%TN
+    int kzPad = 0, rowPitch = 0; // padded |nz| slots; float2 per atom row in rowS: Kx + Ky + kzPad
+    int threads = 128, rowTiles = 0, splits = 0, atomsPerSplit = 0, stages = 3;
+    size_t smem = 0;
+};
+
 struct KSpacePlan {
     int K[3] = {0, 0, 0};        // kmax per axis (reference: nk in [0,K) / (-K,K))
-    int rowPitch = 0;            // float2 per atom row in rowS: Kx + Ky + KzPad
-    int kzPad = 0;               // Kz rounded up to the S kernel's column tile
     int numRows = 0;             // unsigned rows (nx, |ny|): Kx*Ky
     int numSignedRows = 0;       // gather rows (nx, ny): Ky + (Kx-1)*(2Ky-1)
-    // S kernel geometry
-    int sThreads = 128, sTN = 7, sNC = 0, sRowTiles = 0, sSplits = 0, sAtomsPerSplit = 0;   // TN columns per warp, NC column groups
-    int sStages = 3;
-    size_t sSmem = 0;
+    // structure-factor kernels: FP32 CUDA-core kernel (used whenever the reciprocal energy is requested: it sums with
+    // round-to-nearest) and the tensor-core kernel (forces-only evaluations; the tensor core truncates on accumulation,
+    // which biases |S|^2 by ~2e-7)
+    SGeom sF, sT;
+    bool fp32S = false;
     // shard of the unsigned rows this rank owns [rowLo, rowHi) (k-vector sharding)
     int rowLo = 0, rowHi = 0;
     int signedLo = 0, signedHi = 0;
     // gather geometry
     int gThreads = 384, gAtoms = 256, gRowsPerWarp = 2, gBuffers = 2, gRowsPerTile = 64, gRowSplits = 1;
     size_t gSmem = 0;
+    // tensor-core structure factors (kspace_tc.cu)
+    bool tensorS = false;
+    uint32_t tsRowStageBytes = 0, tsOffA = 0, tsOffB = 0, tsOffBar = 0;
     // tensor-core gather (kspace_tc.cu): K padded to 8, atom tiles per work unit, columns per coefficient tile
     bool tensorGather = false;
     int tKp = 0, tKC = 0, tMT = 2, tNT = 128, tStages = 0, tColTiles = 0;
@@ -190,6 +200,9 @@ void launchNoCutoff(State& st, const double* dPos, bool forces, bool energy, lon
 void launchFinalize(State& st, const long long* dForce, cudaStream_t s);
 void planKSpace(State& st);
 void launchKSpace(State& st, const double* dPos, bool forces, bool energy, long long* dForce, long long* dDedq, cudaStream_t s);  // piece (3)
+bool structureTensorEligible(const State& st);                                          // kspace_tc.cu
+void planStructureTensor(State& st);
+void launchStructureTensor(State& st, cudaStream_t s);
 void planKSpaceTensor(State& st);                                                       // kspace_tc.cu
 void launchGatherTensor(State& st, long long* dForce, long long* dDedq, cudaStream_t s);
 void planCells(State& st);

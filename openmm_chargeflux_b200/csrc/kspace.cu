@@ -240,7 +240,7 @@ struct CoefParams {
     double gx, gy, gz;          // 2 pi / L
     double C;                   // 4 pi ke / V
     double invFourAlpha2;
-    bool energy, forces;
+    bool energy, forces, swapPairs;
     float* coefT; int KC, NT, signedLo;     // tensor gather operand (kspace_tc.cu) or nullptr
 };
 
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(128) coefficientKernel(CoefParams p, long long
             P[k] += __shfl_xor_sync(0xffffffffu, P[k], 2);
         }
         // stored order is {rcs, rcc, rss, rsc, ics, icc, iss, isc} (zs product first, see the S kernel)
-        { double t; t = P[0]; P[0] = P[1]; P[1] = t; t = P[2]; P[2] = P[3]; P[3] = t; t = P[4]; P[4] = P[5]; P[5] = t; t = P[6]; P[6] = P[7]; P[7] = t; }
+        if (p.swapPairs) { double t; t = P[0]; P[0] = P[1]; P[1] = t; t = P[2]; P[2] = P[3]; P[3] = t; t = P[4]; P[4] = P[5]; P[5] = t; t = P[6]; P[6] = P[7]; P[7] = t; }
         // P = {rcc, rcs, rsc, rss, icc, ics, isc, iss}
         const double kx = nx*p.gx, ky = m*p.gy, kz = l*p.gz;
         const double k2 = kx*kx + ky*ky + kz*kz;
@@ -511,6 +511,7 @@ size_t gatherSmem(int Kx, int Ky, int Kz, int BA, int rowTile, int nbuf, size_t*
 // ------------------------------------------------------------------------------------------------
 void planKSpace(State& st) {
     KSpacePlan& ks = st.ks;
+    SGeom& f = ks.sF;
     const int Kx = ks.K[0], Ky = ks.K[1], Kz = ks.K[2];
     // S kernel: 2 rows per lane, TN in {6,7,8} columns per warp; pick the TN with the least column
     // padding (ties -> larger TN), at most S_MAX_WARPS column groups per CTA
@@ -518,36 +519,39 @@ void planKSpace(State& st) {
     for (int tn = 6; tn <= 8; tn++) {
         const int g = (Kz + tn - 1)/tn;
         const int pad = g*tn - Kz;
-        if (pad <= bestPad) { bestPad = pad; ks.sTN = tn; ks.sNC = g; }
+        if (pad <= bestPad) { bestPad = pad; f.TN = tn; f.NC = g; }
     }
-    if (ks.sNC > S_MAX_WARPS) throw std::runtime_error("kmax along z too large for the structure-factor kernel (|nz| <= 64)");
-    const int TNP = (ks.sTN + 1) & ~1;
-    ks.kzPad = ks.sNC*TNP;
+    ks.tensorS = structureTensorEligible(st);
+    ks.fp32S = f.NC <= S_MAX_WARPS;
+    if (!ks.fp32S && !ks.tensorS) throw std::runtime_error("kmax along z too large for the structure-factor kernels (|nz| <= 64)");
+    const int TNP = (f.TN + 1) & ~1;
+    f.kzPad = f.NC*TNP;
     const int zOff = (Kx + Ky + 1) & ~1;
-    ks.rowPitch = zOff + ks.kzPad;
+    f.rowPitch = zOff + f.kzPad;
     ks.numRows = Kx*Ky;
     // shard the unsigned rows over ranks (k-vector sharding)
     ks.rowLo = (int) ((int64_t) ks.numRows*st.shardRank/st.shardCount);
     ks.rowHi = (int) ((int64_t) ks.numRows*(st.shardRank + 1)/st.shardCount);
     const int rowsHere = ks.rowHi - ks.rowLo;
-    ks.sThreads = 32*ks.sNC;
-    ks.sRowTiles = (std::max(rowsHere, 1) + S_BM - 1)/S_BM;
-    ks.sStages = 3;
-    const size_t stageBytes = (size_t) S_ATOMS_PER_STAGE*ks.rowPitch*sizeof(float2);
-    ks.sSmem = 128 + ks.sStages*stageBytes;
+    f.threads = 32*f.NC;
+    f.rowTiles = (std::max(rowsHere, 1) + S_BM - 1)/S_BM;
+    f.stages = 3;
+    const size_t stageBytes = (size_t) S_ATOMS_PER_STAGE*f.rowPitch*sizeof(float2);
+    f.smem = 128 + f.stages*stageBytes;
     // atom splits: fill the resident CTA slots (shared memory allows 2-3 CTAs per SM)
     int numSM = 148;
     cudaDeviceGetAttribute(&numSM, cudaDevAttrMultiProcessorCount, st.device);
-    const int ctasPerSM = std::max(1, std::min(4, (int) ((size_t) 220*1024/(ks.sSmem + 1024))));
+    const int ctasPerSM = std::max(1, std::min(4, (int) ((size_t) 220*1024/(f.smem + 1024))));
     const int slots = ctasPerSM*numSM;
-    int splits = std::max(1, slots/std::max(1, ks.sRowTiles));
+    int splits = std::max(1, slots/std::max(1, f.rowTiles));
     const int maxSplits = std::max(1, st.Npad/(4*S_ATOMS_PER_STAGE));       // >= 4 stages per CTA
     splits = std::min(splits, maxSplits);
     int aps = (st.Npad + splits - 1)/splits;
     aps = (aps + S_ATOMS_PER_STAGE - 1)/S_ATOMS_PER_STAGE*S_ATOMS_PER_STAGE;
     splits = (st.Npad + aps - 1)/aps;
-    ks.sSplits = splits;
-    ks.sAtomsPerSplit = aps;
+    f.splits = splits;
+    f.atomsPerSplit = aps;
+    if (ks.tensorS) planStructureTensor(st);                     // fills ks.sT
     // signed rows
     std::vector<int> signedStart(ks.numRows + 1, 0);
     std::vector<int2> rowInfo;
@@ -563,11 +567,14 @@ void planKSpace(State& st) {
     ks.signedHi = signedStart[ks.rowHi];
     for (int k = 0; k < G_MAX_ROW_TILE; k++) rowInfo.push_back(make_int2(0, 0));   // padding rows (zero coefficients)
 
-    CFX_CUDA(cudaMalloc(&st.rowS, (size_t) st.Npad*ks.rowPitch*sizeof(float2)));
+    const SGeom& t = ks.sT;
+    const size_t maxPitch = std::max(f.rowPitch, ks.tensorS ? t.rowPitch : 0);
+    CFX_CUDA(cudaMalloc(&st.rowS, (size_t) st.Npad*maxPitch*sizeof(float2)));
     CFX_CUDA(cudaMalloc(&st.colX, (size_t) Kx*st.Npad*sizeof(float2)));
     CFX_CUDA(cudaMalloc(&st.colY, (size_t) Ky*st.Npad*sizeof(float2)));
     CFX_CUDA(cudaMalloc(&st.colZ4, (size_t) Kz*st.Npad*sizeof(float4)));
-    CFX_CUDA(cudaMalloc(&st.sPart, (size_t) ks.sSplits*ks.numRows*ks.kzPad*8*sizeof(float)));
+    const size_t partSlots = std::max((size_t) f.splits*f.kzPad, ks.tensorS ? (size_t) t.splits*t.kzPad : (size_t) 0);
+    CFX_CUDA(cudaMalloc(&st.sPart, partSlots*ks.numRows*8*sizeof(float)));
     const size_t coefElems = (size_t) (ks.numSignedRows + G_MAX_ROW_TILE)*Kz;
     CFX_CUDA(cudaMalloc(&st.gCoef, coefElems*sizeof(float4)));
     CFX_CUDA(cudaMemset(st.gCoef, 0, coefElems*sizeof(float4)));
@@ -594,13 +601,13 @@ void planKSpace(State& st) {
     ks.gRowsPerTile = (std::max(signedHere, 1) + gRowTile - 1)/gRowTile;          // row tiles per atom tile
     ks.gRowSplits = numSM;                                                        // persistent grid size
 
-    CFX_CUDA(cudaFuncSetAttribute(phaseTableKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (PT_ATOMS*ks.rowPitch*sizeof(float2))));
-    CFX_CUDA(cudaFuncSetAttribute(structureFactorKernel<6, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ks.sSmem));
-    CFX_CUDA(cudaFuncSetAttribute(structureFactorKernel<7, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ks.sSmem));
-    CFX_CUDA(cudaFuncSetAttribute(structureFactorKernel<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ks.sSmem));
-    CFX_CUDA(cudaFuncSetAttribute(structureFactorKernel<6, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ks.sSmem));
-    CFX_CUDA(cudaFuncSetAttribute(structureFactorKernel<7, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ks.sSmem));
-    CFX_CUDA(cudaFuncSetAttribute(structureFactorKernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ks.sSmem));
+    CFX_CUDA(cudaFuncSetAttribute(phaseTableKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (PT_ATOMS*maxPitch*sizeof(float2))));
+    CFX_CUDA(cudaFuncSetAttribute(structureFactorKernel<6, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) f.smem));
+    CFX_CUDA(cudaFuncSetAttribute(structureFactorKernel<7, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) f.smem));
+    CFX_CUDA(cudaFuncSetAttribute(structureFactorKernel<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) f.smem));
+    CFX_CUDA(cudaFuncSetAttribute(structureFactorKernel<6, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) f.smem));
+    CFX_CUDA(cudaFuncSetAttribute(structureFactorKernel<7, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) f.smem));
+    CFX_CUDA(cudaFuncSetAttribute(structureFactorKernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) f.smem));
     CFX_CUDA(cudaFuncSetAttribute(gatherKernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smemCap));
     CFX_CUDA(cudaFuncSetAttribute(gatherKernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smemCap));
     CFX_CUDA(cudaFuncSetAttribute(gatherKernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smemCap));
@@ -610,44 +617,48 @@ void planKSpace(State& st) {
 void launchKSpace(State& st, const double* dPos, bool forces, bool energy, long long* dForce, long long* dDedq, cudaStream_t s) {
     KSpacePlan& ks = st.ks;
     if (!forces && !energy) return;
+    // the reciprocal energy needs round-to-nearest sums: FP32 kernel whenever it is requested
+    const bool useTensorS = ks.tensorS && (!energy || !ks.fp32S);
+    const SGeom& g = useTensorS ? ks.sT : ks.sF;
     const int Kx = ks.K[0], Ky = ks.K[1], Kz = ks.K[2];
-    const int zOff = ks.rowPitch - ks.kzPad;
-    const int TNP = (ks.sTN + 1) & ~1;
-    TableParams tp{st.N, st.Npad, Kx, Ky, Kz, ks.kzPad, zOff, ks.rowPitch, ks.sTN, TNP, 1.0/st.box.L[0], 1.0/st.box.L[1], 1.0/st.box.L[2],
+    const int zOff = g.rowPitch - g.kzPad;
+    const int TNP = (g.TN + 1) & ~1;
+    TableParams tp{st.N, st.Npad, Kx, Ky, Kz, g.kzPad, zOff, g.rowPitch, g.TN, TNP, 1.0/st.box.L[0], 1.0/st.box.L[1], 1.0/st.box.L[2],
                    (ks.tensorGather && forces) ? st.zSplit : nullptr, ks.tKC};
-    phaseTableKernel<<<st.Npad/PT_ATOMS, 128, PT_ATOMS*ks.rowPitch*sizeof(float2), s>>>(tp, dPos, st.qf, st.rowS, st.colX, st.colY, st.colZ4);
+    phaseTableKernel<<<st.Npad/PT_ATOMS, 128, PT_ATOMS*g.rowPitch*sizeof(float2), s>>>(tp, dPos, st.qf, st.rowS, st.colX, st.colY, st.colZ4);
     CFX_LAUNCH_CHECK(); st.launches++;
     mark(st, "phase_tables", s);
     if (ks.rowHi <= ks.rowLo) return;
 
     SParams sp;
     sp.rowS = st.rowS; sp.part = st.sPart;
-    sp.rowPitch = ks.rowPitch; sp.Kx = Kx; sp.Ky = Ky; sp.zOff = zOff; sp.kzPad = ks.kzPad;
-    sp.stages = ks.sStages;
+    sp.rowPitch = g.rowPitch; sp.Kx = Kx; sp.Ky = Ky; sp.zOff = zOff; sp.kzPad = g.kzPad;
+    sp.stages = g.stages;
     sp.rowLo = ks.rowLo; sp.rowHi = ks.rowHi; sp.numRows = ks.numRows;
-    sp.atomsPerSplit = ks.sAtomsPerSplit; sp.Npad = st.Npad;
-    const dim3 sGrid(ks.sRowTiles, ks.sSplits);
-    if (ks.sNC <= 4) {
-        if (ks.sTN == 6)      structureFactorKernel<6, 4><<<sGrid, ks.sThreads, ks.sSmem, s>>>(sp);
-        else if (ks.sTN == 7) structureFactorKernel<7, 4><<<sGrid, ks.sThreads, ks.sSmem, s>>>(sp);
-        else                  structureFactorKernel<8, 4><<<sGrid, ks.sThreads, ks.sSmem, s>>>(sp);
+    sp.atomsPerSplit = g.atomsPerSplit; sp.Npad = st.Npad;
+    const dim3 sGrid(g.rowTiles, g.splits);
+    if (useTensorS) launchStructureTensor(st, s);
+    else if (g.NC <= 4) {
+        if (g.TN == 6)      structureFactorKernel<6, 4><<<sGrid, g.threads, g.smem, s>>>(sp);
+        else if (g.TN == 7) structureFactorKernel<7, 4><<<sGrid, g.threads, g.smem, s>>>(sp);
+        else                  structureFactorKernel<8, 4><<<sGrid, g.threads, g.smem, s>>>(sp);
     }
     else {
-        if (ks.sTN == 6)      structureFactorKernel<6, 8><<<sGrid, ks.sThreads, ks.sSmem, s>>>(sp);
-        else if (ks.sTN == 7) structureFactorKernel<7, 8><<<sGrid, ks.sThreads, ks.sSmem, s>>>(sp);
-        else                  structureFactorKernel<8, 8><<<sGrid, ks.sThreads, ks.sSmem, s>>>(sp);
+        if (g.TN == 6)      structureFactorKernel<6, 8><<<sGrid, g.threads, g.smem, s>>>(sp);
+        else if (g.TN == 7) structureFactorKernel<7, 8><<<sGrid, g.threads, g.smem, s>>>(sp);
+        else                  structureFactorKernel<8, 8><<<sGrid, g.threads, g.smem, s>>>(sp);
     }
-    CFX_LAUNCH_CHECK(); st.launches++;
+    if (!useTensorS) { CFX_LAUNCH_CHECK(); st.launches++; }
     mark(st, "structure_factor", s);
 
     CoefParams cp;
     cp.part = st.sPart; cp.coef = st.gCoef; cp.signedStart = st.ks_signedStart;
-    cp.Kx = Kx; cp.Ky = Ky; cp.Kz = Kz; cp.kzPad = ks.kzPad; cp.numRows = ks.numRows; cp.splits = ks.sSplits;
-    cp.rowLo = ks.rowLo; cp.rowHi = ks.rowHi; cp.TN = ks.sTN; cp.TNP = TNP;
+    cp.Kx = Kx; cp.Ky = Ky; cp.Kz = Kz; cp.kzPad = g.kzPad; cp.numRows = ks.numRows; cp.splits = g.splits;
+    cp.rowLo = ks.rowLo; cp.rowHi = ks.rowHi; cp.TN = g.TN; cp.TNP = TNP;
     cp.gx = 2*M_PI/st.box.L[0]; cp.gy = 2*M_PI/st.box.L[1]; cp.gz = 2*M_PI/st.box.L[2];
     cp.C = 4.0/st.box.L[0]/st.box.L[1]/st.box.L[2]*M_PI*CFX_ONE_4PI_EPS0;
     cp.invFourAlpha2 = 0.25/(st.alpha*st.alpha);
-    cp.energy = energy; cp.forces = forces;
+    cp.energy = energy; cp.forces = forces; cp.swapPairs = !useTensorS;
     cp.coefT = ks.tensorGather ? st.coefT : nullptr; cp.KC = ks.tKC; cp.NT = ks.tNT; cp.signedLo = ks.signedLo;
     const int items = (ks.rowHi - ks.rowLo)*Kz;
     coefficientKernel<<<(4*items + 127)/128, 128, 0, s>>>(cp, st.energyFixed);

@@ -343,6 +343,207 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gatherTensorKernel(GTParams p, 
     if (warp == 0) tmemFree<512>(tmem);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// structure factors on the tensor cores
+// ------------------------------------------------------------------------------------------------
+// P[(comp, row)][(l, c|s)] = sum_atoms A[(comp,row)][atom] * Z[(l,c|s)][atom] with the row operand
+// A = (xr*yc, xr*ys, xi*yc, xi*ys), x = q Ex(nx), y = Ey(|ny|): a [128 x atoms] x [atoms x 64] GEMM per tile of 32
+// unsigned rows, K = atoms. A and Z are formed (products, TF32 hi/lo split) by CUDA-core warps from the per-atom phase
+// rows that arrive by bulk TMA, written to shared memory in the K-major core-matrix layout, multiplied by
+// tcgen05.mma kind::tf32 (three products, small ones first) into tensor memory, and -- because the tensor core
+// truncates on accumulation -- taken out after every 32 atoms and summed in FP32 registers with round-to-nearest.
+// One CTA = 2 row tiles (64 rows) x one split of the atoms.
+constexpr int ST_ATOMS = 32;                 // atoms per stage = 4 MMA k-steps
+constexpr int ST_TILES = 2;                  // row tiles (of 32 rows) per CTA
+constexpr int ST_FORM_WARPS = 8, ST_EPI_WARPS = 8;
+constexpr int ST_FORM_WARP0 = 2, ST_EPI_WARP0 = ST_FORM_WARP0 + ST_FORM_WARPS;
+constexpr int ST_THREADS = (ST_EPI_WARP0 + ST_EPI_WARPS)*32;
+constexpr int ST_N = 64;                     // GEMM N: 2*Kz padded
+constexpr uint32_t ST_A_PLANE = (ST_ATOMS/4)*128*16;      // bytes of one hi or lo plane of one row tile
+constexpr uint32_t ST_B_PLANE = (ST_ATOMS/4)*ST_N*16;
+
+struct STParams {
+    const float2* rowS; float* part;
+    int rowPitch, Kx, Ky, Kz, zOff, kzPad;
+    int rowLo, rowHi, numRows;
+    int atomsPerSplit, Npad;
+    uint32_t rowStageBytes, offA, offB, offBar;
+};
+
+__global__ void __launch_bounds__(ST_THREADS, 1) structureFactorTensorKernel(STParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    // [2 row stages][2 operand buffers: A (tiles x hi|lo planes)][2 operand buffers: B (hi|lo)][barriers]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.offBar);
+    uint64_t* rowsFull = bars;           // [2] TMA -> formers
+    uint64_t* rowsEmpty = bars + 2;      // [2] formers -> TMA
+    uint64_t* abFull = bars + 4;         // [2] formers -> MMA
+    uint64_t* abEmpty = bars + 6;        // [2] MMA -> formers
+    uint64_t* dFull = bars + 8;          // [2] MMA -> epilogue
+    uint64_t* dEmpty = bars + 10;        // [2] epilogue -> MMA
+    uint32_t* tmemSlot = reinterpret_cast<uint32_t*>(bars + 12);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rowBase = p.rowLo + blockIdx.x*(32*ST_TILES);
+    const int atomBegin = blockIdx.y*p.atomsPerSplit;
+    const int atomEnd = min(atomBegin + p.atomsPerSplit, p.Npad);
+    const int numStages = (atomEnd - atomBegin)/ST_ATOMS;
+
+    if (tid == 0) {
+        for (int i = 0; i < 2; i++) {
+            mbarInit(&rowsFull[i], 1); mbarInit(&rowsEmpty[i], ST_FORM_WARPS);
+            mbarInit(&abFull[i], ST_FORM_WARPS); mbarInit(&abEmpty[i], 1);
+            mbarInit(&dFull[i], 1); mbarInit(&dEmpty[i], ST_EPI_WARPS);
+        }
+        mbarFenceInit();
+    }
+    if (warp == 0) tmemAlloc<256>(tmemSlot);
+    tcgen05FenceBefore();
+    __syncthreads();
+    tcgen05FenceAfter();
+    const uint32_t tmem = *tmemSlot;
+
+    if (warp == 0) {
+        // ---------------- producer: per-atom phase rows, 32 atoms per stage ----------------
+        if (lane == 0) {
+            for (int st = 0; st < numStages; st++) {
+                const int b = st & 1;
+                if (st >= 2) mbarWait(&rowsEmpty[b], ((st >> 1) & 1) ^ 1);
+                mbarExpectTx(&rowsFull[b], p.rowStageBytes);
+                bulkLoad(smem + (size_t) b*p.rowStageBytes, p.rowS + (size_t) (atomBegin + st*ST_ATOMS)*p.rowPitch, p.rowStageBytes, &rowsFull[b]);
+            }
+        }
+        __syncwarp();
+    }
+    else if (warp == 1) {
+        // ---------------- MMA issuer (warp-uniform control flow, one elected lane issues) ----------------
+        constexpr uint32_t idesc = ummaIdescTf32(128, ST_N);
+        for (int st = 0; st < numStages; st++) {
+            const int b = st & 1;
+            const uint32_t ph = (st >> 1) & 1;
+            mbarWait(&abFull[b], ph);
+            mbarWait(&dEmpty[b], ph ^ 1);
+            tcgen05FenceAfter();
+            const uint32_t aBase = smemU32(smem) + p.offA + (uint32_t) b*(ST_TILES*2*ST_A_PLANE);
+            const uint32_t bBase = smemU32(smem) + p.offB + (uint32_t) b*(2*ST_B_PLANE);
+            const uint64_t bHi = ummaSmemDesc(bBase, ST_N*16, 128), bLo = ummaSmemDesc(bBase + ST_B_PLANE, ST_N*16, 128);
+            if (electOne()) {
+                #pragma unroll
+                for (int t = 0; t < ST_TILES; t++) {
+                    const uint32_t tD = tmem + (uint32_t) b*(ST_TILES*ST_N) + t*ST_N;
+                    const uint64_t aHi = ummaSmemDesc(aBase + t*2*ST_A_PLANE, 128*16, 128), aLo = ummaSmemDesc(aBase + t*2*ST_A_PLANE + ST_A_PLANE, 128*16, 128);
+                    // one k-step = 8 atoms = two 16-byte chunk columns: 2*128*16 bytes of A, 2*64*16 bytes of Z
+                    #pragma unroll
+                    for (int k8 = 0; k8 < ST_ATOMS/8; k8++) ummaTf32SS(tD, aLo + (uint64_t) (k8*(2*128*16 >> 4)), bHi + (uint64_t) (k8*(2*ST_N*16 >> 4)), idesc, k8 > 0);
+                    #pragma unroll
+                    for (int k8 = 0; k8 < ST_ATOMS/8; k8++) ummaTf32SS(tD, aHi + (uint64_t) (k8*(2*128*16 >> 4)), bLo + (uint64_t) (k8*(2*ST_N*16 >> 4)), idesc, 1);
+                    #pragma unroll
+                    for (int k8 = 0; k8 < ST_ATOMS/8; k8++) ummaTf32SS(tD, aHi + (uint64_t) (k8*(2*128*16 >> 4)), bHi + (uint64_t) (k8*(2*ST_N*16 >> 4)), idesc, 1);
+                }
+                ummaCommit(&abEmpty[b]);
+                ummaCommit(&dFull[b]);
+            }
+            __syncwarp();
+        }
+    }
+    else if (warp < ST_EPI_WARP0) {
+        // ---------------- formers: row operand A (products) and column operand Z, TF32 hi/lo planes ----------------
+        const int ft = tid - ST_FORM_WARP0*32;                     // 0..255
+        // A item: (row r of the 64, quad of 4 atoms); two quads per thread
+        const int r = ft & 63, qd0 = ft >> 6;                      // quads qd0 and qd0 + 4
+        const int row = rowBase + r;
+        const bool rowValid = row < p.rowHi;
+        const int nx = rowValid ? row/p.Ky : 0, m = rowValid ? row - nx*p.Ky : 0;
+        const uint32_t aOff = (uint32_t) (r >> 5)*(2*ST_A_PLANE) + (uint32_t) (r & 31)*16;     // + quad*128*16 + comp*32*16
+        // Z item: (l = ft & 31, quad = ft >> 5)
+        const int zl = ft & 31, zq = ft >> 5;
+        for (int st = 0; st < numStages; st++) {
+            const int b = st & 1;
+            const uint32_t ph = (st >> 1) & 1;
+            mbarWait(&rowsFull[b], ph);
+            mbarWait(&abEmpty[b], ph ^ 1);                        // the MMAs that read this operand buffer are complete
+            const float2* rows = reinterpret_cast<const float2*>(smem + (size_t) b*p.rowStageBytes);
+            unsigned char* aBuf = smem + p.offA + (size_t) b*(ST_TILES*2*ST_A_PLANE);
+            unsigned char* bBuf = smem + p.offB + (size_t) b*(2*ST_B_PLANE);
+            #pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int qd = qd0 + 4*h;
+                float4 pc[4];                                      // per comp: 4 atoms
+                #pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const float2* ar = rows + (size_t) (4*qd + j)*p.rowPitch;
+                    const float2 x = ar[nx], y = ar[p.Kx + m];
+                    const float v0 = x.x*y.x, v1 = x.x*y.y, v2 = x.y*y.x, v3 = x.y*y.y;
+                    (&pc[0].x)[j] = v0; (&pc[1].x)[j] = v1; (&pc[2].x)[j] = v2; (&pc[3].x)[j] = v3;
+                }
+                #pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    float4 hi, lo;
+                    if (rowValid) splitTf32(pc[c], hi, lo);
+                    else { hi = make_float4(0.f, 0.f, 0.f, 0.f); lo = hi; }
+                    unsigned char* dst = aBuf + aOff + (uint32_t) qd*(128*16) + (uint32_t) c*(32*16);
+                    *reinterpret_cast<float4*>(dst) = hi;
+                    *reinterpret_cast<float4*>(dst + ST_A_PLANE) = lo;
+                }
+            }
+            {
+                float4 zc, zs;
+                #pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const float2 z = (zl < p.Kz) ? rows[(size_t) (4*zq + j)*p.rowPitch + p.zOff + zl] : make_float2(0.f, 0.f);
+                    (&zc.x)[j] = z.x; (&zs.x)[j] = z.y;
+                }
+                float4 hi, lo;
+                unsigned char* dst = bBuf + (uint32_t) zq*(ST_N*16) + (uint32_t) (2*zl)*16;
+                splitTf32(zc, hi, lo);
+                *reinterpret_cast<float4*>(dst) = hi; *reinterpret_cast<float4*>(dst + ST_B_PLANE) = lo;
+                splitTf32(zs, hi, lo);
+                *reinterpret_cast<float4*>(dst + 16) = hi; *reinterpret_cast<float4*>(dst + 16 + ST_B_PLANE) = lo;
+            }
+            fenceProxyAsync();                                    // operands visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) { mbarArrive(&abFull[b]); mbarArrive(&rowsEmpty[b]); }
+        }
+    }
+    else {
+        // ---------------- epilogue: FP32 running sums, thread = (row tile, tensor-memory lane = (comp, row)) ----------------
+        const int e = warp - ST_EPI_WARP0;
+        const int q4 = warp & 3, t = e >> 2;                      // lane quarter = comp, row tile
+        const uint32_t laneBase = (uint32_t) (q4*32) << 16;
+        float acc[ST_N];
+        #pragma unroll
+        for (int i = 0; i < ST_N; i++) acc[i] = 0.f;
+        for (int st = 0; st < numStages; st++) {
+            const int b = st & 1;
+            mbarWait(&dFull[b], (st >> 1) & 1);
+            tcgen05FenceAfter();
+            const uint32_t tD = tmem + (uint32_t) b*(ST_TILES*ST_N) + t*ST_N + laneBase;
+            #pragma unroll
+            for (int c = 0; c < ST_N/16; c++) {
+                float v[16];
+                tmemLoad16(tD + 16*c, v);
+                if (c == ST_N/16 - 1) {                           // all columns are in registers: the slot can be refilled
+                    tcgen05FenceBefore();
+                    __syncwarp();
+                    if (lane == 0) mbarArrive(&dEmpty[b]);
+                }
+                #pragma unroll
+                for (int i = 0; i < 16; i++) acc[16*c + i] += v[i];
+            }
+        }
+        const int row = rowBase + t*32 + lane;
+        if (row < p.rowHi) {
+            float* out = p.part + (((size_t) blockIdx.y*p.numRows + row)*p.kzPad)*8 + q4*2;
+            #pragma unroll
+            for (int l = 0; l < ST_N/2; l++)
+                if (l < p.Kz) *reinterpret_cast<float2*>(out + (size_t) l*8) = make_float2(acc[2*l], acc[2*l + 1]);
+        }
+    }
+    tcgen05FenceBefore();
+    __syncthreads();
+    if (warp == 0) tmemFree<256>(tmem);
+}
+
 } // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -430,6 +631,53 @@ void launchGatherTensor(State& st, long long* dForce, long long* dDedq, cudaStre
     const int grid = (int) std::min<long long>(numSM, units);
     if (ks.tMT == 2) gatherTensorKernel<2, 128><<<grid, GT_THREADS, ks.tSmem, s>>>(gp, dForce, dDedq);
     else             gatherTensorKernel<1, 64><<<grid, GT_THREADS, ks.tSmem, s>>>(gp, dForce, dDedq);
+    CFX_LAUNCH_CHECK(); st.launches++;
+}
+
+// ---- structure factors ----
+bool structureTensorEligible(const State& st) {
+    const char* mode = getenv("CFX_KSPACE_S");                  // "fp32" forces the CUDA-core kernel (A/B measurements)
+    if (mode && !strcmp(mode, "fp32")) return false;
+    return st.ks.K[2] <= 32;                                    // 2*Kz columns must fit one N = 64 MMA
+}
+
+void planStructureTensor(State& st) {
+    KSpacePlan& ks = st.ks;
+    SGeom& t = ks.sT;
+    int numSM = 148;
+    cudaDeviceGetAttribute(&numSM, cudaDevAttrMultiProcessorCount, st.device);
+    t.TN = 32; t.NC = 1; t.kzPad = 32;                          // identity |nz| slots, 32 of them (GEMM N = 64)
+    t.rowPitch = ((ks.K[0] + ks.K[1] + 1) & ~1) + t.kzPad;
+    const int rowsHere = std::max(ks.rowHi - ks.rowLo, 1);
+    t.rowTiles = (rowsHere + 32*ST_TILES - 1)/(32*ST_TILES);
+    int splits = std::max(1, numSM/t.rowTiles);
+    splits = std::min(splits, std::max(1, st.Npad/(4*ST_ATOMS)));
+    int aps = (st.Npad + splits - 1)/splits;
+    aps = (aps + ST_ATOMS - 1)/ST_ATOMS*ST_ATOMS;
+    t.splits = (st.Npad + aps - 1)/aps;
+    t.atomsPerSplit = aps;
+    t.threads = ST_THREADS;
+    const size_t rowStage = (size_t) ST_ATOMS*t.rowPitch*sizeof(float2);
+    const size_t rowStagePad = (rowStage + 127) & ~(size_t) 127;
+    ks.tsRowStageBytes = (uint32_t) rowStage;
+    ks.tsOffA = (uint32_t) (2*rowStagePad);
+    ks.tsOffB = ks.tsOffA + 2*ST_TILES*2*ST_A_PLANE;
+    ks.tsOffBar = ks.tsOffB + 2*2*ST_B_PLANE;
+    t.smem = ks.tsOffBar + 128;
+    if (t.smem > 227*1024 - 256) { ks.tensorS = false; return; }
+    CFX_CUDA(cudaFuncSetAttribute(structureFactorTensorKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) t.smem));
+}
+
+void launchStructureTensor(State& st, cudaStream_t s) {
+    KSpacePlan& ks = st.ks;
+    const SGeom& t = ks.sT;
+    STParams sp;
+    sp.rowS = st.rowS; sp.part = st.sPart;
+    sp.rowPitch = t.rowPitch; sp.Kx = ks.K[0]; sp.Ky = ks.K[1]; sp.Kz = ks.K[2]; sp.zOff = t.rowPitch - t.kzPad; sp.kzPad = t.kzPad;
+    sp.rowLo = ks.rowLo; sp.rowHi = ks.rowHi; sp.numRows = ks.numRows;
+    sp.atomsPerSplit = t.atomsPerSplit; sp.Npad = st.Npad;
+    sp.rowStageBytes = ks.tsRowStageBytes; sp.offA = ks.tsOffA; sp.offB = ks.tsOffB; sp.offBar = ks.tsOffBar;
+    structureFactorTensorKernel<<<dim3(t.rowTiles, t.splits), ST_THREADS, t.smem, s>>>(sp);
     CFX_LAUNCH_CHECK(); st.launches++;
 }
 
