@@ -3,17 +3,21 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c4] [--impl reference]
 
-One "step" = one full CalcCoulForceKernel::execute (energy + forces): charge-flux assembly, Ewald
-direct + explicit-k reciprocal + self + excluded-pair correction and the dE/dq.dq/dx chain rule, on the
-synthetic flexible-water box named in `config.workload`.
+One "step" = one CalcCoulForceKernel::execute(includeForces=true, includeEnergy=false) -- the call OpenMM makes
+once per MD time step: charge-flux assembly, Ewald direct + explicit-k reciprocal + self + excluded-pair
+correction and the dE/dq.dq/dx chain rule, on the synthetic flexible-water box named in `config.workload`.
+The energy+forces call (what a reporter / minimiser makes) is measured the same way and reported beside it as
+`energy_and_forces`; both arms (`--impl reference` too) use the same flags.
 
   value     whole-job force-evals/s with positions resident in HBM, CUDA events around every step,
             L2 flushed between steps, max over ranks.
   e2e       the same through the reference-facing call with HOST buffers: pinned H2D of the positions
             and D2H of forces + energy inside the timed region.
-  roofline  dominant kernel: algorithmic FLOP / its CUDA-event duration, against the FP32 FMA peak
-            measured live on this GPU (MEASURED_PEAKS.json has no CUDA-core figure; the path is
-            FP32-FMA bound, not HBM or tensor bound).
+  roofline  dominant kernel (the direct-space pair kernel): algorithmic FLOP / its CUDA-event duration, against
+            the FP32 FMA peak measured live on this GPU (MEASURED_PEAKS.json has no CUDA-core figure).
+            `roofline.kernels` lists every large kernel with its own bound: the reciprocal-space kernels run on
+            the tensor cores (tcgen05 kind::tf32, three-product split) and are held against the TF32 peak measured
+            live, both as algorithmic FP32-equivalent FLOP and as executed TF32 FLOP.
   cpu_baseline  the plugin's Reference-platform kernel (oracle/_ref when present, else the oracle port)
             on one host core, bounded sample, extrapolated in the number of k-vectors.
 
@@ -42,6 +46,7 @@ WORKLOADS = {
     "c4": "c4: 262,143-atom periodic flexible-water box, cutoff 1.0 nm, Ewald tol 1e-5, bond+angle charge flux",
 }
 TIMESTEP_FS = 0.5
+INCLUDE_ENERGY = False          # the headline step is the MD-step call: forces only
 
 
 def ns_per_day(evals_per_s):
@@ -136,7 +141,7 @@ def cpu_reference_sample(pos, box, force, target_kmax, make):
     h = make(force, box / div)
     k = h.ewald_params()[1]
     t = time.perf_counter()
-    h.execute(pos, box, True, True)
+    h.execute(pos, box, True, INCLUDE_ENERGY)
     dt = time.perf_counter() - t
     return dt, _kcount(k), k, nfull
 
@@ -196,7 +201,8 @@ def existing_cuda_baseline(workload, our_ms):
                 "kernels_ms": {k: round(v, 4) for k, v in r["kernels_ms"].items()},
                 "speedup_vs_lower_bound": r["ms_per_eval_lower_bound"] / our_ms,
                 "note": "8 of the existing platform's 9 launches, reference launch geometry, mixed precision; computeNonbonded needs "
-                        "OpenMM's tile list and is not launched, so this is a lower bound on its time"}
+                        "OpenMM's tile list and is not launched, so this is a lower bound on its time. The existing platform "
+                        "ignores includeForces/includeEnergy (CudaCoulKernels.cpp:522-660 launches every kernel on every call)"}
     except Exception as e:                                   # a baseline must never break the bench line
         return {"unavailable": "%s: %s" % (type(e).__name__, e)}
 
@@ -227,7 +233,7 @@ def run_reference_arm(args, pos, box, force, workload):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t_full, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload, "atoms": n, "kvectors": int(nfull)},
+            "config": {"workload": workload, "atoms": n, "kvectors": int(nfull), "flags": "includeForces=1 includeEnergy=0"},
             "ns_per_day": ns_per_day(value),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -241,6 +247,19 @@ def algorithmic_flops(n_atoms, n_k, pairs, n_terms, n_rows, n_excl):
     """FMA = 2 FLOP."""
     return {"structure_factor": 4.0 * n_atoms * n_k, "kspace_gather": 8.0 * n_atoms * n_k, "direct_pairs": 80.0 * pairs,
             "total": 12.0 * n_atoms * n_k + 80.0 * pairs + 150.0 * n_terms + 6.0 * n_rows + 40.0 * n_excl + 4.0 * n_atoms}
+
+
+def executed_tensor_flops(n_atoms, kmax):
+    """TF32 FLOP the tensor-core k-space kernels execute per launch: three products, padded tiles."""
+    kx, ky, kz = kmax
+    npad = (n_atoms + 255) // 256 * 256
+    if kz > 32 or ky < 8:
+        return {}
+    kp = (2 * kz + 7) // 8 * 8
+    signed = ky + (kx - 1) * (2 * ky - 1)
+    cols = (signed + 31) // 32 * 128
+    rows = (kx * ky + 63) // 64 * 64
+    return {"kspace_gather": 3 * 2.0 * npad * kp * cols, "structure_factor": 3 * 2.0 * (4 * rows) * 64 * npad}
 
 
 def run_ours(args, pos, box, force, workload):
@@ -271,26 +290,29 @@ def run_ours(args, pos, box, force, workload):
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        ctx.evaluate_device()
-    barrier()
+    def timed(include_energy):
+        for _ in range(max(args.warmup, 3)):
+            ctx.evaluate_device(True, include_energy)
+        barrier()
+        ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        barrier()
+        for i in range(args.steps):
+            with torch.cuda.stream(ctx.stream):
+                flush.zero_()
+                ev0[i].record(ctx.stream)
+            ctx.evaluate_device(True, include_energy)
+            ev1[i].record(ctx.stream)
+        barrier()
+        ms = torch.tensor([sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()) / args.steps
+
+    ms_ef = timed(True)                                       # energy + forces, reported beside the headline
     sampler = ClockSampler(local) if rank == 0 else None
-    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    barrier()
     t_start = time.perf_counter()
-    for i in range(args.steps):
-        with torch.cuda.stream(ctx.stream):
-            flush.zero_()
-            ev0[i].record(ctx.stream)
-        ctx.evaluate_device()
-        ev1[i].record(ctx.stream)
-    barrier()
-    t_end = time.perf_counter()
-    ms = torch.tensor([sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_per_step = float(ms.item()) / args.steps
+    ms_per_step = timed(INCLUDE_ENERGY)
     launches_per_eval = ctx.kernel.stats().kernel_launches
 
     # end to end through the reference-facing call (host buffers in, host buffers out)
@@ -305,9 +327,9 @@ def run_ours(args, pos, box, force, workload):
             if i == 0:
                 k1 = runtime.CalcCoulForceKernel(device=local)
                 k1.initialize(box, force)
-            k1.execute(pos, box, forces_host)
+            k1.execute(pos, box, forces_host, True, INCLUDE_ENERGY)
         else:
-            ctx.evaluate(pos)
+            ctx.evaluate(pos, True, INCLUDE_ENERGY)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t
         if i >= 3:
@@ -328,10 +350,13 @@ def run_ours(args, pos, box, force, workload):
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32 (f64 energies/accumulation, int64 fixed-point forces)", "data": "synthetic",
                 "config": {"workload": workload, "atoms": n, "kmax": list(kmax), "kvectors": int(nk), "alpha": alpha,
+                           "flags": "includeForces=1 includeEnergy=0 (the per-MD-step call)",
                            "l2": "384 MiB buffer written between timed steps (L2 flush); working set < L2",
                            "parallelism": "k-vector rows + direct-space i-tiles sharded x%d, NCCL all-reduce of int64 forces" % world
                            if world > 1 else "single GPU"},
                 "ns_per_day": ns_per_day(value),
+                "energy_and_forces": {"value": 1e3 / ms_ef, "unit": UNIT, "ms_per_step": ms_ef,
+                                      "note": "includeEnergy=1: FP64 pair energies and the FP32 (round-to-nearest) structure-factor kernel"},
                 "e2e": {"value": 1.0 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 24 * n, "d2h_bytes_per_step": 24 * n + 40,
                         "ns_per_day": ns_per_day(1.0 / e2e_s)},
                 "gpu_launches": int(launches_per_eval) * args.steps,
@@ -339,36 +364,62 @@ def run_ours(args, pos, box, force, workload):
     if world == 1:
         # per-kernel durations (CUDA events on the launching stream) and the roofline of the dominant one
         tf_peak, _ = runtime.measure_fp32_peak(local, 5)
-        kt = ctx.kernel.time_kernels(ctx.d_pos.data_ptr(), box, 10)
-        ctx.evaluate_device()
+        tf32_peak = runtime.measure_tf32_peak(local)
+        kt = ctx.kernel.time_kernels(ctx.d_pos.data_ptr(), box, 10, True, INCLUDE_ENERGY)
+        kt_ef = ctx.kernel.time_kernels(ctx.d_pos.data_ptr(), box, 10, True, True)
+        ctx.evaluate_device(True, INCLUDE_ENERGY)
         torch.cuda.synchronize()
         pairs = ctx.kernel.stats().pairs_in_cutoff
         fl = algorithmic_flops(n, nk, pairs, force.getNumFluxBonds() + force.getNumFluxAngles() + force.getNumFluxWaters(),
                                4 * force.getNumFluxBonds() + 9 * force.getNumFluxAngles() + 9 * force.getNumFluxWaters(),
                                force.getNumExceptions())
+        ex = executed_tensor_flops(n, kmax)
         top = max(kt, key=kt.get)
         total_kernel_ms = sum(kt.values())
         achieved = fl.get(top, 0.0) / (kt[top] * 1e-3) / 1e12
-        traffic = None
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json"))).get(top)
-            if tr and args.workload == "c3":
-                traffic = tr["dram_read_bytes"] + tr["dram_write_bytes"]
+            traffic_db = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json"))) if args.workload == "c3" else {}
         except (OSError, ValueError):
-            pass
+            traffic_db = {}
+
+        def traffic_of(name):
+            tr = traffic_db.get(name)
+            return tr["dram_read_bytes"] + tr["dram_write_bytes"] if tr else None
+
+        kernels = []
+        for name in ("direct_pairs", "kspace_gather", "structure_factor"):
+            if name not in kt:
+                continue
+            tensor = name in ex
+            peak = tf32_peak if tensor else tf_peak
+            a = fl[name] / (kt[name] * 1e-3) / 1e12
+            row = {"kernel": name, "bound": "tensor" if tensor else "fp32", "ms": kt[name], "share_of_step": kt[name] / total_kernel_ms,
+                   "algorithmic_flop_per_launch": fl[name], "achieved": a, "peak": peak, "unit": "TFLOP/s", "frac": a / peak,
+                   "traffic": traffic_of(name)}
+            if tensor:
+                row["executed_tf32_flop_per_launch"] = ex[name]
+                row["executed_tflops"] = ex[name] / (kt[name] * 1e-3) / 1e12
+                row["executed_frac"] = row["executed_tflops"] / peak
+                row["fp32_equivalent_frac_of_fp32_peak"] = a / tf_peak
+            kernels.append(row)
         line["roofline"] = {"bound": "fp32", "kernel": top, "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
-                            "frac": achieved / tf_peak, "traffic": traffic,
-                            "traffic_note": "DRAM bytes per launch of this kernel from the committed ncu capture (profiles/); the kernel is FP32-FMA bound",
+                            "frac": achieved / tf_peak, "traffic": traffic_of(top),
+                            "traffic_note": "DRAM bytes per launch of this kernel from the committed ncu capture (profiles/); far below "
+                                            "the algorithmic FLOP x 4 B: the kernel is instruction-issue / SFU bound, not HBM bound",
                             "peak_source": "FP32 FMA microbenchmark run in this process (cfx_measure_fp32_peak); "
-                                           "theoretical 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
+                                           "theoretical 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4. TF32 peak: tcgen05 kind::tf32 "
+                                           "128x128x8 microbenchmark run in this process (cfx_measure_tf32_peak)",
                             "kernel_ms": kt[top], "kernel_share_of_step": kt[top] / total_kernel_ms,
                             "algorithmic_flop_per_launch": fl.get(top, 0.0),
+                            "kernels": kernels,
                             "whole_step": {"achieved": fl["total"] / (ms_per_step * 1e-3) / 1e12,
                                            "frac": fl["total"] / (ms_per_step * 1e-3) / 1e12 / tf_peak,
-                                           "algorithmic_flop": fl["total"]}}
+                                           "algorithmic_flop": fl["total"],
+                                           "note": "algorithmic FP32-equivalent FLOP of the whole evaluation / step time, against the "
+                                                   "FP32 FMA peak; the reciprocal-space part runs on tensor cores"}}
         line["kernels_ms"] = {k: round(v, 5) for k, v in kt.items()}
-        line["kernel_fp32_frac"] = {k: fl[k] / (kt[k] * 1e-3) / 1e12 / tf_peak for k in ("structure_factor", "kspace_gather", "direct_pairs")
-                                    if k in kt}
+        line["energy_and_forces"]["kernels_ms"] = {k: round(v, 5) for k, v in kt_ef.items()}
+        line["peaks"] = {"fp32_fma_tflops": tf_peak, "tf32_tcgen05_tflops": tf32_peak}
         line["config"]["pairs_in_cutoff"] = int(pairs)
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(pos, box, force)

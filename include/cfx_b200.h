@@ -138,11 +138,14 @@ int  cfx_get_exclusions(cfx_handle* h, int32_t* row_ptr, int32_t* cols, int64_t 
  * (names joined by ';', times in ms, averaged over iters). */
 int  cfx_time_device(cfx_handle* h, const double* d_positions, const double* box,
                      int include_forces, int include_energy, int iters, float* ms_per_eval);
-int  cfx_time_kernels(cfx_handle* h, const double* d_positions, const double* box, int iters,
-                      char* names, int names_capacity, float* ms, int ms_capacity, int* count);
+int  cfx_time_kernels(cfx_handle* h, const double* d_positions, const double* box,
+                      int include_forces, int include_energy, int iters, char* names, int names_capacity, float* ms, int ms_capacity, int* count);
 /* Sustained FP32 FMA throughput of the device (TFLOP/s), the roofline denominator the path is
  * bounded by (MEASURED_PEAKS.json has no FP32 CUDA-core figure). */
 int  cfx_measure_fp32_peak(int device, int iters, double* tflops, double* sm_clock_mhz_est);
+/* Sustained dense TF32 tensor-core throughput (TFLOP/s) of tcgen05.mma kind::tf32 128x128x8, the roofline denominator
+ * of the tensor-core reciprocal-space kernels (MEASURED_PEAKS.json holds a bf16 figure only). */
+int  cfx_measure_tf32_peak(int device, int iters, double* tflops);
 
 /* ------------------------------------------------------------------------------------------------
  * MD harness: what sits either side of the path in an OpenMM simulation of

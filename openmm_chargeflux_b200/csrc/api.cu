@@ -630,7 +630,7 @@ int cfx_time_device(cfx_handle* h, const double* d_positions, const double* box,
     CFX_CATCH
 }
 
-int cfx_time_kernels(cfx_handle* h, const double* d_positions, const double* box, int iters,
+int cfx_time_kernels(cfx_handle* h, const double* d_positions, const double* box, int include_forces, int include_energy, int iters,
                      char* names, int names_capacity, float* ms, int ms_capacity, int* count) {
     CFX_TRY
     if (!h || !d_positions || !names || !ms || !count || iters < 1) throw ArgError("bad argument");
@@ -650,7 +650,7 @@ int cfx_time_kernels(cfx_handle* h, const double* d_positions, const double* box
         st.timing = true;
         CFX_CUDA(cudaMemsetAsync(st.forceFixed, 0, sizeof(long long)*3*st.Npad, s));
         mark(st, "begin", s);
-        enqueueEvaluation(st, d_positions, true, true, st.forceFixed, s, false);
+        enqueueEvaluation(st, d_positions, include_forces != 0, include_energy != 0, st.forceFixed, s, false);
         st.timing = false;
         CFX_CUDA(cudaStreamSynchronize(s));
         if (it == 0) { labels.assign(st.timeNames.begin() + 1, st.timeNames.end()); acc.assign(labels.size(), 0.0); continue; }
@@ -727,6 +727,16 @@ int cfx_measure_fp32_peak(int device, int iters, double* tflops, double* sm_cloc
 }
 
 } // extern "C"
+
+int cfx_measure_tf32_peak(int device, int iters, double* tflops) {
+    CFX_TRY
+    if (!tflops || iters < 1) throw ArgError("bad argument");
+    int dev = device;
+    if (dev < 0) CFX_CUDA(cudaGetDevice(&dev));
+    *tflops = measureTf32Peak(dev, iters);
+    return CFX_OK;
+    CFX_CATCH
+}
 
 // debug only (not part of include/cfx_b200.h): phase timestamps of the last tensor-gather launch, [148][32] ns
 extern "C" int cfx_debug_gather_trace(cfx_handle* h, unsigned long long* out) {

@@ -203,6 +203,7 @@ void launchKSpace(State& st, const double* dPos, bool forces, bool energy, long 
 bool structureTensorEligible(const State& st);                                          // kspace_tc.cu
 void planStructureTensor(State& st);
 void launchStructureTensor(State& st, cudaStream_t s);
+double measureTf32Peak(int device, int iters);
 void planKSpaceTensor(State& st);                                                       // kspace_tc.cu
 void launchGatherTensor(State& st, long long* dForce, long long* dDedq, cudaStream_t s);
 void planCells(State& st);

@@ -51,7 +51,6 @@ struct GTParams {
     float fx, fy, fz;
     int rawStages;              // FP32 coefficient tiles in flight (bulk TMA ring)
     uint32_t planeBytes, offRaw, offEy, offBar, offRd;
-    int dbg;
     unsigned long long* trace;      // optional [gridDim][32] globaltimer stamps (CFX_GT_TRACE)
 };
 
@@ -73,12 +72,11 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gatherTensorKernel(GTParams p, 
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long totalUnits = (long long) p.numAtomGroups*p.numColTiles;
-    const int u0 = (int) (totalUnits*blockIdx.x/gridDim.x);
-    const int u1 = (p.dbg & 32) ? u0 : (int) (totalUnits*(blockIdx.x + 1)/gridDim.x);
+    const int u0 = (int) (totalUnits*blockIdx.x/gridDim.x), u1 = (int) (totalUnits*(blockIdx.x + 1)/gridDim.x);
 
     if (tid == 0) {
         for (int s = 0; s < p.rawStages; s++) { mbarInit(&rawFull[s], 1); mbarInit(&rawEmpty[s], 4*SUBS); }
-        for (int b = 0; b < 2; b++) { mbarInit(&opFull[b], 4*SUBS); mbarInit(&opEmpty[b], (MT == 2 && !(p.dbg & 64)) ? 2 : 1); }
+        for (int b = 0; b < 2; b++) { mbarInit(&opFull[b], 4*SUBS); mbarInit(&opEmpty[b], MT == 2 ? 2 : 1); }
         for (int d = 0; d < 2; d++) { mbarInit(&dFull[d], 1); mbarInit(&dEmpty[d], 4*SUBS); }      // one arrival per epilogue warp
         mbarInit(aFull, 4*SUBS);
         mbarFenceInit();
@@ -97,7 +95,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gatherTensorKernel(GTParams p, 
         // ---------------- producer ----------------
         // one lane keeps rawStages FP32 coefficient tiles in flight (bulk TMA); a stage is refilled as soon as the
         // epilogue warps have split it into the TF32 operand planes
-        if (lane == 0 && !(p.dbg & 8)) {
+        if (lane == 0) {
             const uint32_t planeFloats = p.planeBytes/4;
             unsigned char* raw = smem + p.offRaw;
             int rs = 0; uint32_t rph = 0;
@@ -110,7 +108,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gatherTensorKernel(GTParams p, 
         }
         __syncwarp();
     }
-    else if (warp == GT_MMA_WARP || (warp == GT_MMA_WARP + 1 && !(p.dbg & 64))) {
+    else if (warp == GT_MMA_WARP || warp == GT_MMA_WARP + 1) {
         // ---------------- MMA issuers ----------------
         // Two warps, one per accumulator slot (seq parity), so that the per-tile bookkeeping of one overlaps the
         // issue of the other: the tensor pipe idles whenever nobody is issuing.
@@ -125,7 +123,6 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gatherTensorKernel(GTParams p, 
         uint32_t seq = 0;
         for (int unit = u0; unit < u1; unit++) {
             const int group = unit/p.numColTiles;
-            if (p.dbg & 8) continue;
             if (group != curGroup) {
                 curGroup = group;
                 mbarWait(aFull, aPh); aPh ^= 1;
@@ -141,7 +138,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gatherTensorKernel(GTParams p, 
             #pragma unroll 1
             for (int t = 0; t < MT; t++, seq++) {
                 const uint32_t d = seq & 1;
-                if (d != mySlot && !(p.dbg & 64)) continue;
+                if (d != mySlot) continue;
                 issued = true;
                 if (seq == 20) GT_STAMP(22);
                 mbarWait(&dEmpty[d], ((seq >> 1) & 1) ^ 1);
@@ -149,7 +146,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gatherTensorKernel(GTParams p, 
                 tcgen05FenceAfter();
                 const uint32_t tD = tmem + d*128;
                 const uint32_t aHi = tmemA + (uint32_t) t*2*p.Kp, aLo = aHi + p.Kp;
-                if (!(p.dbg & 2) && electOne()) {
+                if (electOne()) {
                     // small products first: Zlo Chi, Zhi Clo, then Zhi Chi; one k8 step advances the
                     // descriptor by two core-matrix columns (2*NT*16 bytes) and the phase operand by 8 columns
                     #pragma unroll 1
@@ -182,7 +179,6 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gatherTensorKernel(GTParams p, 
         int curGroup = -1;
         uint32_t seq = 0;
         auto flush = [&]() {
-            if (p.dbg & 16) return;
             #pragma unroll
             for (int t = 0; t < MT; t++) {
                 const int atom = (curGroup*MT + t)*GT_TILE_ATOMS + atomInTile;
@@ -217,7 +213,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gatherTensorKernel(GTParams p, 
             if (lane == 0) { mbarArrive(&opFull[ob]); mbarArrive(&rawEmpty[rs]); }
         };
         int buf = 0, cc = 0;
-        if (u0 < u1 && !(p.dbg & 8)) splitUnit(u0);
+        if (u0 < u1) splitUnit(u0);
         if (u0 < u1) {
             const int group0 = u0/p.numColTiles, g8 = (u0 - group0*p.numColTiles)*SUBS + sub;
             const int4 gi = __ldg(p.groupInfo + g8);
@@ -275,7 +271,6 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gatherTensorKernel(GTParams p, 
                 namedBarrier(1, EPI_THREADS);                     // Ey columns complete
                 if (warp == GT_EPI_WARP0) GT_STAMP(gs + 5);
             }
-            if (p.dbg & 8) continue;
             if (unit + 1 < u1) splitUnit(unit + 1);
             // row data / Ex of the NEXT unit are fetched while this one is processed (no exposed global latency)
             const int unitN = (unit + 1 < u1) ? unit + 1 : unit;
@@ -298,7 +293,6 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gatherTensorKernel(GTParams p, 
                 if (lane == 0) mbarArrive(&dEmpty[d]);            // values are in registers: the slot can be refilled
                 if (warp == GT_EPI_WARP0 && seq == 18) GT_STAMP(27);
                 const char* eyCol = reinterpret_cast<const char*>(Eys + t*GT_TILE_ATOMS + atomInTile);
-                if (p.dbg & 1) { oD[t] += v[0] + v[31]; continue; }
                 const float4* rd = rdS + buf*8;
                 #pragma unroll
                 for (int i = 0; i < 8; i++) {
@@ -621,7 +615,6 @@ void launchGatherTensor(State& st, long long* dForce, long long* dDedq, cudaStre
     gp.signedLo = ks.signedLo; gp.signedHi = ks.signedHi; gp.numColTiles = ks.tColTiles;
     gp.numAtomGroups = st.Npad/(GT_TILE_ATOMS*ks.tMT);
     gp.fx = (float) (2*M_PI/st.box.L[0]); gp.fy = (float) (2*M_PI/st.box.L[1]); gp.fz = (float) (2*M_PI/st.box.L[2]);
-    gp.dbg = getenv("CFX_GT_DEBUG") ? atoi(getenv("CFX_GT_DEBUG")) : 0;
     gp.trace = nullptr;
     gp.trace = st.gtTrace;
     gp.rawStages = ks.tStages; gp.planeBytes = ks.tStageBytes; gp.offRaw = 4*ks.tStageBytes; gp.offEy = ks.tOffEy; gp.offBar = ks.tOffBar; gp.offRd = ks.tOffBar + 256;
@@ -679,6 +672,75 @@ void launchStructureTensor(State& st, cudaStream_t s) {
     sp.rowStageBytes = ks.tsRowStageBytes; sp.offA = ks.tsOffA; sp.offB = ks.tsOffB; sp.offBar = ks.tsOffBar;
     structureFactorTensorKernel<<<dim3(t.rowTiles, t.splits), ST_THREADS, t.smem, s>>>(sp);
     CFX_LAUNCH_CHECK(); st.launches++;
+}
+
+// ------------------------------------------------------------------------------------------------
+// TF32 tensor-core peak: every CTA issues `iters` tcgen05.mma kind::tf32 128x128x8 (A in tensor memory, B in shared
+// memory -- the gather's instruction shape) on fixed operands. Roofline denominator of the tensor-core kernels.
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(128) tf32PeakKernel(int iters, float* sink) {
+    constexpr int N = 128;
+    extern __shared__ __align__(128) unsigned char smem[];
+    float* b = reinterpret_cast<float*>(smem);                 // [2][N][4]
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmemSlot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int e = tid; e < 2*N*4; e += 128) b[e] = roundTf32(0.001f*(e % 97));
+    fenceProxyAsync();
+    if (tid == 0) { mbarInit(&bar, 1); mbarFenceInit(); }
+    if (warp == 0) tmemAlloc<512>(&tmemSlot);
+    tcgen05FenceBefore();
+    __syncthreads();
+    tcgen05FenceAfter();
+    const uint32_t tmem = tmemSlot;
+    for (int c = 0; c < 64; c += 4) tmemStore4(tmem + 256 + c + ((uint32_t) (warp*32) << 16), make_float4(0.5f, 0.25f, 0.125f, 1.f));
+    tmemWaitStore();
+    tcgen05FenceBefore();
+    __syncthreads();
+    tcgen05FenceAfter();
+    if (warp == 0) {
+        constexpr uint32_t idesc = ummaIdescTf32(128, N);
+        const uint64_t bd = ummaSmemDesc(smemU32(b), N*16, 128);
+        if (electOne()) {
+            for (int i = 0; i < iters; i++) ummaTf32TS(tmem + (i & 1)*N, tmem + 256 + 8*(i % 7), bd, idesc, i > 1);
+            ummaCommit(&bar);
+        }
+        __syncwarp();
+    }
+    mbarWait(&bar, 0);
+    tcgen05FenceAfter();
+    float v[16];
+    tmemLoad16(tmem + ((uint32_t) (warp*32) << 16), v);
+    if (v[0] == 123.456f) sink[tid] = v[1];
+    tcgen05FenceBefore();
+    __syncthreads();
+    if (warp == 0) tmemFree<512>(tmem);
+}
+} // namespace
+
+double measureTf32Peak(int device, int iters) {
+    CFX_CUDA(cudaSetDevice(device));
+    int numSM = 148;
+    cudaDeviceGetAttribute(&numSM, cudaDevAttrMultiProcessorCount, device);
+    float* sink = nullptr;
+    CFX_CUDA(cudaMalloc(&sink, 4096));
+    cudaEvent_t e0, e1;
+    CFX_CUDA(cudaEventCreate(&e0)); CFX_CUDA(cudaEventCreate(&e1));
+    const size_t smem = 2*128*4*sizeof(float);
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; rep++) {
+        CFX_CUDA(cudaEventRecord(e0));
+        tf32PeakKernel<<<numSM, 128, smem>>>(iters, sink);
+        CFX_CUDA(cudaEventRecord(e1));
+        CFX_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CFX_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0) best = std::min(best, ms);
+    }
+    CFX_CUDA(cudaGetLastError());
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+    return 2.0*128*128*8*(double) iters*numSM/(best*1e-3)*1e-12;
 }
 
 } // namespace cfx

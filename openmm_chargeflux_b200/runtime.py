@@ -51,7 +51,7 @@ def load_library():
     lib.cfx_get_neighbor_pairs.argtypes = [C.c_void_p, _abi.c_int32_p, C.c_int64, C.POINTER(C.c_int64)]
     lib.cfx_get_exclusions.argtypes = [C.c_void_p, _abi.c_int32_p, _abi.c_int32_p, C.c_int64, C.POINTER(C.c_int64)]
     lib.cfx_time_device.argtypes = [C.c_void_p, C.c_void_p, _abi.c_double_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
-    lib.cfx_time_kernels.argtypes = [C.c_void_p, C.c_void_p, _abi.c_double_p, C.c_int, C.c_char_p, C.c_int,
+    lib.cfx_time_kernels.argtypes = [C.c_void_p, C.c_void_p, _abi.c_double_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int,
                                      C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int)]
     lib.cfx_measure_fp32_peak.argtypes = [C.c_int, C.c_int, _abi.c_double_p, _abi.c_double_p]
     _lib = lib
@@ -176,11 +176,11 @@ class CalcCoulForceKernel:
                                               int(iters), C.byref(ms)))
         return ms.value
 
-    def time_kernels(self, d_positions, box, iters):
+    def time_kernels(self, d_positions, box, iters, includeForces=True, includeEnergy=True):
         names = C.create_string_buffer(4096)
         ms = (C.c_float * 64)()
         cnt = C.c_int(0)
-        self._check(self._lib.cfx_time_kernels(self._h, d_positions, _dp(_box9(box)), int(iters), names, 4096, ms, 64, C.byref(cnt)))
+        self._check(self._lib.cfx_time_kernels(self._h, d_positions, _dp(_box9(box)), int(includeForces), int(includeEnergy), int(iters), names, 4096, ms, 64, C.byref(cnt)))
         return dict(zip(names.value.decode().split(";"), [ms[i] for i in range(cnt.value)]))
 
     def close(self):
@@ -193,6 +193,16 @@ class CalcCoulForceKernel:
             self.close()
         except Exception:
             pass
+
+
+def measure_tf32_peak(device=-1, iters=20000):
+    """Dense TF32 tcgen05 throughput in TFLOP/s (roofline denominator of the tensor-core k-space kernels)."""
+    lib = load_library()
+    lib.cfx_measure_tf32_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]
+    tf = C.c_double(0.0)
+    if lib.cfx_measure_tf32_peak(int(device), int(iters), C.byref(tf)) != 0:
+        raise CfxError(lib.cfx_last_error().decode())
+    return tf.value
 
 
 def measure_fp32_peak(device=-1, iters=5):

@@ -7,4 +7,5 @@ dpos = torch.tensor(pos, device='cuda')
 for incF, incE in ((True, True), (True, False), (False, True)):
     ms = ctx.kernel.time_device(dpos.data_ptr(), box, 20, incF, incE)
     print(f"forces={incF} energy={incE}: {ms:.4f} ms/eval")
-print(ctx.kernel.time_kernels(dpos.data_ptr(), box, 5))
+print('E+F kernels', ctx.kernel.time_kernels(dpos.data_ptr(), box, 5))
+print('F-only kernels', ctx.kernel.time_kernels(dpos.data_ptr(), box, 5, True, False))
