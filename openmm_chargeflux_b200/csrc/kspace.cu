@@ -601,16 +601,17 @@ void planKSpace(State& st) {
     ks.gRowsPerTile = (std::max(signedHere, 1) + gRowTile - 1)/gRowTile;          // row tiles per atom tile
     ks.gRowSplits = numSM;                                                        // persistent grid size
 
-    CFX_CUDA(cudaFuncSetAttribute(phaseTableKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (PT_ATOMS*maxPitch*sizeof(float2))));
-    CFX_CUDA(cudaFuncSetAttribute(structureFactorKernel<6, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) f.smem));
-    CFX_CUDA(cudaFuncSetAttribute(structureFactorKernel<7, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) f.smem));
-    CFX_CUDA(cudaFuncSetAttribute(structureFactorKernel<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) f.smem));
-    CFX_CUDA(cudaFuncSetAttribute(structureFactorKernel<6, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) f.smem));
-    CFX_CUDA(cudaFuncSetAttribute(structureFactorKernel<7, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) f.smem));
-    CFX_CUDA(cudaFuncSetAttribute(structureFactorKernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) f.smem));
-    CFX_CUDA(cudaFuncSetAttribute(gatherKernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smemCap));
-    CFX_CUDA(cudaFuncSetAttribute(gatherKernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smemCap));
-    CFX_CUDA(cudaFuncSetAttribute(gatherKernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smemCap));
+    // (function attributes are per process, not per handle: always the hardware maximum)
+    CFX_CUDA(cudaFuncSetAttribute(phaseTableKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024));
+    CFX_CUDA(cudaFuncSetAttribute(structureFactorKernel<6, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024));
+    CFX_CUDA(cudaFuncSetAttribute(structureFactorKernel<7, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024));
+    CFX_CUDA(cudaFuncSetAttribute(structureFactorKernel<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024));
+    CFX_CUDA(cudaFuncSetAttribute(structureFactorKernel<6, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024));
+    CFX_CUDA(cudaFuncSetAttribute(structureFactorKernel<7, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024));
+    CFX_CUDA(cudaFuncSetAttribute(structureFactorKernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024));
+    CFX_CUDA(cudaFuncSetAttribute(gatherKernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024));
+    CFX_CUDA(cudaFuncSetAttribute(gatherKernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024));
+    CFX_CUDA(cudaFuncSetAttribute(gatherKernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024));
     planKSpaceTensor(st);
 }
 

@@ -556,7 +556,7 @@ void planKSpaceTensor(State& st) {
     ks.tNT = (Kp <= 56) ? 128 : 64;
     const size_t planeBytes = (size_t) ks.tKC*ks.tNT*16;         // one FP32 / TF32-hi / TF32-lo plane of a coefficient tile
     const size_t eyBytes = ((size_t) Ky*ks.tMT*GT_TILE_ATOMS*sizeof(float2) + 127) & ~(size_t) 127;
-    const size_t tailBytes = 256 + 16*16*sizeof(float4);          // barriers + per-warp row-data slots
+    const size_t tailBytes = 256 + (size_t) (ks.tNT/8)*16*sizeof(float4);   // barriers + per-epilogue-warp row-data slots (2 x 8 rows)
     const size_t cap = 227*1024 - 256;
     if (4*planeBytes + eyBytes + tailBytes > cap) return;         // operand double buffer (hi+lo) needs 4 planes
     const int rawStages = (int) std::min<size_t>(4, (cap - 4*planeBytes - eyBytes - tailBytes)/planeBytes);
@@ -658,7 +658,7 @@ void planStructureTensor(State& st) {
     ks.tsOffBar = ks.tsOffB + 2*2*ST_B_PLANE;
     t.smem = ks.tsOffBar + 128;
     if (t.smem > 227*1024 - 256) { ks.tensorS = false; return; }
-    CFX_CUDA(cudaFuncSetAttribute(structureFactorTensorKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) t.smem));
+    CFX_CUDA(cudaFuncSetAttribute(structureFactorTensorKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024));
 }
 
 void launchStructureTensor(State& st, cudaStream_t s) {

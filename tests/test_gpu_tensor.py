@@ -1,0 +1,72 @@
+"""GPU: the tensor-core reciprocal-space kernels (kspace_tc.cu) against the FP32 CUDA-core kernels and the oracle.
+
+The tensor kernels replace the FP32 ones whenever the geometry allows (|nz| <= 32 for the structure factors of a
+forces-only evaluation, 2*Kz <= 112 and Ky >= 8 for the gather); CFX_KSPACE_S / CFX_KSPACE_GATHER = fp32 pin the
+FP32 kernels at plan time, which is how the two paths are compared here."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import F_RTOL, rel_rms
+from openmm_chargeflux_b200 import runtime, synthetic
+from oracle import Oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _context(force, box, fp32):
+    keys = ("CFX_KSPACE_S", "CFX_KSPACE_GATHER")
+    old = {k: os.environ.get(k) for k in keys}
+    try:
+        for k in keys:
+            if fp32:
+                os.environ[k] = "fp32"
+            else:
+                os.environ.pop(k, None)
+        return runtime.CoulContext(force, box)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def test_tensor_and_fp32_kspace_paths_agree_on_the_4k_box(build_native):
+    pos, box, force = synthetic.config("c2")
+    tens, fp32 = _context(force, box, False), _context(force, box, True)
+    for inc_e in (False, True):
+        e_t, f_t, c_t = tens.evaluate(pos, True, inc_e)
+        e_f, f_f, c_f = fp32.evaluate(pos, True, inc_e)
+        assert rel_rms(f_t, f_f) <= 3e-6, inc_e
+        assert rel_rms(tens.kernel.dedq(), fp32.kernel.dedq()) <= 3e-6
+        if inc_e:
+            # energy evaluations use the FP32 (round-to-nearest) structure-factor kernel on both paths
+            assert abs(e_t - e_f) <= 1e-9 * np.abs(c_f[:4]).max()
+
+
+@pytest.mark.parametrize("flux", ["bond+angle", "water"])
+def test_large_kmax_variant_of_the_tensor_gather_against_the_oracle(build_native, flux):
+    """Short cutoff => large alpha => |nz| up to ~30: the gather runs its one-atom-tile / 64-column variant
+    (K padded to 64 > 56) and the structure factors still fit one N = 64 MMA."""
+    pos, box, force = synthetic.water_box(216, seed=11, cutoff=0.24, ewald_tol=1e-5, flux=flux)
+    o = Oracle(force, box)
+    ctx = _context(force, box, False)
+    kmax = ctx.kernel.ewald_params()[1]
+    assert 29 <= kmax[2] <= 32, kmax
+    eo, fo = o.execute(pos, box, True, True)
+    e, f, comps = ctx.evaluate(pos, True, True)
+    # alpha = 13.7/nm makes the components (2.4e5 kJ/mol) cancel to 6e2: the FP32 reciprocal sums are good to 1e-7 of
+    # the component scale, which is what is checked here; the headline tolerances are tested on the physical boxes
+    assert abs(e - eo[4]) <= 1e-7 * np.abs(eo[:4]).max()
+    assert rel_rms(f, fo) <= F_RTOL
+    eo, fo = o.execute(pos, box, True, False)
+    e, f, comps = ctx.evaluate(pos, True, False)                  # forces only: tensor-core structure factors too
+    assert rel_rms(f, fo) <= F_RTOL
+    assert rel_rms(ctx.kernel.dedq(), o.dedq()) <= F_RTOL
+
+
+def test_tf32_peak_measurement_is_plausible(build_native):
+    tf = runtime.measure_tf32_peak(iters=5000)
+    assert 300.0 < tf < 2500.0, tf
