@@ -253,13 +253,19 @@ def executed_tensor_flops(n_atoms, kmax):
     """TF32 FLOP the tensor-core k-space kernels execute per launch: three products, padded tiles."""
     kx, ky, kz = kmax
     npad = (n_atoms + 255) // 256 * 256
-    if kz > 32 or ky < 8:
-        return {}
+    out = {}
     kp = (2 * kz + 7) // 8 * 8
-    signed = ky + (kx - 1) * (2 * ky - 1)
-    cols = (signed + 31) // 32 * 128
-    rows = (kx * ky + 63) // 64 * 64
-    return {"kspace_gather": 3 * 2.0 * npad * kp * cols, "structure_factor": 3 * 2.0 * (4 * rows) * 64 * npad}
+    if kp <= 112 and ky >= 8:
+        nt = 128 if kp <= 56 else 64
+        signed = ky + (kx - 1) * (2 * ky - 1)
+        cols = (signed + nt // 4 - 1) // (nt // 4) * nt
+        out["kspace_gather"] = 3 * 2.0 * npad * kp * cols
+    if kz <= 64:
+        nn = 64 if kz <= 32 else 128
+        rows_per_cta = 32 * (128 // nn)
+        rows = (kx * ky + rows_per_cta - 1) // rows_per_cta * rows_per_cta
+        out["structure_factor"] = 3 * 2.0 * (4 * rows) * nn * npad
+    return out
 
 
 def run_ours(args, pos, box, force, workload):

@@ -349,13 +349,10 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gatherTensorKernel(GTParams p, 
 // truncates on accumulation -- taken out after every 32 atoms and summed in FP32 registers with round-to-nearest.
 // One CTA = 2 row tiles (64 rows) x one split of the atoms.
 constexpr int ST_ATOMS = 32;                 // atoms per stage = 4 MMA k-steps
-constexpr int ST_TILES = 2;                  // row tiles (of 32 rows) per CTA
 constexpr int ST_FORM_WARPS = 8, ST_EPI_WARPS = 8;
 constexpr int ST_FORM_WARP0 = 2, ST_EPI_WARP0 = ST_FORM_WARP0 + ST_FORM_WARPS;
 constexpr int ST_THREADS = (ST_EPI_WARP0 + ST_EPI_WARPS)*32;
-constexpr int ST_N = 64;                     // GEMM N: 2*Kz padded
 constexpr uint32_t ST_A_PLANE = (ST_ATOMS/4)*128*16;      // bytes of one hi or lo plane of one row tile
-constexpr uint32_t ST_B_PLANE = (ST_ATOMS/4)*ST_N*16;
 
 struct STParams {
     const float2* rowS; float* part;
@@ -365,7 +362,10 @@ struct STParams {
     uint32_t rowStageBytes, offA, offB, offBar;
 };
 
+// NN = GEMM N (2*Kz padded to 64 or 128), TT = row tiles of 32 rows per CTA; TT*NN = 128 accumulator columns per slot
+template <int NN, int TT>
 __global__ void __launch_bounds__(ST_THREADS, 1) structureFactorTensorKernel(STParams p) {
+    constexpr uint32_t B_PLANE = (ST_ATOMS/4)*NN*16;
     extern __shared__ __align__(128) unsigned char smem[];
     // [2 row stages][2 operand buffers: A (tiles x hi|lo planes)][2 operand buffers: B (hi|lo)][barriers]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.offBar);
@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) structureFactorTensorKernel(STP
     uint32_t* tmemSlot = reinterpret_cast<uint32_t*>(bars + 12);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int rowBase = p.rowLo + blockIdx.x*(32*ST_TILES);
+    const int rowBase = p.rowLo + blockIdx.x*(32*TT);
     const int atomBegin = blockIdx.y*p.atomsPerSplit;
     const int atomEnd = min(atomBegin + p.atomsPerSplit, p.Npad);
     const int numStages = (atomEnd - atomBegin)/ST_ATOMS;
@@ -411,28 +411,29 @@ __global__ void __launch_bounds__(ST_THREADS, 1) structureFactorTensorKernel(STP
     }
     else if (warp == 1) {
         // ---------------- MMA issuer (warp-uniform control flow, one elected lane issues) ----------------
-        constexpr uint32_t idesc = ummaIdescTf32(128, ST_N);
+        constexpr uint32_t idesc = ummaIdescTf32(128, NN);
         for (int st = 0; st < numStages; st++) {
             const int b = st & 1;
             const uint32_t ph = (st >> 1) & 1;
             mbarWait(&abFull[b], ph);
             mbarWait(&dEmpty[b], ph ^ 1);
             tcgen05FenceAfter();
-            const uint32_t aBase = smemU32(smem) + p.offA + (uint32_t) b*(ST_TILES*2*ST_A_PLANE);
-            const uint32_t bBase = smemU32(smem) + p.offB + (uint32_t) b*(2*ST_B_PLANE);
-            const uint64_t bHi = ummaSmemDesc(bBase, ST_N*16, 128), bLo = ummaSmemDesc(bBase + ST_B_PLANE, ST_N*16, 128);
+            const uint32_t aBase = smemU32(smem) + p.offA + (uint32_t) b*(TT*2*ST_A_PLANE);
+            const uint32_t bBase = smemU32(smem) + p.offB + (uint32_t) b*(2*B_PLANE);
+            const uint64_t bHi = ummaSmemDesc(bBase, NN*16, 128), bLo = ummaSmemDesc(bBase + B_PLANE, NN*16, 128);
             if (electOne()) {
                 #pragma unroll
-                for (int t = 0; t < ST_TILES; t++) {
-                    const uint32_t tD = tmem + (uint32_t) b*(ST_TILES*ST_N) + t*ST_N;
+                for (int t = 0; t < TT; t++) {
+                    const uint32_t tD = tmem + (uint32_t) b*(TT*NN) + t*NN;
                     const uint64_t aHi = ummaSmemDesc(aBase + t*2*ST_A_PLANE, 128*16, 128), aLo = ummaSmemDesc(aBase + t*2*ST_A_PLANE + ST_A_PLANE, 128*16, 128);
-                    // one k-step = 8 atoms = two 16-byte chunk columns: 2*128*16 bytes of A, 2*64*16 bytes of Z
+                    // one k-step = 8 atoms = two 16-byte chunk columns: 2*128*16 bytes of A, 2*NN*16 bytes of Z;
+                    // small products first
                     #pragma unroll
-                    for (int k8 = 0; k8 < ST_ATOMS/8; k8++) ummaTf32SS(tD, aLo + (uint64_t) (k8*(2*128*16 >> 4)), bHi + (uint64_t) (k8*(2*ST_N*16 >> 4)), idesc, k8 > 0);
+                    for (int k8 = 0; k8 < ST_ATOMS/8; k8++) ummaTf32SS(tD, aLo + (uint64_t) (k8*(2*128*16 >> 4)), bHi + (uint64_t) (k8*(2*NN*16 >> 4)), idesc, k8 > 0);
                     #pragma unroll
-                    for (int k8 = 0; k8 < ST_ATOMS/8; k8++) ummaTf32SS(tD, aHi + (uint64_t) (k8*(2*128*16 >> 4)), bLo + (uint64_t) (k8*(2*ST_N*16 >> 4)), idesc, 1);
+                    for (int k8 = 0; k8 < ST_ATOMS/8; k8++) ummaTf32SS(tD, aHi + (uint64_t) (k8*(2*128*16 >> 4)), bLo + (uint64_t) (k8*(2*NN*16 >> 4)), idesc, 1);
                     #pragma unroll
-                    for (int k8 = 0; k8 < ST_ATOMS/8; k8++) ummaTf32SS(tD, aHi + (uint64_t) (k8*(2*128*16 >> 4)), bHi + (uint64_t) (k8*(2*ST_N*16 >> 4)), idesc, 1);
+                    for (int k8 = 0; k8 < ST_ATOMS/8; k8++) ummaTf32SS(tD, aHi + (uint64_t) (k8*(2*128*16 >> 4)), bHi + (uint64_t) (k8*(2*NN*16 >> 4)), idesc, 1);
                 }
                 ummaCommit(&abEmpty[b]);
                 ummaCommit(&dFull[b]);
@@ -443,44 +444,48 @@ __global__ void __launch_bounds__(ST_THREADS, 1) structureFactorTensorKernel(STP
     else if (warp < ST_EPI_WARP0) {
         // ---------------- formers: row operand A (products) and column operand Z, TF32 hi/lo planes ----------------
         const int ft = tid - ST_FORM_WARP0*32;                     // 0..255
-        // A item: (row r of the 64, quad of 4 atoms); two quads per thread
-        const int r = ft & 63, qd0 = ft >> 6;                      // quads qd0 and qd0 + 4
-        const int row = rowBase + r;
-        const bool rowValid = row < p.rowHi;
-        const int nx = rowValid ? row/p.Ky : 0, m = rowValid ? row - nx*p.Ky : 0;
-        const uint32_t aOff = (uint32_t) (r >> 5)*(2*ST_A_PLANE) + (uint32_t) (r & 31)*16;     // + quad*128*16 + comp*32*16
-        // Z item: (l = ft & 31, quad = ft >> 5)
-        const int zl = ft & 31, zq = ft >> 5;
+        constexpr int A_PER = 32*TT*(ST_ATOMS/4)/(32*ST_FORM_WARPS);    // (row, quad of 4 atoms) items per thread
+        constexpr int Z_PER = (NN/2)*(ST_ATOMS/4)/(32*ST_FORM_WARPS);   // (|nz|, quad of 4 atoms) items per thread
+        int aNx[A_PER], aM[A_PER], aQd[A_PER]; uint32_t aDst[A_PER]; bool aValid[A_PER];
+        #pragma unroll
+        for (int k = 0; k < A_PER; k++) {
+            const int item = ft + k*32*ST_FORM_WARPS, r = item % (32*TT), row = rowBase + r;
+            aQd[k] = item/(32*TT);
+            aValid[k] = row < p.rowHi;
+            aNx[k] = aValid[k] ? row/p.Ky : 0;
+            aM[k] = aValid[k] ? row - aNx[k]*p.Ky : 0;
+            aDst[k] = (uint32_t) (r >> 5)*(2*ST_A_PLANE) + (uint32_t) aQd[k]*(128*16) + (uint32_t) (r & 31)*16;
+        }
         for (int st = 0; st < numStages; st++) {
             const int b = st & 1;
             const uint32_t ph = (st >> 1) & 1;
             mbarWait(&rowsFull[b], ph);
             mbarWait(&abEmpty[b], ph ^ 1);                        // the MMAs that read this operand buffer are complete
             const float2* rows = reinterpret_cast<const float2*>(smem + (size_t) b*p.rowStageBytes);
-            unsigned char* aBuf = smem + p.offA + (size_t) b*(ST_TILES*2*ST_A_PLANE);
-            unsigned char* bBuf = smem + p.offB + (size_t) b*(2*ST_B_PLANE);
+            unsigned char* aBuf = smem + p.offA + (size_t) b*(TT*2*ST_A_PLANE);
+            unsigned char* bBuf = smem + p.offB + (size_t) b*(2*B_PLANE);
             #pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const int qd = qd0 + 4*h;
+            for (int k = 0; k < A_PER; k++) {
                 float4 pc[4];                                      // per comp: 4 atoms
                 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    const float2* ar = rows + (size_t) (4*qd + j)*p.rowPitch;
-                    const float2 x = ar[nx], y = ar[p.Kx + m];
-                    const float v0 = x.x*y.x, v1 = x.x*y.y, v2 = x.y*y.x, v3 = x.y*y.y;
-                    (&pc[0].x)[j] = v0; (&pc[1].x)[j] = v1; (&pc[2].x)[j] = v2; (&pc[3].x)[j] = v3;
+                    const float2* ar = rows + (size_t) (4*aQd[k] + j)*p.rowPitch;
+                    const float2 x = ar[aNx[k]], y = ar[p.Kx + aM[k]];
+                    (&pc[0].x)[j] = x.x*y.x; (&pc[1].x)[j] = x.x*y.y; (&pc[2].x)[j] = x.y*y.x; (&pc[3].x)[j] = x.y*y.y;
                 }
+                unsigned char* dst0 = aBuf + aDst[k];
                 #pragma unroll
                 for (int c = 0; c < 4; c++) {
                     float4 hi, lo;
-                    if (rowValid) splitTf32(pc[c], hi, lo);
+                    if (aValid[k]) splitTf32(pc[c], hi, lo);
                     else { hi = make_float4(0.f, 0.f, 0.f, 0.f); lo = hi; }
-                    unsigned char* dst = aBuf + aOff + (uint32_t) qd*(128*16) + (uint32_t) c*(32*16);
-                    *reinterpret_cast<float4*>(dst) = hi;
-                    *reinterpret_cast<float4*>(dst + ST_A_PLANE) = lo;
+                    *reinterpret_cast<float4*>(dst0 + c*(32*16)) = hi;
+                    *reinterpret_cast<float4*>(dst0 + c*(32*16) + ST_A_PLANE) = lo;
                 }
             }
-            {
+            #pragma unroll
+            for (int k = 0; k < Z_PER; k++) {
+                const int item = ft + k*32*ST_FORM_WARPS, zl = item % (NN/2), zq = item/(NN/2);
                 float4 zc, zs;
                 #pragma unroll
                 for (int j = 0; j < 4; j++) {
@@ -488,11 +493,11 @@ __global__ void __launch_bounds__(ST_THREADS, 1) structureFactorTensorKernel(STP
                     (&zc.x)[j] = z.x; (&zs.x)[j] = z.y;
                 }
                 float4 hi, lo;
-                unsigned char* dst = bBuf + (uint32_t) zq*(ST_N*16) + (uint32_t) (2*zl)*16;
+                unsigned char* dst = bBuf + (uint32_t) zq*(NN*16) + (uint32_t) (2*zl)*16;
                 splitTf32(zc, hi, lo);
-                *reinterpret_cast<float4*>(dst) = hi; *reinterpret_cast<float4*>(dst + ST_B_PLANE) = lo;
+                *reinterpret_cast<float4*>(dst) = hi; *reinterpret_cast<float4*>(dst + B_PLANE) = lo;
                 splitTf32(zs, hi, lo);
-                *reinterpret_cast<float4*>(dst + 16) = hi; *reinterpret_cast<float4*>(dst + 16 + ST_B_PLANE) = lo;
+                *reinterpret_cast<float4*>(dst + 16) = hi; *reinterpret_cast<float4*>(dst + 16 + B_PLANE) = lo;
             }
             fenceProxyAsync();                                    // operands visible to the tensor core (async proxy)
             __syncwarp();
@@ -500,23 +505,24 @@ __global__ void __launch_bounds__(ST_THREADS, 1) structureFactorTensorKernel(STP
         }
     }
     else {
-        // ---------------- epilogue: FP32 running sums, thread = (row tile, tensor-memory lane = (comp, row)) ----------------
+        // ---------------- epilogue: FP32 running sums; thread = (tensor-memory lane = (comp, row), block of 64 columns) ----------------
         const int e = warp - ST_EPI_WARP0;
-        const int q4 = warp & 3, t = e >> 2;                      // lane quarter = comp, row tile
+        const int q4 = warp & 3, cb = e >> 2;                     // lane quarter = comp; column block of the 128-column slot
+        const int t = cb/(NN/64), colOff = (cb % (NN/64))*64;     // row tile, first column within its NN columns
         const uint32_t laneBase = (uint32_t) (q4*32) << 16;
-        float acc[ST_N];
+        float acc[64];
         #pragma unroll
-        for (int i = 0; i < ST_N; i++) acc[i] = 0.f;
+        for (int i = 0; i < 64; i++) acc[i] = 0.f;
         for (int st = 0; st < numStages; st++) {
             const int b = st & 1;
             mbarWait(&dFull[b], (st >> 1) & 1);
             tcgen05FenceAfter();
-            const uint32_t tD = tmem + (uint32_t) b*(ST_TILES*ST_N) + t*ST_N + laneBase;
+            const uint32_t tD = tmem + (uint32_t) b*(TT*NN) + cb*64 + laneBase;
             #pragma unroll
-            for (int c = 0; c < ST_N/16; c++) {
+            for (int c = 0; c < 4; c++) {
                 float v[16];
                 tmemLoad16(tD + 16*c, v);
-                if (c == ST_N/16 - 1) {                           // all columns are in registers: the slot can be refilled
+                if (c == 3) {                                     // all columns are in registers: the slot can be refilled
                     tcgen05FenceBefore();
                     __syncwarp();
                     if (lane == 0) mbarArrive(&dEmpty[b]);
@@ -527,10 +533,10 @@ __global__ void __launch_bounds__(ST_THREADS, 1) structureFactorTensorKernel(STP
         }
         const int row = rowBase + t*32 + lane;
         if (row < p.rowHi) {
-            float* out = p.part + (((size_t) blockIdx.y*p.numRows + row)*p.kzPad)*8 + q4*2;
+            float* out = p.part + (((size_t) blockIdx.y*p.numRows + row)*p.kzPad + colOff/2)*8 + q4*2;
             #pragma unroll
-            for (int l = 0; l < ST_N/2; l++)
-                if (l < p.Kz) *reinterpret_cast<float2*>(out + (size_t) l*8) = make_float2(acc[2*l], acc[2*l + 1]);
+            for (int l = 0; l < 32; l++)
+                if (colOff/2 + l < p.Kz) *reinterpret_cast<float2*>(out + (size_t) l*8) = make_float2(acc[2*l], acc[2*l + 1]);
         }
     }
     tcgen05FenceBefore();
@@ -631,7 +637,7 @@ void launchGatherTensor(State& st, long long* dForce, long long* dDedq, cudaStre
 bool structureTensorEligible(const State& st) {
     const char* mode = getenv("CFX_KSPACE_S");                  // "fp32" forces the CUDA-core kernel (A/B measurements)
     if (mode && !strcmp(mode, "fp32")) return false;
-    return st.ks.K[2] <= 32;                                    // 2*Kz columns must fit one N = 64 MMA
+    return st.ks.K[2] <= 64;                                    // 2*Kz columns must fit one N <= 128 MMA
 }
 
 void planStructureTensor(State& st) {
@@ -639,10 +645,11 @@ void planStructureTensor(State& st) {
     SGeom& t = ks.sT;
     int numSM = 148;
     cudaDeviceGetAttribute(&numSM, cudaDevAttrMultiProcessorCount, st.device);
-    t.TN = 32; t.NC = 1; t.kzPad = 32;                          // identity |nz| slots, 32 of them (GEMM N = 64)
+    const int NN = ks.K[2] <= 32 ? 64 : 128, TT = 128/NN;        // GEMM N; row tiles per CTA
+    t.TN = NN/2; t.NC = 1; t.kzPad = NN/2;                      // identity |nz| slots
     t.rowPitch = ((ks.K[0] + ks.K[1] + 1) & ~1) + t.kzPad;
     const int rowsHere = std::max(ks.rowHi - ks.rowLo, 1);
-    t.rowTiles = (rowsHere + 32*ST_TILES - 1)/(32*ST_TILES);
+    t.rowTiles = (rowsHere + 32*TT - 1)/(32*TT);
     int splits = std::max(1, numSM/t.rowTiles);
     splits = std::min(splits, std::max(1, st.Npad/(4*ST_ATOMS)));
     int aps = (st.Npad + splits - 1)/splits;
@@ -654,11 +661,12 @@ void planStructureTensor(State& st) {
     const size_t rowStagePad = (rowStage + 127) & ~(size_t) 127;
     ks.tsRowStageBytes = (uint32_t) rowStage;
     ks.tsOffA = (uint32_t) (2*rowStagePad);
-    ks.tsOffB = ks.tsOffA + 2*ST_TILES*2*ST_A_PLANE;
-    ks.tsOffBar = ks.tsOffB + 2*2*ST_B_PLANE;
+    ks.tsOffB = ks.tsOffA + 2*TT*2*ST_A_PLANE;
+    ks.tsOffBar = ks.tsOffB + 2*2*(ST_ATOMS/4)*NN*16;
     t.smem = ks.tsOffBar + 128;
     if (t.smem > 227*1024 - 256) { ks.tensorS = false; return; }
-    CFX_CUDA(cudaFuncSetAttribute(structureFactorTensorKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024));
+    CFX_CUDA(cudaFuncSetAttribute(structureFactorTensorKernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024));
+    CFX_CUDA(cudaFuncSetAttribute(structureFactorTensorKernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024));
 }
 
 void launchStructureTensor(State& st, cudaStream_t s) {
@@ -670,7 +678,8 @@ void launchStructureTensor(State& st, cudaStream_t s) {
     sp.rowLo = ks.rowLo; sp.rowHi = ks.rowHi; sp.numRows = ks.numRows;
     sp.atomsPerSplit = t.atomsPerSplit; sp.Npad = st.Npad;
     sp.rowStageBytes = ks.tsRowStageBytes; sp.offA = ks.tsOffA; sp.offB = ks.tsOffB; sp.offBar = ks.tsOffBar;
-    structureFactorTensorKernel<<<dim3(t.rowTiles, t.splits), ST_THREADS, t.smem, s>>>(sp);
+    if (t.kzPad == 32) structureFactorTensorKernel<64, 2><<<dim3(t.rowTiles, t.splits), ST_THREADS, t.smem, s>>>(sp);
+    else               structureFactorTensorKernel<128, 1><<<dim3(t.rowTiles, t.splits), ST_THREADS, t.smem, s>>>(sp);
     CFX_LAUNCH_CHECK(); st.launches++;
 }
 

@@ -46,15 +46,15 @@ def test_tensor_and_fp32_kspace_paths_agree_on_the_4k_box(build_native):
             assert abs(e_t - e_f) <= 1e-9 * np.abs(c_f[:4]).max()
 
 
-@pytest.mark.parametrize("flux", ["bond+angle", "water"])
-def test_large_kmax_variant_of_the_tensor_gather_against_the_oracle(build_native, flux):
+@pytest.mark.parametrize("cutoff,flux,kz_range", [(0.24, "bond+angle", (29, 32)), (0.24, "water", (29, 32)), (0.23, "bond+angle", (33, 56))])
+def test_large_kmax_variants_of_the_tensor_kernels_against_the_oracle(build_native, cutoff, flux, kz_range):
     """Short cutoff => large alpha => |nz| up to ~30: the gather runs its one-atom-tile / 64-column variant
-    (K padded to 64 > 56) and the structure factors still fit one N = 64 MMA."""
-    pos, box, force = synthetic.water_box(216, seed=11, cutoff=0.24, ewald_tol=1e-5, flux=flux)
+    (K padded to 64 > 56) and the structure factors still fit one N = 64 MMA; |nz| > 32 selects their N = 128 variant."""
+    pos, box, force = synthetic.water_box(216, seed=11, cutoff=cutoff, ewald_tol=1e-5, flux=flux)
     o = Oracle(force, box)
     ctx = _context(force, box, False)
     kmax = ctx.kernel.ewald_params()[1]
-    assert 29 <= kmax[2] <= 32, kmax
+    assert kz_range[0] <= kmax[2] <= kz_range[1], kmax
     eo, fo = o.execute(pos, box, True, True)
     e, f, comps = ctx.evaluate(pos, True, True)
     # alpha = 13.7/nm makes the components (2.4e5 kJ/mol) cancel to 6e2: the FP32 reciprocal sums are good to 1e-7 of

@@ -7,6 +7,7 @@ print(ctx.kernel.ewald_params())
 t=time.time(); e, frc, comps = ctx.evaluate(pos); print("first eval", time.time()-t, comps)
 print("sumF", frc.sum(0), "Fmax", np.abs(frc).max(), "finite", np.isfinite(frc).all())
 dpos = torch.tensor(pos, device='cuda')
-print("ms/eval", ctx.kernel.time_device(dpos.data_ptr(), box, 5))
-print(ctx.kernel.time_kernels(dpos.data_ptr(), box, 3))
+print("ms/eval E+F", ctx.kernel.time_device(dpos.data_ptr(), box, 5), "F only", ctx.kernel.time_device(dpos.data_ptr(), box, 5, True, False))
+print("E+F", ctx.kernel.time_kernels(dpos.data_ptr(), box, 3))
+print("F only", ctx.kernel.time_kernels(dpos.data_ptr(), box, 3, True, False))
 s = ctx.kernel.stats(); print("pairs", s.pairs_in_cutoff, "cand", s.pair_candidates, "cells", tuple(s.cells))
