@@ -281,8 +281,12 @@ def run_ours(args, pos, box, force, workload):
         raise SystemExit("bench.py needs a B200: there is no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
-        # rank 0 must print exactly one JSON line: keep NCCL's version banner off stdout
-        os.environ["NCCL_DEBUG"] = os.environ.get("CFX_NCCL_DEBUG", "WARN")
+        # rank 0 must print exactly one JSON line: NCCL's banner / debug output (NCCL_DEBUG >= VERSION) goes to a file
+        if "CFX_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["CFX_NCCL_DEBUG"]
+        else:
+            os.environ.pop("NCCL_DEBUG", None)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/cfx_nccl_%h_%p.log")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n = len(pos)
     ctx = ShardedCoulContext(force, box, rank=rank, world=world, device=local)
