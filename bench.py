@@ -451,7 +451,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--md-steps", type=int, default=500, help="length of the NVE MD leg (0 = skip)")
+    ap.add_argument("--md-steps", type=int, default=2000, help="length of the NVE MD leg (0 = skip)")
     args = ap.parse_args()
     from openmm_chargeflux_b200 import synthetic
     pos, box, force = synthetic.config(args.workload)

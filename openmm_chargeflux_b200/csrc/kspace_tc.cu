@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gatherTensorKernel(GTParams p, 
                     oY[t] = fmaf(r.y, im, oY[t]);
                     oZ[t] = fmaf(tr, vi, oZ[t]);  oZ[t] = fmaf(ti, vr, oZ[t]);
                 }
-                if (warp == GT_EPI_WARP0 && (seq == 18 || seq == 19)) GT_STAMP(seq == 18 ? 8 : 9);
+                if (warp == GT_EPI_WARP0 && (seq == 18 || seq == 19)) GT_STAMP(seq == 18 ? 14 : 15);
                 if (t == 0) {
                     #pragma unroll
                     for (int tt = 0; tt < MT; tt++) {

@@ -15,11 +15,16 @@ rc = lib.cfx_debug_gather_trace(ctx.kernel._h, buf.ctypes.data)
 print("rc", rc)
 t = buf.astype(np.int64)
 t0 = t[:, 0].min()
-names = {0: "setup done", 1: "g0 begin", 2: "g0 flush done", 3: "g0 barrier1", 4: "g0 A loads+st issued", 5: "g0 A visible+arrive", 6: "g0 barrier2 (Ey ready)",
-         20: "MMA first aFull", 21: "MMA second aFull", 8: "epi math done seq18", 9: "epi math done seq19", 19: "epi dFull seq19 seen", 7: "epi dFull seq20 seen", 10: "split u10 begin wait raw", 11: "split u10 raw arrived", 12: "split u10 op buffer free", 13: "split u10 loop done", 14: "split u10 fenced+arrived", 15: "split u10 group barrier",
-         24: "MMA commit seq18", 26: "epi dFull seq18 seen", 27: "epi arrive dEmpty seq18", 22: "MMA begin wait dEmpty seq20", 23: "MMA dEmpty seq20 seen", 25: "MMA commit seq20",
-         28: "MMA begin wait coefFull unit10", 29: "MMA coefFull unit10 seen", 30: "TMA begin wait empty for unit10", 31: "TMA issue load unit10",
-         16: "epilogue loop done", 17: "final flush done", 18: "all done"}
+names = {0: "setup done (barriers, TMEM alloc)",
+         1: "epi: group 0 begin", 2: "epi: g0 flush done", 3: "epi: g0 barrier 1", 4: "epi: g0 phase operand loads + tcgen05.st issued",
+         5: "epi: g0 operand visible, arrive", 6: "epi: g0 barrier 2 (Ey columns ready)", 20: "MMA: first phase operand seen",
+         8: "epi: group 1 begin", 9: "epi: g1 flush done", 10: "epi: g1 barrier 1", 11: "epi: g1 operand stores issued",
+         12: "epi: g1 operand visible, arrive", 13: "epi: g1 barrier 2", 21: "MMA: second phase operand seen",
+         24: "MMA: commit tile seq 18", 26: "epi: accumulator seq 18 seen", 27: "epi: slot of seq 18 released", 14: "epi: math of seq 18 done",
+         19: "epi: accumulator seq 19 seen", 15: "epi: math of seq 19 done",
+         28: "MMA: wait operand planes of unit 10", 29: "MMA: operand planes of unit 10 seen",
+         22: "MMA: wait slot for seq 20", 23: "MMA: slot for seq 20 free", 25: "MMA: commit tile seq 20", 7: "epi: accumulator seq 20 seen",
+         16: "epi: unit loop done", 17: "epi: final flush done", 18: "all roles done"}
 for cta in (0, 73):
     print("CTA", cta)
     for k in sorted(names, key=lambda k: t[cta, k] if t[cta, k] else 1 << 62):
