@@ -118,6 +118,13 @@ int  cfx_execute_device(cfx_handle* h, const double* d_positions, const double* 
                         int include_forces, int include_energy,
                         long long* d_force_fixed, long long* d_dedq_fixed, double* d_energy, void* stream);
 
+/* The same evaluation for a sharded (multi-GPU) step: d_reduce is this rank's reduction buffer, int64
+ * [3*Npad + 8] = fixed-point forces (value*2^32) followed by the CFX_E_* energies as value*2^24 (3 spare slots).
+ * The buffer is ZEROED and filled inside the call's CUDA graph, so one step of a sharded evaluation is this call
+ * plus one sum all-reduce of d_reduce (NCCL over NVLink); integer sums make the result independent of the order. */
+int  cfx_execute_shard(cfx_handle* h, const double* d_positions, const double* box,
+                       int include_forces, int include_energy, long long* d_reduce, void* stream);
+
 int  cfx_padded_num_particles(const cfx_handle* h);
 int  cfx_get_ewald_params(const cfx_handle* h, cfx_ewald_params* out);
 int  cfx_get_stats(const cfx_handle* h, cfx_stats* out);

@@ -94,6 +94,15 @@ __global__ void addEnergyKernel(const long long* __restrict__ energyFixed, doubl
     }
 }
 
+// shard mode: the four components and their sum, still fixed point, appended to the reduction buffer
+__global__ void appendEnergyFixedKernel(const long long* __restrict__ energyFixed, long long* __restrict__ out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        long long tot = 0;
+        for (int k = 0; k < 4; k++) { out[k] = energyFixed[k]; tot += energyFixed[k]; }
+        out[CFX_E_TOTAL] = tot;
+    }
+}
+
 } // namespace
 
 // The kernel sequence of one evaluation. Forces are ADDED into dForce (fixed point); dE/dq of this
@@ -412,8 +421,10 @@ int cfx_execute(cfx_handle* h, const double* positions, const double* box, int i
     CFX_CATCH
 }
 
-int cfx_execute_device(cfx_handle* h, const double* d_positions, const double* box, int include_forces, int include_energy,
-                       long long* d_force_fixed, long long* d_dedq_fixed, double* d_energy, void* stream) {
+// shared body of cfx_execute_device and cfx_execute_shard (shard: d_force_fixed is the [3*Npad + 8] reduction buffer,
+// zeroed here, energies appended as 2^24 fixed point)
+static int executeDeviceImpl(cfx_handle* h, const double* d_positions, const double* box, int include_forces, int include_energy,
+                             long long* d_force_fixed, long long* d_dedq_fixed, double* d_energy, void* stream, bool shard) {
     CFX_TRY
     if (!h) throw ArgError("null handle");
     State& st = h->st;
@@ -430,6 +441,7 @@ int cfx_execute_device(cfx_handle* h, const double* d_positions, const double* b
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     auto enqueueAll = [&]() {
+        if (shard) CFX_CUDA(cudaMemsetAsync(d_force_fixed, 0, sizeof(long long)*(3*(size_t) st.Npad + 8), s));
         enqueueEvaluation(st, d_positions, include_forces != 0, include_energy != 0, d_force_fixed, s, false);
         if (d_dedq_fixed) {
             addFixedKernel<<<(st.N + 255)/256, 256, 0, s>>>(st.N, st.dedqFixed, d_dedq_fixed);
@@ -439,13 +451,17 @@ int cfx_execute_device(cfx_handle* h, const double* d_positions, const double* b
             addEnergyKernel<<<1, 32, 0, s>>>(st.energyFixed, d_energy);
             CFX_LAUNCH_CHECK(); st.launches++;
         }
+        if (shard) {
+            appendEnergyFixedKernel<<<1, 32, 0, s>>>(st.energyFixed, d_force_fixed + 3*(size_t) st.Npad);
+            CFX_LAUNCH_CHECK(); st.launches++;
+        }
     };
     st.launches = 0;
     // the legacy default stream cannot be captured: plain launches there
     const bool capturable = s != nullptr && s != cudaStreamLegacy;
     if (st.useGraph && capturable) {
         State::DeviceGraphKey key{d_positions, d_force_fixed, d_dedq_fixed, d_energy,
-                                  (include_forces ? 1 : 0) | (include_energy ? 2 : 0), {st.box.L[0], st.box.L[1], st.box.L[2]}};
+                                  (include_forces ? 1 : 0) | (include_energy ? 2 : 0) | (shard ? 4 : 0), {st.box.L[0], st.box.L[1], st.box.L[2]}};
         const State::DeviceGraphKey& old = st.devKey;
         const bool same = old.pos == key.pos && old.force == key.force && old.dedq == key.dedq && old.energy == key.energy &&
                           old.flags == key.flags && old.L[0] == key.L[0] && old.L[1] == key.L[1] && old.L[2] == key.L[2];
@@ -469,6 +485,16 @@ int cfx_execute_device(cfx_handle* h, const double* d_positions, const double* b
     st.evaluated = true;
     return CFX_OK;
     CFX_CATCH
+}
+
+int cfx_execute_device(cfx_handle* h, const double* d_positions, const double* box, int include_forces, int include_energy,
+                       long long* d_force_fixed, long long* d_dedq_fixed, double* d_energy, void* stream) {
+    return executeDeviceImpl(h, d_positions, box, include_forces, include_energy, d_force_fixed, d_dedq_fixed, d_energy, stream, false);
+}
+
+int cfx_execute_shard(cfx_handle* h, const double* d_positions, const double* box, int include_forces, int include_energy,
+                      long long* d_reduce, void* stream) {
+    return executeDeviceImpl(h, d_positions, box, include_forces, include_energy, d_reduce, nullptr, nullptr, stream, true);
 }
 
 int cfx_padded_num_particles(const cfx_handle* h) { return h ? h->st.Npad : 0; }

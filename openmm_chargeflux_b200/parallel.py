@@ -59,18 +59,28 @@ class ShardedCoulContext:
         return self.torch.cuda.stream(self.stream) if self.stream is not None else contextlib.nullcontext()
 
     def evaluate_device(self, include_forces=True, include_energy=True):
-        """Positions already in ``self.d_pos``. Leaves the reduced results in d_force / d_energy."""
+        """Positions already in ``self.d_pos``. Leaves the reduced fixed-point results in ``d_buf``
+        (forces [3][Npad] at 2^32, then the energy components at 2^24): one library call (one CUDA graph that
+        also zeroes the buffer) and, for world > 1, one all-reduce."""
         with self._on_stream():
-            self.d_force.zero_()
-            self.d_energy.zero_()
             stream = self.stream.cuda_stream if self.stream is not None else 0
-            self.kernel.execute_device(self.d_pos.data_ptr(), self.box, self.d_force.data_ptr(), 0, self.d_energy.data_ptr(),
-                                       stream, include_forces, include_energy)
-            if self.world > 1:
+            if hasattr(self.kernel, "execute_shard"):
+                self.kernel.execute_shard(self.d_pos.data_ptr(), self.box, self.d_buf.data_ptr(), stream, include_forces, include_energy)
+            else:                                              # injected CPU backend of the gloo tests
                 t = self.torch
+                self.d_force.zero_()
+                self.d_energy.zero_()
+                self.kernel.execute_device(self.d_pos.data_ptr(), self.box, self.d_force.data_ptr(), 0, self.d_energy.data_ptr(),
+                                           stream, include_forces, include_energy)
                 self.d_buf[3 * self.npad:] = t.round(self.d_energy * ENERGY_SCALE).to(t.int64)
+            if self.world > 1:
                 self.dist.all_reduce(self.d_buf)
-                self.d_energy.copy_(self.d_buf[3 * self.npad:].to(t.float64) / ENERGY_SCALE)
+
+    def energies(self):
+        """The five energy components [self, recip, direct, excl, total] of the last evaluation (host array)."""
+        if self.stream is not None:
+            self.stream.synchronize()
+        return self.d_buf[3 * self.npad:3 * self.npad + 5].cpu().numpy().astype(np.float64) / ENERGY_SCALE
 
     def evaluate(self, positions, include_forces=True, include_energy=True):
         """Host positions in, (energy, forces[N,3], components[5]) out -- the end-to-end call."""
@@ -85,6 +95,7 @@ class ShardedCoulContext:
         self.evaluate_device(include_forces, include_energy)
         if self.stream is not None:
             self.stream.synchronize()
-        f = self.d_force.cpu().numpy().reshape(3, self.npad)[:, :self.n].T.astype(np.float64) / FIXED_SCALE
-        e = self.d_energy.cpu().numpy()[:5].copy()
+        buf = self.d_buf.cpu().numpy()
+        f = buf[:3 * self.npad].reshape(3, self.npad)[:, :self.n].T.astype(np.float64) / FIXED_SCALE
+        e = buf[3 * self.npad:3 * self.npad + 5].astype(np.float64) / ENERGY_SCALE
         return float(e[4]), np.ascontiguousarray(f), e

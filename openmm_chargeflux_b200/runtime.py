@@ -41,6 +41,7 @@ def load_library():
     lib.cfx_execute.argtypes = [C.c_void_p, _abi.c_double_p, _abi.c_double_p, C.c_int, C.c_int, _abi.c_double_p, _abi.c_double_p]
     lib.cfx_execute_device.argtypes = [C.c_void_p, C.c_void_p, _abi.c_double_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p]
+    lib.cfx_execute_shard.argtypes = [C.c_void_p, C.c_void_p, _abi.c_double_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     lib.cfx_padded_num_particles.argtypes = [C.c_void_p]
     lib.cfx_get_ewald_params.argtypes = [C.c_void_p, C.POINTER(_abi.EwaldParams)]
     lib.cfx_get_stats.argtypes = [C.c_void_p, C.POINTER(_abi.Stats)]
@@ -122,6 +123,11 @@ class CalcCoulForceKernel:
         b = _box9(box)
         self._check(self._lib.cfx_execute_device(self._h, d_positions, _dp(b), int(includeForces), int(includeEnergy),
                                                  d_force_fixed, d_dedq_fixed or None, d_energy or None, stream or None))
+
+    def execute_shard(self, d_positions, box, d_reduce, stream=0, includeForces=True, includeEnergy=True):
+        """Sharded step: zero + fill the int64 reduction buffer [3*Npad + 8] (forces 2^32, energies 2^24); asynchronous."""
+        self._check(self._lib.cfx_execute_shard(self._h, d_positions, _dp(_box9(box)), int(includeForces), int(includeEnergy),
+                                                d_reduce, stream or None))
 
     # -- derived parameters, counters, parity getters --------------------------------------------
     def padded_num_particles(self):
