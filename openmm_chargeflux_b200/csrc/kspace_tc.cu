@@ -351,7 +351,8 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gatherTensorKernel(GTParams p, 
 constexpr int ST_ATOMS = 32;                 // atoms per stage = 4 MMA k-steps
 constexpr int ST_FORM_WARPS = 8, ST_EPI_WARPS = 8;
 constexpr int ST_FORM_WARP0 = 2, ST_EPI_WARP0 = ST_FORM_WARP0 + ST_FORM_WARPS;
-constexpr int ST_THREADS = (ST_EPI_WARP0 + ST_EPI_WARPS)*32;
+constexpr int ST_MMA_WARP1 = ST_EPI_WARP0 + ST_EPI_WARPS;    // second MMA issuer (the first is warp 1)
+constexpr int ST_THREADS = (ST_MMA_WARP1 + 1)*32;
 constexpr uint32_t ST_A_PLANE = (ST_ATOMS/4)*128*16;      // bytes of one hi or lo plane of one row tile
 
 struct STParams {
@@ -409,10 +410,11 @@ __global__ void __launch_bounds__(ST_THREADS, 1) structureFactorTensorKernel(STP
         }
         __syncwarp();
     }
-    else if (warp == 1) {
-        // ---------------- MMA issuer (warp-uniform control flow, one elected lane issues) ----------------
+    else if (warp == 1 || warp == ST_MMA_WARP1) {
+        // ---------------- MMA issuers (warp-uniform control flow, one elected lane issues) ----------------
+        // two warps, one per operand buffer / accumulator slot: the waits and commits of one overlap the issue of the other
         constexpr uint32_t idesc = ummaIdescTf32(128, NN);
-        for (int st = 0; st < numStages; st++) {
+        for (int st = (warp == 1 ? 0 : 1); st < numStages; st += 2) {
             const int b = st & 1;
             const uint32_t ph = (st >> 1) & 1;
             mbarWait(&abFull[b], ph);
@@ -441,7 +443,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) structureFactorTensorKernel(STP
             __syncwarp();
         }
     }
-    else if (warp < ST_EPI_WARP0) {
+    else if (warp >= ST_FORM_WARP0 && warp < ST_EPI_WARP0) {
         // ---------------- formers: row operand A (products) and column operand Z, TF32 hi/lo planes ----------------
         const int ft = tid - ST_FORM_WARP0*32;                     // 0..255
         constexpr int A_PER = 32*TT*(ST_ATOMS/4)/(32*ST_FORM_WARPS);    // (row, quad of 4 atoms) items per thread

@@ -42,12 +42,13 @@ __device__ __forceinline__ void fenceProxyAsync() { asm volatile("fence.proxy.as
 // ---- TF32 split ----
 __device__ __forceinline__ float roundTf32(float x) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return __uint_as_float(r); }
 
-// x = hi + lo with hi, lo representable in TF32 (round to nearest, ties away, finite inputs): the integer form of
-// cvt.rna.tf32.f32 without its inf/nan handling
+// x = hi + lo: hi = x rounded to TF32 (nearest, ties away; integer form of cvt.rna.tf32.f32 for finite inputs),
+// lo = x - hi exactly (|lo| <= 2^-11 |x|, random sign). lo is NOT rounded here: the tensor core ignores the low 13
+// mantissa bits of its FP32 containers, i.e. truncates lo to TF32, an error <= 2^-22 |x| whose sign follows lo's
+// (unbiased). 3 instructions per value.
 __device__ __forceinline__ void splitTf32(float x, float& hi, float& lo) {
     hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
-    const float r = x - hi;
-    lo = __uint_as_float((__float_as_uint(r) + 0x1000u) & 0xFFFFE000u);
+    lo = x - hi;
 }
 __device__ __forceinline__ void splitTf32(const float4& v, float4& h, float4& l) {
     splitTf32(v.x, h.x, l.x); splitTf32(v.y, h.y, l.y); splitTf32(v.z, h.z, l.z); splitTf32(v.w, h.w, l.w);
