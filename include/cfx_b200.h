@@ -98,6 +98,10 @@ int  cfx_device_count(void);
 
 int  cfx_create(const cfx_system_desc* desc, const cfx_options* opts, cfx_handle** out);
 void cfx_destroy(cfx_handle* h);
+/* New parameter values (charges, sigma, epsilon, flux k/b/theta0/...) for an existing handle with the same particle
+ * and flux-term counts and the same index lists; the exception list, cutoff, tolerance and box rule are not re-read.
+ * What an `updateParametersInContext` of the API layer would call (the reference has none: SURVEY.md section 8 f4). */
+int  cfx_update_parameters(cfx_handle* h, const cfx_system_desc* desc);
 
 /* Host-buffer evaluation (the reference-facing call). positions: [3N] double, unwrapped, nm.
  * box: row-major a,b,c (only read when use_pbc). energy: [CFX_E_COUNT] written. forces: [3N] double,

@@ -43,7 +43,7 @@ class Stats(C.Structure):
 
 # every symbol include/cfx_b200.h declares (tests check the built library exports all of them)
 EXPORTED_SYMBOLS = [
-    "cfx_last_error", "cfx_device_count", "cfx_create", "cfx_destroy", "cfx_execute", "cfx_execute_device", "cfx_execute_shard",
+    "cfx_last_error", "cfx_device_count", "cfx_create", "cfx_destroy", "cfx_update_parameters", "cfx_execute", "cfx_execute_device", "cfx_execute_shard",
     "cfx_padded_num_particles", "cfx_get_ewald_params", "cfx_get_stats", "cfx_get_charges", "cfx_get_dedq",
     "cfx_num_jacobian_rows", "cfx_get_jacobian", "cfx_get_neighbor_pairs", "cfx_get_exclusions",
     "cfx_time_device", "cfx_time_kernels", "cfx_measure_fp32_peak", "cfx_measure_tf32_peak",

@@ -754,6 +754,42 @@ int cfx_measure_fp32_peak(int device, int iters, double* tflops, double* sm_cloc
 
 } // extern "C"
 
+// SURVEY.md 8 f4 (absent in the reference): new parameter VALUES for an existing handle, same topology. Only q0, the LJ
+// pre-combination and the flux-term parameters depend on them; device pointers stay, so the cached CUDA graphs stay valid.
+int cfx_update_parameters(cfx_handle* h, const cfx_system_desc* d) {
+    CFX_TRY
+    if (!h || !d) throw ArgError("null argument");
+    State& st = h->st;
+    if (d->num_particles != st.N || d->num_flux_bonds != st.nb || d->num_flux_angles != st.na || d->num_flux_waters != st.nw)
+        throw ArgError("cfx_update_parameters: particle / flux term counts differ from the handle's (topology changes need a new handle)");
+    if (st.N == 0) return CFX_OK;
+    if (!d->charge || !d->sigma || !d->epsilon) throw ArgError("null particle parameter array");
+    if ((st.nb && !d->flux_bond_params) || (st.na && !d->flux_angle_params) || (st.nw && !d->flux_water_params))
+        throw ArgError("null flux parameter array");
+    CFX_CUDA(cudaSetDevice(st.device));
+    const int N = st.N;
+    std::vector<double> q0(d->charge, d->charge + N);
+    std::vector<float2> lj(N);
+    std::vector<double2> ljd(N);
+    for (int i = 0; i < N; i++) {
+        if (!(d->epsilon[i] >= 0.0)) throw ArgError("negative LJ epsilon");
+        ljd[i] = make_double2(0.5*d->sigma[i], 2.0*sqrt(d->epsilon[i]));
+        lj[i] = make_float2((float) ljd[i].x, (float) ljd[i].y);
+    }
+    std::vector<double> termPar(5*(size_t) st.numTerms, 0.0);
+    for (int t = 0; t < st.nb; t++) { termPar[5*(size_t) t] = d->flux_bond_params[2*t]; termPar[5*(size_t) t + 1] = d->flux_bond_params[2*t+1]; }
+    for (int t = 0; t < st.na; t++) { const size_t g = (size_t) st.nb + t; termPar[5*g] = d->flux_angle_params[2*t]; termPar[5*g + 1] = d->flux_angle_params[2*t+1]; }
+    for (int t = 0; t < st.nw; t++) { const size_t g = (size_t) st.nb + st.na + t; for (int a = 0; a < 5; a++) termPar[5*g + a] = d->flux_water_params[5*t + a]; }
+    if (st.stream) CFX_CUDA(cudaStreamSynchronize(st.stream));
+    CFX_CUDA(cudaMemcpy(st.q0, q0.data(), sizeof(double)*N, cudaMemcpyHostToDevice));
+    CFX_CUDA(cudaMemcpy(st.lj, lj.data(), sizeof(float2)*N, cudaMemcpyHostToDevice));
+    CFX_CUDA(cudaMemcpy(st.ljd, ljd.data(), sizeof(double2)*N, cudaMemcpyHostToDevice));
+    if (st.numTerms) CFX_CUDA(cudaMemcpy(st.termPar, termPar.data(), sizeof(double)*termPar.size(), cudaMemcpyHostToDevice));
+    st.evaluated = false;
+    return CFX_OK;
+    CFX_CATCH
+}
+
 int cfx_measure_tf32_peak(int device, int iters, double* tflops) {
     CFX_TRY
     if (!tflops || iters < 1) throw ArgError("bad argument");

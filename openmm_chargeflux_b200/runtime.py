@@ -99,6 +99,14 @@ class CalcCoulForceKernel:
         self.num_particles = force.getNumParticles()
         del keep
 
+    def copyParametersToContext(self, default_box, force):
+        """New parameter values for the same topology (what CoulForce.updateParametersInContext would reach; the
+        reference has no such call). Index lists, exceptions, cutoff and tolerance are not re-read."""
+        desc, keep = force.to_desc(_box9(default_box).reshape(3, 3))
+        self._lib.cfx_update_parameters.argtypes = [C.c_void_p, C.c_void_p]
+        self._check(self._lib.cfx_update_parameters(self._h, C.byref(desc)))
+        del keep
+
     # CalcCoulForceKernel::execute(ContextImpl&, includeForces, includeEnergy): adds to `forces`
     # (a [N,3] float64 array, the platform's force vector) and returns the energy in kJ/mol.
     def execute(self, positions, box, forces=None, includeForces=True, includeEnergy=True, components=None):

@@ -174,3 +174,38 @@ def test_finite_difference_of_gpu_energy(build_native):
             p[a, c] -= 2 * h
             em = ctx.evaluate(p, False, True)[0]
             assert abs(-(ep - em) / (2 * h) - f[a, c]) <= 2e-3 * np.abs(f).max()
+
+
+def test_update_parameters_equals_a_fresh_handle(build_native):
+    """cfx_update_parameters: new charges / LJ / flux parameters on a live handle give exactly what a
+    handle created with them gives, and a topology change is refused."""
+    pos, box, f0 = synthetic.water_box(216, seed=3, cutoff=0.9, ewald_tol=1e-5)
+    f1 = CoulForce()                                            # same topology, other parameter values
+    for i in range(f0.getNumParticles()):
+        q, s, e = f0.getParticleParameters(i)
+        f1.addParticle(0.9 * q, 1.05 * s, 1.2 * e)
+    for x in range(f0.getNumExceptions()):
+        f1.addException(*f0.getExceptionParameters(x))
+    for t in range(f0.getNumFluxBonds()):
+        p1, p2, k, b = f0.getFluxBondParameters(t)
+        f1.addFluxBond(p1, p2, 1.3 * k, b + 0.001)
+    for t in range(f0.getNumFluxAngles()):
+        p1, p2, p3, k, th = f0.getFluxAngleParameters(t)
+        f1.addFluxAngle(p1, p2, p3, 0.7 * k, th - 0.01)
+    f1.setUsesPeriodicBoundaryConditions(True)
+    f1.setCutoffDistance(f0.getCutoffDistance())
+    f1.setEwaldErrorTolerance(f0.getEwaldErrorTolerance())
+    live = runtime.CoulContext(f0, box)
+    e_old, f_old, _ = live.evaluate(pos)
+    live.kernel.copyParametersToContext(box, f1)
+    e_new, f_new, c_new = live.evaluate(pos)
+    fresh = runtime.CoulContext(f1, box)
+    e_ref, f_ref, c_ref = fresh.evaluate(pos)
+    assert e_new == e_ref and np.array_equal(f_new, f_ref) and np.array_equal(c_new, c_ref)
+    assert abs(e_new - e_old) > 1e-3 * abs(e_old)
+    o = Oracle(f1, box)
+    eo, fo = o.execute(pos, box)
+    assert abs(e_new - eo[4]) <= E_RTOL * max(abs(eo[4]), 1e-3 * np.abs(eo[:4]).max()) and rel_rms(f_new, fo) <= F_RTOL
+    _, _, smaller = synthetic.water_box(125, seed=3, cutoff=0.9, ewald_tol=1e-5)
+    with pytest.raises(runtime.CfxError):
+        live.kernel.copyParametersToContext(box, smaller)

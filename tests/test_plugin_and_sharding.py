@@ -142,3 +142,37 @@ def test_sharded_handles_sum_to_the_unsharded_result(world, build_native):
     assert abs(es[4] - e) <= 1e-8 * abs(e)
     assert np.abs(es[:4] - comps[:4]).max() <= 1e-8 * np.abs(comps[:4]).max()
     assert rel_rms(fs, f) <= 2e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("flags", [(True, True), (True, False)])
+def test_execute_shard_fills_the_reduction_buffer_like_execute_device(flags, build_native):
+    """cfx_execute_shard = zero + forces (2^32) + energies (2^24) in one int64 buffer: summing the buffers of the shard
+    handles (what the all-reduce does) reproduces the unsharded evaluation."""
+    import torch
+    from openmm_chargeflux_b200 import runtime
+    from openmm_chargeflux_b200.parallel import ENERGY_SCALE
+    pos, box, force = synthetic.config("c2")
+    n, world = len(pos), 3
+    whole = runtime.CoulContext(force, box)
+    e, f, comps = whole.evaluate(pos, *flags)
+    d_pos = torch.tensor(pos.reshape(-1), device="cuda")
+    kernels = [runtime.CalcCoulForceKernel(shard_rank=r, shard_count=world) for r in range(world)]
+    for k in kernels:
+        k.initialize(box, force)
+    npad = kernels[0].padded_num_particles()
+    stream = torch.cuda.Stream()
+    total = torch.zeros(3 * npad + 8, dtype=torch.int64, device="cuda")
+    with torch.cuda.stream(stream):
+        for k in kernels:
+            d_reduce = torch.full((3 * npad + 8,), 12345, dtype=torch.int64, device="cuda")     # stale contents must be cleared
+            for _ in range(2):                                                                    # second call replays the graph
+                k.execute_shard(d_pos.data_ptr(), box, d_reduce.data_ptr(), stream.cuda_stream, *flags)
+            total += d_reduce
+    stream.synchronize()
+    buf = total.cpu().numpy()
+    fs = buf[:3 * npad].reshape(3, npad)[:, :n].T / FIXED_SCALE
+    es = buf[3 * npad:3 * npad + 5] / ENERGY_SCALE
+    assert abs(es[4] - e) <= 1e-8 * max(abs(e), 1e-3 * np.abs(comps[:4]).max())
+    assert abs(es[:4].sum() - es[4]) <= 1e-6
+    assert rel_rms(fs, f) <= 2e-6
