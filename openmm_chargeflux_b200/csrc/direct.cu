@@ -24,6 +24,7 @@
 #include "cfx_internal.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cmath>
 
 namespace cfx {
@@ -142,6 +143,7 @@ __global__ void __launch_bounds__(256) cellRankGatherKernel(int N, int ncy, int 
 
 struct PairParams {
     int N, Npad, numGroups, groupLo, groupHi;
+    int jSplits;                 // the (x,y) columns of an i-tile's stencil are dealt over gridDim.y CTAs (small shards)
     int ncx, ncy, ncz;
     float csx, csy, csz;
     float Lx, Ly, Lz, invLx, invLy, invLz;
@@ -357,6 +359,7 @@ __global__ void __launch_bounds__(P_WARPS*32) pairKernel(PairParams p) {
         const int offx = loX + ax;
         const int cx = modPos(c0x + offx, p.ncx);
         for (int ay = 0; ay < nY; ay++) {
+            if (p.jSplits > 1 && (ax*nY + ay) % p.jSplits != (int) blockIdx.y) continue;
             const int offy = loY + ay;
             const int cy = modPos(c0y + offy, p.ncy);
             const int rowCell = (cx*p.ncy + cy)*p.ncz;
@@ -433,7 +436,7 @@ __global__ void __launch_bounds__(P_WARPS*32) pairKernel(PairParams p) {
 }
 
 template <bool EMIT>
-void dispatchPair(const PairParams& pp, bool forces, int emode, int blocks, cudaStream_t s) {
+void dispatchPair(const PairParams& pp, bool forces, int emode, dim3 blocks, cudaStream_t s) {
     const int t = P_WARPS*32;
     if (forces) {
         if (emode == 2)      pairKernel<true, 2, EMIT><<<blocks, t, 0, s>>>(pp);
@@ -513,8 +516,17 @@ void launchDirect(State& st, const double* dPos, bool forces, int emode, bool em
     const int groups = pp.groupHi - pp.groupLo;
     if (groups <= 0) return;
     const int blocks = (groups + P_WARPS - 1)/P_WARPS;
-    if (emitPairs) dispatchPair<true>(pp, forces, emode, blocks, s);
-    else           dispatchPair<false>(pp, forces, emode, blocks, s);
+    // Deal each i-tile's stencil columns over several CTAs until ~10 CTAs per SM exist (5 with the FP64 energy queue,
+    // whose 32-pair batches fill more slowly when split): a shard with few i-tiles would otherwise run at single-CTA
+    // latency (~0.1 ms), and at one GPU 2 splits smooth the last wave (0.247 -> 0.222 ms at C3).
+    int numSM = 148;
+    cudaDeviceGetAttribute(&numSM, cudaDevAttrMultiProcessorCount, st.device);
+    pp.jSplits = std::max(1, std::min(8, ((emode == 2 ? 5 : 10)*numSM + blocks - 1)/blocks));
+    if (const char* e = getenv("CFX_PAIR_JSPLITS")) pp.jSplits = std::max(1, std::min(8, atoi(e)));     // experiments
+    if (emitPairs) pp.jSplits = 1;
+    const dim3 grid(blocks, pp.jSplits);
+    if (emitPairs) dispatchPair<true>(pp, forces, emode, grid, s);
+    else           dispatchPair<false>(pp, forces, emode, grid, s);
     CFX_LAUNCH_CHECK(); st.launches++;
     mark(st, "direct_pairs", s);
 }
