@@ -51,6 +51,9 @@ class ShardedCoulContext:
         self.d_force = self.d_buf[:3 * self.npad]
         self.d_energy = torch.zeros(8, dtype=torch.float64, device=self.device)
         self.h_pos = torch.zeros(3 * self.n, dtype=torch.float64).pin_memory() if self.device.type == "cuda" else None
+        if self.device.type == "cuda":
+            self._out_dev = torch.zeros(3 * self.n + 8, dtype=torch.float64, device=self.device)
+            self._out_host = torch.zeros(3 * self.n + 8, dtype=torch.float64).pin_memory()
         # a dedicated (capturable) stream: the step is replayed as one CUDA graph on it
         self.stream = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
 
@@ -93,9 +96,18 @@ class ShardedCoulContext:
             else:
                 self.d_pos.copy_(pos)
         self.evaluate_device(include_forces, include_energy)
-        if self.stream is not None:
-            self.stream.synchronize()
-        buf = self.d_buf.cpu().numpy()
-        f = buf[:3 * self.npad].reshape(3, self.npad)[:, :self.n].T.astype(np.float64) / FIXED_SCALE
-        e = buf[3 * self.npad:3 * self.npad + 5].astype(np.float64) / ENERGY_SCALE
-        return float(e[4]), np.ascontiguousarray(f), e
+        if self.stream is None:                                # CPU (gloo) test backend
+            buf = self.d_buf.numpy()
+            f = buf[:3 * self.npad].reshape(3, self.npad)[:, :self.n].T.astype(np.float64) / FIXED_SCALE
+            e = buf[3 * self.npad:3 * self.npad + 5].astype(np.float64) / ENERGY_SCALE
+            return float(e[4]), np.ascontiguousarray(f), e
+        # fixed point -> double and [3][Npad] -> [N][3] on the GPU, one pinned D2H of forces + energies
+        with self._on_stream():
+            out = self._out_dev
+            out[:3 * self.n] = (self.d_force.view(3, self.npad)[:, :self.n].to(torch.float64) * (1.0 / FIXED_SCALE)).t().reshape(-1)
+            out[3 * self.n:] = self.d_buf[3 * self.npad:].to(torch.float64) * (1.0 / ENERGY_SCALE)
+            self._out_host.copy_(out, non_blocking=True)
+        self.stream.synchronize()
+        host = self._out_host.numpy()
+        e = host[3 * self.n:3 * self.n + 5].copy()
+        return float(e[4]), host[:3 * self.n].reshape(self.n, 3).copy(), e
