@@ -94,6 +94,28 @@ __global__ void addEnergyKernel(const long long* __restrict__ energyFixed, doubl
     }
 }
 
+// host entry point with page-locked caller buffers: the caller's force array (mapped) += this evaluation's forces
+__global__ void addToMappedKernel(int n, const double* __restrict__ src, double* dst) {
+    const int i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i < n) dst[i] += src[i];
+}
+
+// Page-lock a caller buffer once it has been passed twice in a row (buffers that change every call are staged as
+// before: registering costs more than the copy). Returns true when `ptr` is usable for DMA / mapped access.
+bool useRegistered(State::HostReg& r, const void* ptr, size_t bytes) {
+    if (getenv("CFX_NO_HOST_REGISTER")) return false;
+    if (r.registered && r.ptr == ptr && r.bytes == bytes) return true;
+    if (r.registered) { cudaHostUnregister(const_cast<void*>(r.ptr)); cudaGetLastError(); r.registered = false; r.seen = 0; r.ptr = nullptr; }
+    if (r.ptr == ptr && r.bytes == bytes) r.seen++;
+    else { r.ptr = ptr; r.bytes = bytes; r.seen = 1; }
+    if (r.seen == 2) {
+        if (cudaHostRegister(const_cast<void*>(ptr), bytes, cudaHostRegisterMapped) == cudaSuccess &&
+            cudaHostGetDevicePointer(&r.dev, const_cast<void*>(ptr), 0) == cudaSuccess) { r.registered = true; return true; }
+        cudaGetLastError();                                      // e.g. already registered by the caller: keep staging
+    }
+    return false;
+}
+
 // shard mode: the four components and their sum, still fixed point, appended to the reduction buffer
 __global__ void appendEnergyFixedKernel(const long long* __restrict__ energyFixed, long long* __restrict__ out) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
@@ -342,6 +364,8 @@ void cfx_destroy(cfx_handle* h) {
     cudaSetDevice(st.device);
     if (st.stream) cudaStreamSynchronize(st.stream);
     dropGraphs(st);
+    if (st.posReg.registered) { cudaHostUnregister(const_cast<void*>(st.posReg.ptr)); cudaGetLastError(); }
+    if (st.forceReg.registered) { cudaHostUnregister(const_cast<void*>(st.forceReg.ptr)); cudaGetLastError(); }
     if (st.devGraph) cudaGraphExecDestroy(st.devGraph);
     freeCells(st);
     void* ptrs[] = {st.q0, st.lj, st.ljd, st.termIdx, st.termPar, st.qcsrPtr, st.qcsrSlot, st.qcsrCoef, st.rowDq, st.rowDx, st.exclPairs,
@@ -385,18 +409,31 @@ int cfx_execute(cfx_handle* h, const double* positions, const double* box, int i
         ensureCells(st);
     }
     cudaStream_t s = st.stream;
-    memcpy(st.hPos, positions, sizeof(double)*3*st.N);
+    const size_t vecBytes = sizeof(double)*3*(size_t) st.N;
+    const bool regP = useRegistered(st.posReg, positions, vecBytes);
+    const bool regF = forces && useRegistered(st.forceReg, forces, vecBytes);
+    if (!regP) memcpy(st.hPos, positions, vecBytes);
     const int key = (incF ? 1 : 0) | (incE ? 2 : 0);
     st.launches = 0;
     auto enqueueAll = [&]() {
-        CFX_CUDA(cudaMemcpyAsync(st.pos, st.hPos, sizeof(double)*3*st.N, cudaMemcpyHostToDevice, s));
+        CFX_CUDA(cudaMemcpyAsync(st.pos, regP ? positions : st.hPos, vecBytes, cudaMemcpyHostToDevice, s));
         CFX_CUDA(cudaMemsetAsync(st.forceFixed, 0, sizeof(long long)*3*st.Npad, s));
         enqueueEvaluation(st, st.pos, incF, incE, st.forceFixed, s, false);
         launchFinalize(st, st.forceFixed, s);
-        CFX_CUDA(cudaMemcpyAsync(st.hForce, st.forceOut, sizeof(double)*3*st.N, cudaMemcpyDeviceToHost, s));
+        if (regF) {
+            addToMappedKernel<<<(3*st.N + 255)/256, 256, 0, s>>>(3*st.N, st.forceOut, static_cast<double*>(st.forceReg.dev));
+            CFX_LAUNCH_CHECK(); st.launches++;
+        }
+        else
+            CFX_CUDA(cudaMemcpyAsync(st.hForce, st.forceOut, vecBytes, cudaMemcpyDeviceToHost, s));
         CFX_CUDA(cudaMemcpyAsync(st.hEnergy, st.energyOut, sizeof(double)*CFX_E_COUNT, cudaMemcpyDeviceToHost, s));
     };
     if (st.useGraph) {
+        const void* gp = regP ? positions : nullptr;
+        const void* gf = regF ? forces : static_cast<const void*>(st.hForce);      // staged: D2H always goes to hForce
+        if (st.graphs[key] && (st.graphPos[key] != gp || st.graphForce[key] != gf)) {
+            cudaGraphExecDestroy(st.graphs[key]); st.graphs[key] = nullptr;
+        }
         if (!st.graphs[key]) {
             cudaGraph_t graph;
             CFX_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
@@ -406,6 +443,7 @@ int cfx_execute(cfx_handle* h, const double* positions, const double* box, int i
             CFX_CUDA(cudaGraphInstantiate(&st.graphs[key], graph, 0));
             CFX_CUDA(cudaGraphDestroy(graph));
             st.launchesPerGraph[key] = st.launches;
+            st.graphPos[key] = gp; st.graphForce[key] = gf;
         }
         st.launches = st.launchesPerGraph[key];
         CFX_CUDA(cudaGraphLaunch(st.graphs[key], s));
@@ -415,7 +453,7 @@ int cfx_execute(cfx_handle* h, const double* positions, const double* box, int i
     CFX_CUDA(cudaStreamSynchronize(s));
     st.evaluated = true;
     if (energy) memcpy(energy, st.hEnergy, sizeof(double)*CFX_E_COUNT);
-    if (forces)
+    if (forces && !regF)
         for (size_t k = 0; k < 3*(size_t) st.N; k++) forces[k] += st.hForce[k];
     return CFX_OK;
     CFX_CATCH

@@ -173,6 +173,12 @@ struct State {
     int2* pairBuffer = nullptr; int64_t pairCapacity = 0;
     // pinned host staging
     double* hPos = nullptr; double* hForce = nullptr; double* hEnergy = nullptr;
+    // caller buffers of the host entry point that turned out to be stable across calls are page-locked in place
+    // (cudaHostRegister): positions are then DMA-read and forces accumulated by the GPU directly, no staging copies
+    struct HostReg { const void* ptr = nullptr; size_t bytes = 0; bool registered = false; int seen = 0; void* dev = nullptr; };
+    HostReg posReg, forceReg;
+    const void* graphPos[4] = {nullptr, nullptr, nullptr, nullptr};     // what each cached graph was captured with
+    const void* graphForce[4] = {nullptr, nullptr, nullptr, nullptr};
     // graphs, one per (includeForces, includeEnergy)
     cudaGraphExec_t graphs[4] = {nullptr, nullptr, nullptr, nullptr};
     int64_t launchesPerGraph[4] = {0, 0, 0, 0};
