@@ -1,25 +1,31 @@
-// kspace_tc.cu -- the reciprocal-space force / dE/dq gather of piece (3) on the 5th-generation tensor cores.
+// kspace_tc.cu -- the two reciprocal-space contractions of piece (3) on the 5th-generation tensor cores.
 //
-// After the factorisation of kspace.cu the gather is a dense contraction: for every atom a and signed row
-// r = (nx, ny)
-//     (Ur, Ui, Vr, Vi)[a][r] = sum_k Z[a][k] * C[r][comp][k],     k = (|nz| = l, cos|sin),  K = 2 Kz
-// with Z[a][2l] = cos(2 pi l z_a), Z[a][2l+1] = sin(..) and the coefficient rows
-//     Ur: (Ar, Br)   Ui: (Ai, Bi)   Vr: (l Bi, -l Ai)   Vi: (-l Br, l Ar)
-// (A, B as defined in coefficientKernel). That is a [atoms x K] x [K x 4 rows] GEMM with K ~ 56: 21 GFLOP at
-// 32k atoms. It runs as tcgen05.mma kind::tf32 with FP32 accumulators in tensor memory, made FP32-accurate by
-// the three-product split  x = hi + lo (both TF32):  Z C ~ Zlo Chi + Zhi Clo + Zhi Chi  (measured relative RMS
-// error 1.7e-7 at K = 56, tools/umma_test.cu). The epilogue (T = Ex Ey, dE/dq += Re(T U), F += q g (nx Im TU,
-// ny Im TU, Im TU')) stays on the CUDA cores, one thread per atom = per tensor-memory lane.
+// After the factorisation of kspace.cu both k-space sums are dense contractions:
+//   gather             (Ur, Ui, Vr, Vi)[a][r] = sum_k Z[a][k] * C[r][comp][k],  k = (|nz| = l, cos|sin), K = 2 Kz,
+//                      Z[a][2l] = cos(2 pi l z_a), Z[a][2l+1] = sin(..), coefficient rows Ur: (Ar, Br), Ui: (Ai, Bi),
+//                      Vr: (l Bi, -l Ai), Vi: (-l Br, l Ar) (A, B as defined in coefficientKernel): [atoms x K] x [K x 4 rows]
+//   structure factors  P[(comp,row)][(l,c|s)] = sum_atoms A[(comp,row)][atom] * Z[(l,c|s)][atom], A = q Ex(nx) x Ey(|ny|)
+// Both run as tcgen05.mma kind::tf32 with FP32 accumulators in tensor memory, made FP32-accurate by the three-product
+// split x = hi + lo: product ~ lo*hi + hi*lo + hi*hi (relative RMS error 1.7e-7 at K = 56, tools/umma_test.cu).
+// Operands are written in the K-major, no-swizzle core-matrix layout (8 rows x 16 bytes contiguous) that the UMMA
+// shared-memory descriptor addresses with two strides, so tiles can be produced by ordinary stores or one bulk-TMA copy.
 //
-// One persistent CTA per SM, three roles:
-//   warp 0     bulk-TMA producer: streams coefficient tiles (NT columns x K, hi and lo planes, stored by
-//              coefficientKernel in the canonical K-major no-swizzle core-matrix layout) through a ring of
-//              shared-memory stages
-//   warp 1     MMA issuer (one lane): A = phase tile held in tensor memory (written there once per atom group
-//              by the epilogue warps with tcgen05.st), B = coefficient stage, D = accumulator slot in TMEM
-//   warps 2-5  epilogue: tcgen05.ld the accumulator slot, apply T and accumulate the four outputs of their atom
-//              in registers; one fixed-point atomic per output when the atom group changes
-// Work units (atom group, column tile) are split contiguously over the CTAs, atom-group major.
+// gatherTensorKernel<MT, NT>: one persistent CTA per SM, work units (MT x 128 atoms, NT/4 signed rows) in contiguous
+// atom-major ranges.
+//   warp 0        bulk-TMA ring of FP32 coefficient tiles
+//   warps 2-3     MMA issuers, one per accumulator slot: A = phase operand in TENSOR MEMORY (hi, lo; written with
+//                 tcgen05.st by the epilogue warps when the atom group changes), B = coefficient hi/lo planes in shared memory
+//   warps 4-19    split the arrived FP32 tile into the TF32 hi/lo operand planes (double buffered); then, for 8 rows each:
+//                 tcgen05.ld the accumulators, release the slot, T = Ex Ey, dE/dq += Re(T U), F += q g (nx Im TU, ny Im TU,
+//                 Im TU') in registers; one fixed-point atomic per atom/output/warp when the atom group changes
+// structureFactorTensorKernel<NN, TT>: CTA = TT row tiles x one split of the atoms.
+//   warp 0        bulk-TMA of 32 atoms' phase rows per stage
+//   warps 2-9     form both operands (products + hi/lo split) in shared memory
+//   warps 1, 18   MMA issuers, one per operand buffer / accumulator slot
+//   warps 10-17   tcgen05.ld the slot after every stage and sum it in FP32 registers with round-to-nearest: the tensor
+//                 core TRUNCATES on accumulation, so long sums must not stay in tensor memory (and evaluations that
+//                 return the energy use the FP32 kernel of kspace.cu: the residual bias of |S|^2 is ~2e-7)
+// CFX_GT_TRACE=1 records %globaltimer stamps of the gather's roles (tools/gt_trace.py).
 #include "cfx_internal.cuh"
 #include "ptx_sm100.cuh"
 
