@@ -658,8 +658,16 @@ void planStructureTensor(State& st) {
     t.rowPitch = ((ks.K[0] + ks.K[1] + 1) & ~1) + t.kzPad;
     const int rowsHere = std::max(ks.rowHi - ks.rowLo, 1);
     t.rowTiles = (rowsHere + 32*TT - 1)/(32*TT);
-    int splits = std::max(1, numSM/t.rowTiles);
-    splits = std::min(splits, std::max(1, st.Npad/(4*ST_ATOMS)));
+    // atom splits: the smallest count that fills >= 95 % of the SM slots of its last wave (one CTA per SM)
+    const int maxSplits = std::max(1, st.Npad/(4*ST_ATOMS));
+    int splits = 1;
+    double bestUtil = 0.0;
+    for (int sp = 1; sp <= std::min(maxSplits, 4*numSM); sp++) {
+        const int ctas = t.rowTiles*sp;
+        const double util = (double) ctas/((double) ((ctas + numSM - 1)/numSM)*numSM);
+        if (util > bestUtil + 1e-9) { bestUtil = util; splits = sp; }
+        if (util >= 0.95) { splits = sp; break; }
+    }
     int aps = (st.Npad + splits - 1)/splits;
     aps = (aps + ST_ATOMS - 1)/ST_ATOMS*ST_ATOMS;
     t.splits = (st.Npad + aps - 1)/aps;
