@@ -19,6 +19,11 @@
 //                     F += q (2pi/L) (nx Im(T U), ny Im(T U), Im(T U')).
 //
 // All main loops are FP32 FMA; cross-CTA reductions, a_k and energies are FP64 / fixed point.
+//
+// structureFactorKernel and gatherKernel here are the CUDA-core versions: the structure-factor one serves every
+// evaluation that returns the energy (round-to-nearest sums), both serve geometries outside the tensor-core variants.
+// Whenever the geometry allows, launchKSpace runs the tcgen05 kernels of kspace_tc.cu instead (same tables, same
+// coefficient kernel).
 #include "cfx_internal.cuh"
 #include "ptx_sm100.cuh"
 
