@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(P_WARPS*32) pairKernel(PairParams p) {
     const int loZ = ominz - 2, nZ = min(omaxz - ominz + 5, p.ncz);
     const bool minImage = (omaxx - ominx + 5 > p.ncx) || (omaxy - ominy + 5 > p.ncy) || (omaxz - ominz + 5 > p.ncz);
 
-    float fx = 0.f, fy = 0.f, fz = 0.f, dq = 0.f;
+    float fx = 0.f, fy = 0.f, fz = 0.f, dq = 0.f, enf = 0.f;
     double en = 0.0;
     unsigned int nPairs = 0, nCand = 0;
     int count = 0;                                   // entries waiting in the j-tile
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(P_WARPS*32) pairKernel(PairParams p) {
                         fx = fmaf(dEdR, dx, fx); fy = fmaf(dEdR, dy, fy); fz = fmaf(dEdR, dz, fz);
                         dq = fmaf((float) CFX_ONE_4PI_EPS0*pj.w*invR, erfcv, dq);
                     }
-                    if (EMODE == 1) en += (double) (coul*erfcv + es6*(s6 - 1.f));
+                    if (EMODE == 1) enf += coul*erfcv + es6*(s6 - 1.f);      // discarded partial energy: FP32 per lane
                 }
                 if (ui < uj) {
                     nPairs++;
@@ -423,6 +423,7 @@ __global__ void __launch_bounds__(P_WARPS*32) pairKernel(PairParams p) {
         }
     }
     if (EMODE != 0) {
+        if (EMODE == 1) en = (double) enf;
         en = warpSum(en);
         // FP64 queue: each i<j pair once. FP32 terms: every pair is seen from both sides.
         if (lane == 0) atomicAddEnergy(p.energyFixed + CFX_E_DIRECT, EMODE == 2 ? en : 0.5*en);
