@@ -15,7 +15,8 @@
  *     (openmm_chargeflux_b200/plugin/) rethrows them as OpenMMException.
  *
  * Units follow OpenMM: nm, elementary charge, kJ/mol, radians. All arrays are caller-owned and only
- * read during the call; the handle owns every device allocation, stream and CUDA graph.
+ * touched during the call (the one opt-in exception is CFX_OPT_PIN_CALLER_BUFFERS below); the handle owns
+ * every device allocation, stream and CUDA graph.
  * One handle per host thread; no global state besides the per-thread last-error string.
  *
  * There is no CPU fallback: every entry point that computes fails with CFX_ERR_CUDA when no sm_100
@@ -66,13 +67,22 @@ typedef struct cfx_system_desc {
     double         default_box[9];      /* row-major a,b,c; alpha/kmax are fixed from this at create */
 } cfx_system_desc;
 
+/* cfx_options.flags. PIN_CALLER_BUFFERS: the caller promises that a positions / forces array it passes to
+ * cfx_execute stays allocated until it passes a different array or destroys the handle (true for a platform's own
+ * persistent vectors, platforms/reference/src/ReferenceCoulKernels.cpp:14-27). The library then page-locks such an
+ * array in place (cudaHostRegister) the second time it sees it, DMA-reads positions from it and accumulates forces
+ * into it directly, and unregisters it when a different array arrives or at cfx_destroy. Without the flag (default)
+ * every call stages through the handle's own pinned buffers and caller memory is only touched during the call. */
+#define CFX_OPT_PIN_CALLER_BUFFERS 1
+
 /* Execution options (all optional; pass NULL for defaults). */
 typedef struct cfx_options {
     int32_t device;        /* CUDA device ordinal; -1 = current device                              */
     int32_t shard_rank;    /* this handle's rank in a k-vector / spatial-tile sharded evaluation     */
     int32_t shard_count;   /* number of ranks sharing one evaluation (1 = whole evaluation here)     */
     int32_t use_graph;     /* 1 = replay the step as one CUDA graph (default), 0 = plain launches    */
-    int32_t reserved[4];
+    int32_t flags;         /* CFX_OPT_* bits                                                         */
+    int32_t reserved[3];
 } cfx_options;
 
 typedef struct cfx_handle cfx_handle;

@@ -7,6 +7,7 @@ three can be driven with identical inputs.
 import ctypes as C
 
 CFX_OK, CFX_ERR_ARGUMENT, CFX_ERR_CUDA, CFX_ERR_STATE = 0, 1, 2, 3
+OPT_PIN_CALLER_BUFFERS = 1
 E_SELF, E_RECIP, E_DIRECT, E_EXCL, E_TOTAL, E_COUNT = 0, 1, 2, 3, 4, 5
 ONE_4PI_EPS0 = 138.935456
 
@@ -29,7 +30,7 @@ class SystemDesc(C.Structure):
 
 class Options(C.Structure):
     _fields_ = [("device", C.c_int32), ("shard_rank", C.c_int32), ("shard_count", C.c_int32),
-                ("use_graph", C.c_int32), ("reserved", C.c_int32 * 4)]
+                ("use_graph", C.c_int32), ("flags", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
 class EwaldParams(C.Structure):

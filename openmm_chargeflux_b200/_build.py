@@ -33,7 +33,7 @@ def _newer(target, sources):
 def build_cuda(force=False, verbose=False):
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     sources = [os.path.join(CSRC, f) for f in ("api.cu", "flux.cu", "kspace.cu", "kspace_tc.cu", "direct.cu", "md.cu")]
-    deps = sources + [os.path.join(CSRC, "cfx_internal.cuh"), os.path.join(ROOT, "include", "cfx_b200.h")]
+    deps = sources + [os.path.join(CSRC, "cfx_internal.cuh"), os.path.join(CSRC, "ptx_sm100.cuh"), os.path.join(ROOT, "include", "cfx_b200.h")]
     if not force and not _newer(LIB, deps):
         return LIB
     cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + sources
@@ -46,8 +46,10 @@ def build_cuda(force=False, verbose=False):
 def build_plugin(force=False, verbose=False):
     """The KernelFactory-registered adapter; needs the plugin's own openmmapi headers."""
     api_inc = os.path.join(REF, "openmmapi", "include")
-    ref_out = os.path.join(ROOT, "oracle", "_ref")
-    if not os.path.isdir(api_inc) or not os.path.exists(os.path.join(ref_out, "libOpenMMCoul.so")):
+    # the OpenMM stand-in and the plugin's unchanged API library (built by oracle/Makefile from the reference tree):
+    # what a real installation provides as libOpenMM.so / libOpenMMCoul.so
+    api_out = os.path.join(ROOT, "shim", "_build")
+    if not os.path.isdir(api_inc) or not os.path.exists(os.path.join(api_out, "libOpenMMCoul.so")):
         return PLUGIN_LIB if os.path.exists(PLUGIN_LIB) else None
     src_dir = os.path.join(PKG, "plugin")
     sources = [os.path.join(src_dir, f) for f in ("B200CoulKernels.cpp", "B200CoulKernelFactory.cpp")]
@@ -57,8 +59,8 @@ def build_plugin(force=False, verbose=False):
         return PLUGIN_LIB
     cmd = ["g++", "-O2", "-fPIC", "-std=c++17", "-shared", "-I" + os.path.join(ROOT, "shim"), "-I" + api_inc,
            "-I" + os.path.join(ROOT, "include"), "-o", PLUGIN_LIB] + sources + [
-           "-L" + ref_out, "-lOpenMMCoul", "-lOpenMMShim", "-L" + PKG, "-lcfx_b200",
-           "-Wl,-rpath,$ORIGIN/../../oracle/_ref", "-Wl,-rpath,$ORIGIN/.."]
+           "-L" + api_out, "-lOpenMMCoul", "-lOpenMMShim", "-L" + PKG, "-lcfx_b200",
+           "-Wl,-rpath,$ORIGIN/../../shim/_build", "-Wl,-rpath,$ORIGIN/.."]
     if verbose:
         print(" ".join(cmd))
     subprocess.run(cmd, check=True)

@@ -60,10 +60,12 @@ void checkBox(const double* box) {
 }
 
 void setBox(State& st, const double* box) {
+    st.planGeneration++;
     for (int d = 0; d < 3; d++) { st.box.L[d] = box[4*d]; st.box.invL[d] = 1.0/box[4*d]; }
 }
 
 void freeCells(State& st) {
+    st.planGeneration++;
     cudaFree(st.cellOfAtom); cudaFree(st.cellCount); cudaFree(st.cellStart); cudaFree(st.cellFill);
     cudaFree(st.userLocal); cudaFree(st.sortedLocal); cudaFree(st.sortedCell); cudaFree(st.sortedLJ); cudaFree(st.sortedUser);
     cudaFree(st.pairCounters); cudaFree(st.filledUser); st.filledUser = nullptr;
@@ -72,6 +74,7 @@ void freeCells(State& st) {
 }
 
 void dropGraphs(State& st) {
+    st.planGeneration++;
     for (int k = 0; k < 4; k++)
         if (st.graphs[k]) { cudaGraphExecDestroy(st.graphs[k]); st.graphs[k] = nullptr; }
     if (st.devGraph) { cudaGraphExecDestroy(st.devGraph); st.devGraph = nullptr; }
@@ -100,10 +103,12 @@ __global__ void addToMappedKernel(int n, const double* __restrict__ src, double*
     if (i < n) dst[i] += src[i];
 }
 
-// Page-lock a caller buffer once it has been passed twice in a row (buffers that change every call are staged as
-// before: registering costs more than the copy). Returns true when `ptr` is usable for DMA / mapped access.
-bool useRegistered(State::HostReg& r, const void* ptr, size_t bytes) {
-    if (getenv("CFX_NO_HOST_REGISTER")) return false;
+// Only for handles created with CFX_OPT_PIN_CALLER_BUFFERS (the caller promises that a buffer it passes stays allocated
+// until it passes a different one or destroys the handle): page-lock a caller buffer once it has been passed twice in a
+// row (buffers that change every call are staged: registering costs more than the copy). Returns true when `ptr` is
+// usable for DMA / mapped access.
+bool useRegistered(const State& st, State::HostReg& r, const void* ptr, size_t bytes) {
+    if (!st.pinCallerBuffers) return false;                     // opt-in: cfx_options.flags & CFX_OPT_PIN_CALLER_BUFFERS
     if (r.registered && r.ptr == ptr && r.bytes == bytes) return true;
     if (r.registered) { cudaHostUnregister(const_cast<void*>(r.ptr)); cudaGetLastError(); r.registered = false; r.seen = 0; r.ptr = nullptr; }
     if (r.ptr == ptr && r.bytes == bytes) r.seen++;
@@ -205,9 +210,11 @@ int cfx_device_count(void) {
 }
 
 int cfx_create(const cfx_system_desc* d, const cfx_options* opts, cfx_handle** out) {
-    cfx_handle* h = nullptr;
+    // a failed create must not leak the handle, its streams, pinned buffers or device allocations
+    struct Guard { cfx_handle* h = nullptr; ~Guard() { if (h) cfx_destroy(h); } } guard;
     CFX_TRY
     if (!d || !out) throw ArgError("null argument");
+    *out = nullptr;
     const int N = d->num_particles;
     if (N < 0) throw ArgError("negative particle count");
     if (N > 0 && (!d->charge || !d->sigma || !d->epsilon)) throw ArgError("null particle parameter array");
@@ -216,7 +223,11 @@ int cfx_create(const cfx_system_desc* d, const cfx_options* opts, cfx_handle** o
         cudaGetLastError();
         throw std::runtime_error("no CUDA device available: libcfx_b200 has no CPU fallback");
     }
-    h = new cfx_handle();
+    if ((d->num_exceptions > 0 && !d->exception_pairs) || (d->num_flux_bonds > 0 && (!d->flux_bond_idx || !d->flux_bond_params)) ||
+        (d->num_flux_angles > 0 && (!d->flux_angle_idx || !d->flux_angle_params)) ||
+        (d->num_flux_waters > 0 && (!d->flux_water_idx || !d->flux_water_params)))
+        throw ArgError("null index / parameter array with a non-zero count");
+    cfx_handle* h = guard.h = new cfx_handle();
     State& st = h->st;
     int dev = (opts && opts->device >= 0) ? opts->device : -1;
     if (dev < 0) CFX_CUDA(cudaGetDevice(&dev));
@@ -230,6 +241,9 @@ int cfx_create(const cfx_system_desc* d, const cfx_options* opts, cfx_handle** o
     st.shardCount = (opts && opts->shard_count > 0) ? opts->shard_count : 1;
     if (st.shardRank < 0 || st.shardRank >= st.shardCount) throw ArgError("shard_rank out of range");
     st.useGraph = opts ? (opts->use_graph != 0) : true;
+    st.pinCallerBuffers = opts && (opts->flags & CFX_OPT_PIN_CALLER_BUFFERS);
+    if (d->use_pbc == 0 && st.shardCount != 1)
+        throw ArgError("sharded handles need a periodic system: the non-periodic all-pairs branch is not partitioned");
     st.N = N;
     st.Npad = std::max(256, (N + 255)/256*256);
     st.nb = d->num_flux_bonds; st.na = d->num_flux_angles; st.nw = d->num_flux_waters;
@@ -351,11 +365,10 @@ int cfx_create(const cfx_system_desc* d, const cfx_options* opts, cfx_handle** o
             planCells(st);
         }
     }
+    guard.h = nullptr;
     *out = h;
     return CFX_OK;
     CFX_CATCH
-    if (h) cfx_destroy(h);
-    return CFX_ERR_CUDA;
 }
 
 void cfx_destroy(cfx_handle* h) {
@@ -399,19 +412,12 @@ int cfx_execute(cfx_handle* h, const double* positions, const double* box, int i
     const bool incF = include_forces != 0, incE = include_energy != 0;
     if (st.pbc) {
         if (!box) throw ArgError("null box for a periodic system");
-        checkBox(box);
-        if (box[0] < 2*st.cutoff || box[4] < 2*st.cutoff || box[8] < 2*st.cutoff)
-            throw ArgError("the periodic box must be at least twice the cutoff in every direction");
-        if (st.box.L[0] != box[0] || st.box.L[1] != box[4] || st.box.L[2] != box[8]) {
-            setBox(st, box);
-            dropGraphs(st);
-        }
-        ensureCells(st);
+        ensureBox(st, box);
     }
     cudaStream_t s = st.stream;
     const size_t vecBytes = sizeof(double)*3*(size_t) st.N;
-    const bool regP = useRegistered(st.posReg, positions, vecBytes);
-    const bool regF = forces && useRegistered(st.forceReg, forces, vecBytes);
+    const bool regP = useRegistered(st, st.posReg, positions, vecBytes);
+    const bool regF = forces && useRegistered(st, st.forceReg, forces, vecBytes);
     if (!regP) memcpy(st.hPos, positions, vecBytes);
     const int key = (incF ? 1 : 0) | (incE ? 2 : 0);
     st.launches = 0;
@@ -452,6 +458,7 @@ int cfx_execute(cfx_handle* h, const double* positions, const double* box, int i
         enqueueAll();
     CFX_CUDA(cudaStreamSynchronize(s));
     st.evaluated = true;
+    st.stagedPosCurrent = true;
     if (energy) memcpy(energy, st.hEnergy, sizeof(double)*CFX_E_COUNT);
     if (forces && !regF)
         for (size_t k = 0; k < 3*(size_t) st.N; k++) forces[k] += st.hForce[k];
@@ -471,11 +478,7 @@ static int executeDeviceImpl(cfx_handle* h, const double* d_positions, const dou
     CFX_CUDA(cudaSetDevice(st.device));
     if (st.pbc) {
         if (!box) throw ArgError("null box for a periodic system");
-        checkBox(box);
-        if (box[0] < 2*st.cutoff || box[4] < 2*st.cutoff || box[8] < 2*st.cutoff)
-            throw ArgError("the periodic box must be at least twice the cutoff in every direction");
-        if (st.box.L[0] != box[0] || st.box.L[1] != box[4] || st.box.L[2] != box[8]) { setBox(st, box); dropGraphs(st); }
-        ensureCells(st);
+        ensureBox(st, box);
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     auto enqueueAll = [&]() {
@@ -521,6 +524,7 @@ static int executeDeviceImpl(cfx_handle* h, const double* d_positions, const dou
     else
         enqueueAll();
     st.evaluated = true;
+    st.stagedPosCurrent = false;
     return CFX_OK;
     CFX_CATCH
 }
@@ -613,6 +617,9 @@ int cfx_get_neighbor_pairs(cfx_handle* h, int32_t* pairs, int64_t capacity, int6
     State& st = h->st;
     if (!st.pbc) throw StateError("neighbour pairs exist only for periodic systems");
     requireEvaluated(st);
+    if (!st.stagedPosCurrent)
+        throw StateError("neighbour pairs are rebuilt from the positions of the last cfx_execute; the last evaluation on this handle "
+                         "went through a device-pointer / timing / MD entry point");
     unsigned long long c[4];
     CFX_CUDA(cudaMemcpy(c, st.pairCounters, sizeof(c), cudaMemcpyDeviceToHost));
     *count = (int64_t) c[0];
@@ -660,10 +667,10 @@ int cfx_time_device(cfx_handle* h, const double* d_positions, const double* box,
     State& st = h->st;
     CFX_CUDA(cudaSetDevice(st.device));
     if (st.pbc) {
-        checkBox(box);
-        if (st.box.L[0] != box[0] || st.box.L[1] != box[4] || st.box.L[2] != box[8]) { setBox(st, box); dropGraphs(st); }
-        ensureCells(st);
+        if (!box) throw ArgError("null box for a periodic system");
+        ensureBox(st, box);
     }
+    st.stagedPosCurrent = false;
     cudaStream_t s = st.stream;
     // one evaluation = one graph of kernels only (inputs already resident in HBM)
     cudaGraph_t graph; cudaGraphExec_t exec;
@@ -701,10 +708,10 @@ int cfx_time_kernels(cfx_handle* h, const double* d_positions, const double* box
     State& st = h->st;
     CFX_CUDA(cudaSetDevice(st.device));
     if (st.pbc) {
-        checkBox(box);
-        if (st.box.L[0] != box[0] || st.box.L[1] != box[4] || st.box.L[2] != box[8]) { setBox(st, box); dropGraphs(st); }
-        ensureCells(st);
+        if (!box) throw ArgError("null box for a periodic system");
+        ensureBox(st, box);
     }
+    st.stagedPosCurrent = false;
     cudaStream_t s = st.stream;
     std::vector<std::string> labels;
     std::vector<double> acc;

@@ -123,6 +123,7 @@ struct State {
     double cutoff = 0, tol = 0, alpha = 0;
     int device = 0, shardRank = 0, shardCount = 1;
     bool useGraph = true;
+    bool pinCallerBuffers = false;      // cfx_options.flags & CFX_OPT_PIN_CALLER_BUFFERS
     KSpacePlan ks;
     CellPlan cells;
     int64_t numKVectors = 0;
@@ -188,6 +189,8 @@ struct State {
     DeviceGraphKey devKey = {nullptr, nullptr, nullptr, nullptr, -1, {0, 0, 0}};
     int64_t devGraphLaunches = 0;
     bool evaluated = false;
+    bool stagedPosCurrent = false;      // st.pos holds the positions of the last evaluation (host entry point only)
+    uint64_t planGeneration = 0;        // bumped whenever box-dependent plans / buffers change (external graphs must re-capture)
     int64_t launches = 0;
     Box box;
     // host copies for getters

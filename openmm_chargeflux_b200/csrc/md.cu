@@ -20,6 +20,7 @@ struct cfx_md {
     double box[9];
     cudaGraphExec_t stepGraph = nullptr;
     double graphDt = -1.0;
+    uint64_t graphPlanGen = 0;          // State::planGeneration the step graph was captured with
     bool forcesCurrent = false;
 };
 
@@ -136,6 +137,8 @@ void computeForces(cfx_md* md, cudaStream_t s, bool withEnergy) {
         CFX_LAUNCH_CHECK();
     }
     enqueueEvaluation(st, md->pos, true, withEnergy, md->force, s, true);
+    st.stagedPosCurrent = false;                 // the handle's staged positions no longer match its last evaluation
+    st.evaluated = true;
 }
 
 template <class T> T* dupload(const T* src, size_t n) {
@@ -158,10 +161,13 @@ int cfx_md_create(cfx_handle* h, const double* masses, int32_t nb, const int32_t
     if (!h || !masses || !out) { setLastError("null argument"); return CFX_ERR_ARGUMENT; }
     State& st = h->st;
     if (!st.pbc) { setLastError("the MD harness needs a periodic system"); return CFX_ERR_ARGUMENT; }
+    if (st.shardCount != 1) { setLastError("the MD harness integrates whole forces: it needs an unsharded handle"); return CFX_ERR_ARGUMENT; }
+    if ((nb > 0 && (!bondIdx || !bondPar)) || (na > 0 && (!angleIdx || !anglePar))) { setLastError("null bonded-term array"); return CFX_ERR_ARGUMENT; }
     for (int i = 0; i < 2*nb; i++) if (bondIdx[i] < 0 || bondIdx[i] >= st.N) { setLastError("bond index out of range"); return CFX_ERR_ARGUMENT; }
     for (int i = 0; i < 3*na; i++) if (angleIdx[i] < 0 || angleIdx[i] >= st.N) { setLastError("angle index out of range"); return CFX_ERR_ARGUMENT; }
     CFX_CUDA(cudaSetDevice(st.device));
-    cfx_md* md = new cfx_md();
+    struct Guard { cfx_md* md = nullptr; ~Guard() { if (md) cfx_md_destroy(md); } } guard;     // no leak when an allocation below throws
+    cfx_md* md = guard.md = new cfx_md();
     md->h = h; md->N = st.N; md->Npad = st.Npad; md->nb = nb; md->na = na;
     md->mass = dupload(masses, st.N);
     md->bondIdx = dupload(bondIdx, 2*(size_t) nb); md->bondPar = dupload(bondPar, 2*(size_t) nb);
@@ -173,6 +179,7 @@ int cfx_md_create(cfx_handle* h, const double* masses, int32_t nb, const int32_t
     CFX_CUDA(cudaMalloc(&md->scratch, sizeof(long long)*4));
     for (int k = 0; k < 9; k++) md->box[k] = 0.0;
     md->box[0] = st.box.L[0]; md->box[4] = st.box.L[1]; md->box[8] = st.box.L[2];
+    guard.md = nullptr;
     *out = md;
     return CFX_OK;
     MD_CATCH
@@ -240,7 +247,9 @@ int cfx_md_step(cfx_md* md, int32_t nsteps, double dt, float* msElapsed) {
     ensureBox(st, md->box);
     cudaStream_t s = st.stream;
     if (!md->forcesCurrent) { computeForces(md, s, false); md->forcesCurrent = true; }
-    if (!md->stepGraph || md->graphDt != dt) {
+    // the step graph captures the handle's cell-list buffers and box-dependent kernel arguments by value: any re-plan
+    // of the handle (box change through another entry point) invalidates it
+    if (!md->stepGraph || md->graphDt != dt || md->graphPlanGen != st.planGeneration) {
         if (md->stepGraph) { cudaGraphExecDestroy(md->stepGraph); md->stepGraph = nullptr; }
         cudaGraph_t graph;
         CFX_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
@@ -257,6 +266,7 @@ int cfx_md_step(cfx_md* md, int32_t nsteps, double dt, float* msElapsed) {
         CFX_CUDA(cudaGraphInstantiate(&md->stepGraph, graph, 0));
         CFX_CUDA(cudaGraphDestroy(graph));
         md->graphDt = dt;
+        md->graphPlanGen = st.planGeneration;
     }
     cudaEvent_t e0, e1;
     CFX_CUDA(cudaEventCreate(&e0)); CFX_CUDA(cudaEventCreate(&e1));

@@ -55,9 +55,13 @@ void B200CalcCoulForceKernel::initialize(const System& system, const CoulForce& 
     for (int a = 0; a < 3; a++)
         for (int c = 0; c < 3; c++)
             d.default_box[3*a+c] = box[a][c];
-    check(cfx_create(&d, NULL, &handle), "B200CalcCoulForceKernel::initialize");
-    positions.resize(3*numParticles);
-    forces.resize(3*numParticles);
+    // The platform's position and force vectors live as long as the Context and are handed to every execute(): let the
+    // library page-lock them in place instead of staging (include/cfx_b200.h, CFX_OPT_PIN_CALLER_BUFFERS).
+    cfx_options opts;
+    opts.device = -1; opts.shard_rank = 0; opts.shard_count = 1; opts.use_graph = 1;
+    opts.flags = CFX_OPT_PIN_CALLER_BUFFERS;
+    for (int k = 0; k < 3; k++) opts.reserved[k] = 0;
+    check(cfx_create(&d, &opts, &handle), "B200CalcCoulForceKernel::initialize");
 }
 
 double B200CalcCoulForceKernel::execute(ContextImpl& context, bool includeForces, bool includeEnergy) {
@@ -69,14 +73,12 @@ double B200CalcCoulForceKernel::execute(ContextImpl& context, bool includeForces
     for (int a = 0; a < 3; a++)
         for (int c = 0; c < 3; c++)
             box[3*a+c] = boxVectors[a][c];
-    for (int i = 0; i < numParticles; i++)
-        for (int c = 0; c < 3; c++) {
-            positions[3*i+c] = pos[i][c];
-            forces[3*i+c] = 0.0;
-        }
-    check(cfx_execute(handle, positions.data(), box, includeForces, includeEnergy, lastEnergy, forces.data()),
+    // vector<Vec3> is [N][3] doubles, the layout cfx_execute takes; it ADDS to the force array as the reference kernel
+    // does (ReferenceCoulKernels.cpp:455-630), so the platform's own vectors are passed straight through.
+    static_assert(sizeof(Vec3) == 3*sizeof(double), "Vec3 must be three packed doubles");
+    if ((int) pos.size() < numParticles || (int) frc.size() < numParticles)
+        throw OpenMMException("B200CalcCoulForceKernel::execute: platform vectors are smaller than the System");
+    check(cfx_execute(handle, numParticles ? &pos[0][0] : NULL, box, includeForces, includeEnergy, lastEnergy, numParticles ? &frc[0][0] : NULL),
           "B200CalcCoulForceKernel::execute");
-    for (int i = 0; i < numParticles; i++)
-        frc[i] += Vec3(forces[3*i], forces[3*i+1], forces[3*i+2]);
     return lastEnergy[CFX_E_TOTAL];
 }

@@ -36,7 +36,6 @@ private:
     cfx_handle* handle;
     int numParticles;
     double lastEnergy[CFX_E_COUNT];
-    std::vector<double> positions, forces;
 };
 
 } // namespace CoulPlugin

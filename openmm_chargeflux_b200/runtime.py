@@ -77,10 +77,13 @@ class CalcCoulForceKernel:
     def Name():
         return "CalcCoulForce"      # CoulKernels.h:17-19
 
-    def __init__(self, device=-1, shard_rank=0, shard_count=1, use_graph=True):
+    def __init__(self, device=-1, shard_rank=0, shard_count=1, use_graph=True, pin_caller_buffers=False):
+        """pin_caller_buffers: the caller keeps the positions / forces arrays it passes to execute() alive until it passes
+        different ones or closes the kernel; they are then page-locked in place (CFX_OPT_PIN_CALLER_BUFFERS)."""
         self._lib = load_library()
         self._opts = _abi.Options(device=device, shard_rank=shard_rank, shard_count=shard_count,
-                                  use_graph=1 if use_graph else 0)
+                                  use_graph=1 if use_graph else 0,
+                                  flags=_abi.OPT_PIN_CALLER_BUFFERS if pin_caller_buffers else 0)
         self._h = None
         self.num_particles = 0
 
