@@ -67,10 +67,10 @@ void setBox(State& st, const double* box) {
 void freeCells(State& st) {
     st.planGeneration++;
     cudaFree(st.cellOfAtom); cudaFree(st.cellCount); cudaFree(st.cellStart); cudaFree(st.cellFill);
-    cudaFree(st.userLocal); cudaFree(st.sortedLocal); cudaFree(st.sortedCell); cudaFree(st.sortedLJ); cudaFree(st.sortedUser);
+    cudaFree(st.userLocal); cudaFree(st.sortedLocal); cudaFree(st.sortedMeta);
     cudaFree(st.pairCounters); cudaFree(st.filledUser); st.filledUser = nullptr;
-    st.cellOfAtom = st.cellCount = st.cellStart = st.cellFill = st.sortedCell = st.sortedUser = nullptr;
-    st.userLocal = st.sortedLocal = nullptr; st.sortedLJ = nullptr; st.pairCounters = nullptr;
+    st.cellOfAtom = st.cellCount = st.cellStart = st.cellFill = nullptr;
+    st.userLocal = st.sortedLocal = st.sortedMeta = nullptr; st.pairCounters = nullptr;
 }
 
 void dropGraphs(State& st) {
@@ -150,16 +150,16 @@ void enqueueEvaluation(State& st, const double* dPos, bool includeForces, bool i
             // overlap with the k-space kernels. Fork/join are captured into the step's CUDA graph.
             CFX_CUDA(cudaEventRecord(st.evFork, s));
             CFX_CUDA(cudaStreamWaitEvent(st.sideStream, st.evFork, 0));
+            launchExclusionCorrection(st, dPos, includeForces, dForce, st.dedqFixed, st.sideStream);   // first: see flux.cu
             launchDirect(st, dPos, includeForces, emode, false, dForce, st.dedqFixed, st.sideStream);
-            launchExclusionCorrection(st, dPos, includeForces, dForce, st.dedqFixed, st.sideStream);
             CFX_CUDA(cudaEventRecord(st.evJoin, st.sideStream));
             launchKSpace(st, dPos, includeForces, includeEnergy, dForce, st.dedqFixed, s);
             CFX_CUDA(cudaStreamWaitEvent(s, st.evJoin, 0));
         }
         else {
             launchKSpace(st, dPos, includeForces, includeEnergy, dForce, st.dedqFixed, s);
-            launchDirect(st, dPos, includeForces, emode, false, dForce, st.dedqFixed, s);
             launchExclusionCorrection(st, dPos, includeForces, dForce, st.dedqFixed, s);
+            launchDirect(st, dPos, includeForces, emode, false, dForce, st.dedqFixed, s);
         }
     }
     else
@@ -561,7 +561,7 @@ int cfx_get_stats(const cfx_handle* hc, cfx_stats* out) {
         CFX_CUDA(cudaSetDevice(st.device));
         CFX_CUDA(cudaDeviceSynchronize());
         CFX_CUDA(cudaMemcpy(c, st.pairCounters, sizeof(c), cudaMemcpyDeviceToHost));
-        out->pairs_in_cutoff = (int64_t) c[0];
+        out->pairs_in_cutoff = (int64_t) (c[0]/2);          // the kernel counts every pair from both sides
         out->pair_candidates = (int64_t) c[1];
     }
     return CFX_OK;
@@ -622,7 +622,7 @@ int cfx_get_neighbor_pairs(cfx_handle* h, int32_t* pairs, int64_t capacity, int6
                          "went through a device-pointer / timing / MD entry point");
     unsigned long long c[4];
     CFX_CUDA(cudaMemcpy(c, st.pairCounters, sizeof(c), cudaMemcpyDeviceToHost));
-    *count = (int64_t) c[0];
+    *count = (int64_t) (c[0]/2);                         // the kernel counts every pair from both sides
     if (!pairs) return CFX_OK;
     if (capacity < *count) throw ArgError("pair buffer too small");
     if (st.pairCapacity < *count) {

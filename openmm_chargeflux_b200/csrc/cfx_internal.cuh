@@ -7,8 +7,8 @@
 //                per-index phase columns, n-major  Ex/Ey[n][Npad], Z4[l][Npad] = (c, s, l*c, l*s)
 //                structure-factor partials         part[split][row][col][8] (float)
 //                gather coefficients               coef[signedRow][Kz] (float4: Ar, Ai, Br, Bi)
-//   direct     : atoms sorted by cell: sortedLocal (float4: local xyz in cell, q), sortedCell (packed
-//                cell coordinates), sortedLJ (float2), sortedUser (user index), cellStart[ncell+1]
+//   direct     : atoms sorted by cell: sortedLocal (float4: local xyz in cell, q), sortedMeta (float4: sigma/2,
+//                2 sqrt(eps), user index, packed cell coordinates), cellStart[ncell+1]
 #pragma once
 
 #include <cuda_runtime.h>
@@ -168,7 +168,8 @@ struct State {
     // direct space
     int* cellOfAtom = nullptr; int* cellCount = nullptr; int* cellStart = nullptr; int* cellFill = nullptr;
     float4* userLocal = nullptr;        // [N] local xyz in own cell + q, user order (scratch of the cell build)
-    float4* sortedLocal = nullptr; int* sortedCell = nullptr; float2* sortedLJ = nullptr; int* sortedUser = nullptr;
+    float4* sortedLocal = nullptr;      // [N] atoms sorted by cell, z inside the cell: local xyz + q
+    float4* sortedMeta = nullptr;       // [N] (sigma/2, 2 sqrt(eps), user index, packed cell coordinates)
     int* filledUser = nullptr;          // cell fill in arrival order (input of the rank pass)
     unsigned long long* pairCounters = nullptr;   // [4]: pairs in cutoff, candidates, emitted, overflow
     int2* pairBuffer = nullptr; int64_t pairCapacity = 0;

@@ -4,28 +4,38 @@
 // The reference rebuilds a neighbour list every call (all i<j, not excluded, min-image r2 <= rc2) and
 // evaluates erfc Coulomb + Lennard-Jones on it in FP64. Here:
 //
-//  cell build   atoms are wrapped (FP64), binned into cells of edge >= rc/2 and sorted by cell with a
-//               deterministic order inside each cell; each sorted atom keeps its position as a FP32
-//               offset inside its own cell, so pair separations are formed from small numbers
-//               (cell-relative coordinates: no loss of precision in large boxes).
-//  pair kernel  one warp per i-tile of 8 consecutive sorted atoms, 4 lanes per i atom. Candidate j
-//               atoms from the 5x5x5 cell stencil are pruned against the i-tile's bounding box and
-//               compacted (ballot) into a 32-entry j-tile in shared memory; each lane then walks its
-//               quarter of the j-tile. Forces and dE/dq are accumulated together in registers and
-//               reduced over the 4 lanes of an i atom with warp shuffles. Every ordered pair is
-//               evaluated once from each side (full shell): no j-side atomics.
-//  exactness    the in-cutoff predicate of a pair whose FP32 r2 falls within 1e-5 of rc2 is re-evaluated
-//               in FP64 on the original coordinates with the reference's operation order, so the
-//               neighbour set is bit-exact. Exclusions are looked up in the per-atom CSR.
+//  cell build   atoms are wrapped (FP64), binned into cells of edge >= rc/2 and sorted by cell (z fastest) and, inside a
+//               cell, by z: a column of cells is one z-ordered run of atoms, so 8 consecutive sorted atoms -- an
+//               i-cluster -- occupy a flat slab of the column (about 0.53 x 0.53 x 0.29 nm in water) and their bounding
+//               box prunes well. Each sorted atom keeps its position as a FP32 offset inside its own cell, so pair
+//               separations are formed from small numbers (no loss of precision in large boxes).
+//  pair kernel  one warp per i-cluster, 4 lanes per i atom. The warp walks the (x, y) columns of the 5x5 stencil; per
+//               column the z range is clipped to the sphere of radius rc around the cluster's bounding box; candidates
+//               are tested against the bounding box 32 at a time and ballot-compacted into two 64-entry rings in shared
+//               memory (j atoms with and without a Lennard-Jones well depth: the second kind -- two thirds of the
+//               atoms of water -- runs an inner loop without the LJ arithmetic). Whenever a ring holds 32 entries the
+//               warp runs the straight-line inner loop over them: lane (i, part) takes entries part, part+4, ...
+//               (one LDS.128 wavefront per 4 j atoms), everything after the distance test is predicated, not
+//               branched. Forces and dE/dq are accumulated together in registers and reduced over the 4 lanes of an
+//               i atom with warp shuffles; every ordered pair is evaluated from both sides (full shell): no j-side
+//               atomics, and the FP32 summation order is fixed, so results are bitwise reproducible.
+//  erfc         erfc(x) = exp(-x^2) t P7(t), t = 1/(1 + p x) (tools/erfcx_fit.py, 5e-8 relative): one MUFU.RCP, one
+//               MUFU.EX2 (shared with the force's Gaussian term), 7 FFMA.
+//  exactness    the in-cutoff predicate of a pair whose FP32 r2 falls within 1e-5 of rc2 is re-evaluated in FP64 on the
+//               original coordinates with the reference's operation order, so the neighbour set is bit-exact.
+//  exclusions   the excluded-pair kernel (flux.cu), which runs first, leaves the largest r2 of any excluded pair in a
+//               device scalar; only pairs at or below that separation (bonded neighbours; also the self pair at
+//               r2 = 0) take the rare branch that probes the per-atom exclusion CSR.
 //
-// FP32 pair arithmetic for forces and dE/dq (erfcf/expf), int64 fixed-point accumulation. Pair ENERGIES
-// are evaluated in FP64: in-cutoff i<j pairs are ballot-compacted into a per-warp queue and evaluated 32
-// at a time, because E_direct cancels against E_self + E_excl to a small fraction of its size.
+// FP32 pair arithmetic for forces and dE/dq, int64 fixed-point accumulation. Pair ENERGIES are evaluated in FP64:
+// in-cutoff i<j pairs are ballot-compacted into a per-warp queue and evaluated 32 at a time, because E_direct cancels
+// against E_self + E_excl to a small fraction of its size.
 #include "cfx_internal.cuh"
 
 #include <algorithm>
 #include <cstdlib>
 #include <cmath>
+#include <type_traits>
 
 namespace cfx {
 
@@ -111,26 +121,31 @@ __global__ void __launch_bounds__(256) cellFillKernel(int N, const int* __restri
     sortedUser[slot] = i;
 }
 
-// One thread per slot of the (arbitrarily ordered) cell fill: the atom's final slot is the start of
-// its cell plus its rank among the cell's atoms by user index, so the sorted order -- and with it every
-// FP32 accumulation order downstream -- is deterministic. Writes all sorted arrays in one pass.
+// One thread per slot of the (arbitrarily ordered) cell fill: the atom's final slot is the start of its cell plus its
+// rank among the cell's atoms by (z inside the cell, user index), so the sorted order -- and with it every FP32
+// accumulation order downstream -- is deterministic, and a column of cells is one z-ordered run. Writes both sorted
+// records in one pass: sortedLocal = (x, y, z inside the cell, q), sortedMeta = (sigma/2, 2 sqrt(eps), user index,
+// packed cell coordinates).
 __global__ void __launch_bounds__(256) cellRankGatherKernel(int N, int ncy, int ncz, const int* __restrict__ filledUser,
         const int* __restrict__ cellOfAtom, const int* __restrict__ cellStart, const float4* __restrict__ userLocal,
-        const float2* __restrict__ lj, int* __restrict__ sortedUser, float4* __restrict__ sortedLocal,
-        int* __restrict__ sortedCell, float2* __restrict__ sortedLJ) {
+        const float2* __restrict__ lj, float4* __restrict__ sortedLocal, float4* __restrict__ sortedMeta) {
     const int s = blockIdx.x*blockDim.x + threadIdx.x;
     if (s >= N) return;
     const int u = filledUser[s];
     const int cell = cellOfAtom[u];
     const int s0 = cellStart[cell], s1 = cellStart[cell+1];
+    const float4 mine = userLocal[u];
     int rank = 0;
-    for (int t = s0; t < s1; t++) rank += (filledUser[t] < u) ? 1 : 0;
+    for (int t = s0; t < s1; t++) {
+        const int v = filledUser[t];
+        const float zv = userLocal[v].z;
+        rank += (zv < mine.z || (zv == mine.z && v < u)) ? 1 : 0;
+    }
     const int dst = s0 + rank;
     const int cz = cell % ncz, cy = (cell/ncz) % ncy, cx = cell/(ncz*ncy);
-    sortedUser[dst] = u;
-    sortedLocal[dst] = userLocal[u];
-    sortedCell[dst] = cx | (cy << CELL_BITS) | (cz << (2*CELL_BITS));
-    sortedLJ[dst] = lj[u];
+    const float2 l = lj[u];
+    sortedLocal[dst] = mine;
+    sortedMeta[dst] = make_float4(l.x, l.y, __int_as_float(u), __int_as_float(cx | (cy << CELL_BITS) | (cz << (2*CELL_BITS))));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -139,22 +154,33 @@ __global__ void __launch_bounds__(256) cellRankGatherKernel(int N, int ncy, int 
 #define P_WARPS 4
 #define P_ITILE 8
 #define P_JTILE 32
-#define P_JCAP 64
+#ifndef P_FAST_MINBLOCKS
+#define P_FAST_MINBLOCKS 5     // resident CTAs per SM the fast kernel is compiled for (register cap 96)
+#endif
+#define R_COMPS 7
+#ifndef P_UNROLL
+#define P_UNROLL 1        // the packed loop already carries two independent pairs per iteration
+#endif
+constexpr int kPairUnroll = P_UNROLL;
+#define P_JCAP 64            // ring capacity: < 32 waiting entries + one 32-candidate chunk
 
 struct PairParams {
     int N, Npad, numGroups, groupLo, groupHi;
-    int jSplits;                 // the (x,y) columns of an i-tile's stencil are dealt over gridDim.y CTAs (small shards)
+    int jSplits;                 // the (x,y) columns of an i-cluster's stencil are dealt over jSplits work items (small shards)
+    int onlyMinImage;            // generic kernel launched after the fast one: only the clusters the fast one skipped
     int ncx, ncy, ncz;
-    float csx, csy, csz;
+    float csx, csy, csz, invCsz;
     float Lx, Ly, Lz, invLx, invLy, invLz;
     double dLx, dLy, dLz, rc2d;
-    float rc2, alpha, band;
-    const float4* sortedLocal; const int* sortedCell; const float2* sortedLJ; const int* sortedUser;
+    float rc2, alpha, alpha2, band;
+    const float4* sortedLocal; const float4* sortedMeta;
     const int* cellStart;
     const int* exclPtr; const int* exclCols;
+    const unsigned int* exclMaxR2Bits;       // float bits of the largest r2 over the excluded pairs (exclusionKernel)
     const double* pos; const double* q; const double2* ljd; double alphaD, dInvLx, dInvLy, dInvLz;
     long long* forceFixed; long long* dedqFixed; long long* energyFixed;
     unsigned long long* counters; int2* pairBuffer; unsigned long long pairCapacity;
+    unsigned int* workCounter;               // dynamic work distribution: next (cluster, column share) item
 };
 
 __device__ __forceinline__ int wrapNearest(int d, int nc) {
@@ -164,25 +190,14 @@ __device__ __forceinline__ int wrapNearest(int d, int nc) {
     return d;
 }
 
-// erfc(x), x >= 0, relative error ~1.2e-7 (Chebyshev fit in t = 1/(1 + x/2), Numerical Recipes erfcc):
-// one MUFU.RCP, nine FFMA and one MUFU.EX2 instead of the ~40-instruction erfcf().
-__device__ __forceinline__ float erfcFast(float x, float x2) {
-    const float t = __fdividef(1.f, fmaf(0.5f, x, 1.f));
-    float p = fmaf(t, 0.17087277f, -0.82215223f);
-    p = fmaf(t, p, 1.48851587f);
-    p = fmaf(t, p, -1.13520398f);
-    p = fmaf(t, p, 0.27886807f);
-    p = fmaf(t, p, -0.18628806f);
-    p = fmaf(t, p, 0.09678418f);
-    p = fmaf(t, p, 0.37409196f);
-    p = fmaf(t, p, 1.00002368f);
-    p = fmaf(t, p, -1.26551223f);
-    return t*__expf(p - x2);
-}
+// approximate special functions without the denormal fix-ups nvcc wraps around rsqrtf/__expf (inputs here are normal)
+__device__ __forceinline__ float rsqrtFtz(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcpFtz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float ex2Ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 // exact FP64 predicate with the reference's operation order (J - I with I the lower user index;
 // z, y, x floor-based wrap; left-to-right sum of squares; no FMA contraction)
-__device__ __noinline__ bool exactInCutoff(const double* __restrict__ pos, int ua, int ub, double Lx, double Ly, double Lz, double rc2) {
+__device__ __forceinline__ bool exactInCutoff(const double* __restrict__ pos, int ua, int ub, double Lx, double Ly, double Lz, double rc2) {
     const int I = min(ua, ub), J = max(ua, ub);
     double dx = __dsub_rn(pos[3*(size_t) J], pos[3*(size_t) I]);
     double dy = __dsub_rn(pos[3*(size_t) J + 1], pos[3*(size_t) I + 1]);
@@ -194,260 +209,392 @@ __device__ __noinline__ bool exactInCutoff(const double* __restrict__ pos, int u
     return r2 <= rc2;
 }
 
-__device__ __forceinline__ int modPos(int v, int n) { v %= n; return v < 0 ? v + n : v; }
+// rare path: is (ui, uj) the self pair or an excluded pair? (symmetric, sorted per-atom CSR)
+__device__ __forceinline__ bool selfOrExcluded(const int* __restrict__ exclPtr, const int* __restrict__ exclCols, int ui, int uj) {
+    if (ui == uj) return true;
+    for (int e = exclPtr[ui], e1 = exclPtr[ui + 1]; e < e1; e++)
+        if (exclCols[e] == uj) return true;
+    return false;
+}
 
+// The two rare cases of the inner loop in one out-of-line call: a pair whose FP32 r2 lies within the band around rc2
+// (decided in FP64 with the reference's operation order), and a pair at bonded-neighbour separation (self / excluded?).
+__device__ __noinline__ int rareInCutoff(const PairParams* p, int ui, int uj, float r2, float r2close) {
+    bool in = r2 <= p->rc2;
+    if (fabsf(r2 - p->rc2) < p->band) in = exactInCutoff(p->pos, ui, uj, p->dLx, p->dLy, p->dLz, p->rc2d);
+    if (in && r2 <= r2close) in = !selfOrExcluded(p->exclPtr, p->exclCols, ui, uj);
+    return in ? 1 : 0;
+}
+
+__device__ __forceinline__ float2 pk(float a) { return make_float2(a, a); }     // scalar broadcast operand of a packed instruction
+__device__ __forceinline__ int modPos(int v, int n) { v %= n; return v < 0 ? v + n : v; }
+// v in (-n, 2n): the fast kernel's cell grids have at least 7 cells per axis and stencils of at most n cells
+__device__ __forceinline__ int wrapOnce(int v, int n) { return v < 0 ? v + n : (v >= n ? v - n : v); }
+
+// FAST: the cell grid has >= 7 cells per axis; clusters whose stencil would wrap onto itself (min-image needed) are
+//       left to the generic instantiation, so no min-image code and no integer divisions are compiled in.
 // EMODE: 0 = no pair energy, 1 = FP32 pair terms (the partial energy the reference returns when
 // includeEnergy is false is discarded by OpenMM; it is still produced, at FP32 accuracy), 2 = FP64 terms.
-template <bool FORCES, int EMODE, bool EMIT>
-__global__ void __launch_bounds__(P_WARPS*32) pairKernel(PairParams p) {
-    __shared__ float4 sPos[P_WARPS][P_JCAP];
-    __shared__ float2 sLJ[P_WARPS][P_JCAP];
-    __shared__ int sUser[P_WARPS][P_JCAP];
-    __shared__ int2 sEq[P_WARPS][P_JCAP];          // queue of in-cutoff (ui<uj) pairs awaiting the FP64 energy
+template <bool FAST, bool FORCES, int EMODE, bool EMIT>
+__global__ void __launch_bounds__(P_WARPS*32, FAST ? P_FAST_MINBLOCKS : 4) pairKernel(const __grid_constant__ PairParams p) {
+    // rings of staged j atoms, [0: without LJ well depth, 1: with][warp][slot], one array per component so that a lane
+    // fetches the same component of two consecutive entries with one LDS.64 -- the operand layout of the packed
+    // (two pairs per instruction) FP32 arithmetic of the inner loop
+    // components: 0-2 xyz in the cluster frame, 3 charge, 4 user index (rare paths, pair emission, energy queue),
+    // 5-6 sigma/2 and 2 sqrt(eps) (LJ ring only); one block per warp so that every access is base + constant offset
+    __shared__ __align__(16) float sRing[P_WARPS][2][R_COMPS][P_JCAP];
+    __shared__ int2 sEq[EMODE == 2 ? P_WARPS : 1][P_JCAP];   // queue of in-cutoff (ui<uj) pairs awaiting the FP64 energy
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = p.groupLo + blockIdx.x*P_WARPS + warp;
-    if (g >= p.groupHi) return;                      // whole warp exits; only __syncwarp below
-    float4* tPos = sPos[warp]; float2* tLJ = sLJ[warp]; int* tUser = sUser[warp]; int2* eq = sEq[warp];
-
-    const int i0 = g*P_ITILE;
-    const int ni = min(P_ITILE, p.N - i0);
     const int ii = lane >> 2, part = lane & 3;
-    const bool validI = ii < ni;
-    const int iIdx = i0 + (validI ? ii : 0);
-    const int c0 = p.sortedCell[i0];
-    const int c0x = c0 & CELL_MASK, c0y = (c0 >> CELL_BITS) & CELL_MASK, c0z = c0 >> (2*CELL_BITS);
+    const unsigned int lt = (1u << lane) - 1u;
+    int2* eq = sEq[EMODE == 2 ? warp : 0];
+    const float alpha = p.alpha, alpha2 = p.alpha2, band = p.band;
+    const float rcut2 = p.rc2*1.0001f;
+    const float4 farAway = make_float4(1e4f, 1e4f, 1e4f, 0.f);
+    const unsigned int totalItems = (unsigned int) (p.groupHi - p.groupLo)*(unsigned int) p.jSplits;
+    if (!FAST && p.onlyMinImage && p.counters[7] == 0ull) return;     // the fast kernel skipped nothing
 
-    // my i atom, expressed in the frame of cell c0
-    const float4 li = p.sortedLocal[iIdx];
-    const int ci = p.sortedCell[iIdx];
-    const int ox = wrapNearest((ci & CELL_MASK) - c0x, p.ncx);
-    const int oy = wrapNearest(((ci >> CELL_BITS) & CELL_MASK) - c0y, p.ncy);
-    const int oz = wrapNearest((ci >> (2*CELL_BITS)) - c0z, p.ncz);
-    const float pix = li.x + ox*p.csx, piy = li.y + oy*p.csy, piz = li.z + oz*p.csz;
-    const float2 lji = p.sortedLJ[iIdx];
-    const int ui = p.sortedUser[iIdx];
-    const float keqi = (float) CFX_ONE_4PI_EPS0*li.w;
-    const int exBeg = p.exclPtr[ui], exEnd = p.exclPtr[ui+1];
-    int exLo = 0x7fffffff, exHi = -1;
-    if (exEnd > exBeg) { exLo = p.exclCols[exBeg]; exHi = p.exclCols[exEnd-1]; }    // CSR columns are sorted
+    // persistent warps: work items (i-cluster, share of its stencil columns) are handed out by an atomic counter, so the
+    // GPU stays full whatever the item count (no partial last wave)
+    for (;;) {
+        unsigned int item = 0;
+        if (lane == 0) item = atomicAdd(p.workCounter, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= totalItems) break;
+        const int g = p.groupLo + (int) (item/(unsigned int) p.jSplits);
+        const int share = (int) (item % (unsigned int) p.jSplits);
 
-    // bounding box of the i-tile and its cell-offset range (warp reductions)
-    float bminx = pix, bminy = piy, bminz = piz, bmaxx = pix, bmaxy = piy, bmaxz = piz;
-    int ominx = ox, ominy = oy, ominz = oz, omaxx = ox, omaxy = oy, omaxz = oz;
-    #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        bminx = fminf(bminx, __shfl_xor_sync(0xffffffffu, bminx, o)); bmaxx = fmaxf(bmaxx, __shfl_xor_sync(0xffffffffu, bmaxx, o));
-        bminy = fminf(bminy, __shfl_xor_sync(0xffffffffu, bminy, o)); bmaxy = fmaxf(bmaxy, __shfl_xor_sync(0xffffffffu, bmaxy, o));
-        bminz = fminf(bminz, __shfl_xor_sync(0xffffffffu, bminz, o)); bmaxz = fmaxf(bmaxz, __shfl_xor_sync(0xffffffffu, bmaxz, o));
-        ominx = min(ominx, __shfl_xor_sync(0xffffffffu, ominx, o)); omaxx = max(omaxx, __shfl_xor_sync(0xffffffffu, omaxx, o));
-        ominy = min(ominy, __shfl_xor_sync(0xffffffffu, ominy, o)); omaxy = max(omaxy, __shfl_xor_sync(0xffffffffu, omaxy, o));
-        ominz = min(ominz, __shfl_xor_sync(0xffffffffu, ominz, o)); omaxz = max(omaxz, __shfl_xor_sync(0xffffffffu, omaxz, o));
-    }
-    // stencil: offsets [omin-2, omax+2] per axis. If that range would wrap onto itself (tiny box, or an
-    // i-tile straddling a large empty region) it is truncated to all nc cells of the axis and the
-    // separation of every pair is min-imaged instead (warp-uniform flag).
-    const int loX = ominx - 2, nX = min(omaxx - ominx + 5, p.ncx);
-    const int loY = ominy - 2, nY = min(omaxy - ominy + 5, p.ncy);
-    const int loZ = ominz - 2, nZ = min(omaxz - ominz + 5, p.ncz);
-    const bool minImage = (omaxx - ominx + 5 > p.ncx) || (omaxy - ominy + 5 > p.ncy) || (omaxz - ominz + 5 > p.ncz);
+        const int i0 = g*P_ITILE;
+        const int ni = min(P_ITILE, p.N - i0);
+        const bool validI = ii < ni;
+        const int iIdx = i0 + (validI ? ii : 0);
+        const int c0 = __float_as_int(p.sortedMeta[i0].w);
+        const int c0x = c0 & CELL_MASK, c0y = (c0 >> CELL_BITS) & CELL_MASK, c0z = c0 >> (2*CELL_BITS);
 
-    float fx = 0.f, fy = 0.f, fz = 0.f, dq = 0.f, enf = 0.f;
-    double en = 0.0;
-    unsigned int nPairs = 0, nCand = 0;
-    int count = 0;                                   // entries waiting in the j-tile
-    int qCount = 0;                                  // entries waiting in the energy queue
+        // my i atom, expressed in the frame of cell c0
+        const float4 li = p.sortedLocal[iIdx];
+        const float4 mi = p.sortedMeta[iIdx];
+        const int ci = __float_as_int(mi.w);
+        const int ox = wrapNearest((ci & CELL_MASK) - c0x, p.ncx);
+        const int oy = wrapNearest(((ci >> CELL_BITS) & CELL_MASK) - c0y, p.ncy);
+        const int oz = wrapNearest((ci >> (2*CELL_BITS)) - c0z, p.ncz);
+        const float pix = li.x + ox*p.csx, piy = li.y + oy*p.csy, piz = li.z + oz*p.csz;
+        const float ljix = mi.x, ljiy = mi.y;
+        const int ui = __float_as_int(mi.z);
+        const float keqi = (float) CFX_ONE_4PI_EPS0*li.w;
+        // per-lane copies of the thresholds: lanes without an i atom (last cluster) never see a pair
+        const float rc2i = validI ? p.rc2 : -1.f;
+        // (floor 1e-8 nm^2: the self pair is r2 = 0 up to rounding when a small box folds the stencil onto itself)
+        const float r2close = validI ? fmaxf(__uint_as_float(*p.exclMaxR2Bits)*1.0001f, 1e-8f) : -1.f;
+        const bool anyLJi = __any_sync(0xffffffffu, validI && ljiy != 0.f);
 
-    // Pair energies are evaluated in FP64 on the original coordinates (the direct, self and exclusion
-    // sums cancel to a small fraction of their size, FP32 terms would cost ~1e-3 kJ/mol). In-cutoff
-    // pairs are compacted into a queue so that all 32 lanes do FP64 work together.
-    auto energyBatch = [&](int n) {
-        __syncwarp();
-        if (lane < n) {
-            const int a = eq[lane].x, b = eq[lane].y;
-            double dx = p.pos[3*(size_t) a] - p.pos[3*(size_t) b];
-            double dy = p.pos[3*(size_t) a + 1] - p.pos[3*(size_t) b + 1];
-            double dz = p.pos[3*(size_t) a + 2] - p.pos[3*(size_t) b + 2];
-            dx -= p.dLx*floor(dx*p.dInvLx + 0.5); dy -= p.dLy*floor(dy*p.dInvLy + 0.5); dz -= p.dLz*floor(dz*p.dInvLz + 0.5);
-            const double r2 = dx*dx + dy*dy + dz*dz;
-            const double invR = rsqrt(r2);
-            const double ar = p.alphaD*r2*invR;
-            const double2 la = p.ljd[a], lb = p.ljd[b];
-            const double sig = la.x + lb.x;
-            double s2 = sig*invR; s2 *= s2;
-            const double s6 = s2*s2*s2;
-            en += CFX_ONE_4PI_EPS0*p.q[a]*p.q[b]*invR*erfc(ar) + s6*(la.y*lb.y)*(s6 - 1.0);
+        // bounding box of the i-cluster and its cell-offset range (warp reductions)
+        float bminx = pix, bminy = piy, bminz = piz, bmaxx = pix, bmaxy = piy, bmaxz = piz;
+        int ominx = ox, ominy = oy, ominz = oz, omaxx = ox, omaxy = oy, omaxz = oz;
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            bminx = fminf(bminx, __shfl_xor_sync(0xffffffffu, bminx, o)); bmaxx = fmaxf(bmaxx, __shfl_xor_sync(0xffffffffu, bmaxx, o));
+            bminy = fminf(bminy, __shfl_xor_sync(0xffffffffu, bminy, o)); bmaxy = fmaxf(bmaxy, __shfl_xor_sync(0xffffffffu, bmaxy, o));
+            bminz = fminf(bminz, __shfl_xor_sync(0xffffffffu, bminz, o)); bmaxz = fmaxf(bmaxz, __shfl_xor_sync(0xffffffffu, bmaxz, o));
+            ominx = min(ominx, __shfl_xor_sync(0xffffffffu, ominx, o)); omaxx = max(omaxx, __shfl_xor_sync(0xffffffffu, omaxx, o));
+            ominy = min(ominy, __shfl_xor_sync(0xffffffffu, ominy, o)); omaxy = max(omaxy, __shfl_xor_sync(0xffffffffu, omaxy, o));
+            ominz = min(ominz, __shfl_xor_sync(0xffffffffu, ominz, o)); omaxz = max(omaxz, __shfl_xor_sync(0xffffffffu, omaxz, o));
         }
-        __syncwarp();
-    };
+        // stencil: offsets [omin-2, omax+2] per axis. If that range would wrap onto itself (tiny box, or an
+        // i-cluster straddling a large empty region) it is truncated to all nc cells of the axis and the
+        // separation of every pair is min-imaged instead (warp-uniform flag; generic instantiation only).
+        const int loX = ominx - 2, nX = min(omaxx - ominx + 5, p.ncx);
+        const int loY = ominy - 2, nY = min(omaxy - ominy + 5, p.ncy);
+        const int loZ = ominz - 2, nZ = min(omaxz - ominz + 5, p.ncz);
+        const bool wraps = (omaxx - ominx + 5 > p.ncx) || (omaxy - ominy + 5 > p.ncy) || (omaxz - ominz + 5 > p.ncz);
+        if (FAST && wraps) {                            // left to the generic kernel launched behind this one
+            if (lane == 0 && share == 0) atomicAdd(p.counters + 7, 1ull);
+            continue;
+        }
+        if (!FAST && p.onlyMinImage && !wraps) continue;
+        const bool minImage = FAST ? false : wraps;
 
-    auto processTile = [&](int n) {
-        __syncwarp();
-        #pragma unroll 2
-        for (int k = part; k < P_JTILE; k += 4) {
-            const float4 pj = tPos[k];
-            const int uj = tUser[k];
-            float dx = pix - pj.x, dy = piy - pj.y, dz = piz - pj.z;      // pos[i] - pos[j]
-            if (minImage) {
-                dx -= p.Lx*rintf(dx*p.invLx); dy -= p.Ly*rintf(dy*p.invLy); dz -= p.Lz*rintf(dz*p.invLz);
+        float2 fx2 = pk(0.f), fy2 = pk(0.f), fz2 = pk(0.f), dq2 = pk(0.f), enf2 = pk(0.f);     // two partial sums each
+        double en = 0.0;
+        unsigned int nIn = 0, nCand = 0;                 // in-cutoff ordered pairs seen by this lane; candidates staged by the warp
+        int qCount = 0;                                  // entries waiting in the energy queue
+
+        // Pair energies are evaluated in FP64 on the original coordinates (the direct, self and exclusion
+        // sums cancel to a small fraction of their size, FP32 terms would cost ~1e-3 kJ/mol). In-cutoff
+        // pairs are compacted into a queue so that all 32 lanes do FP64 work together.
+        auto energyBatch = [&](int n) {
+            __syncwarp();
+            if (lane < n) {
+                const int a = eq[lane].x, b = eq[lane].y;
+                double dx = p.pos[3*(size_t) a] - p.pos[3*(size_t) b];
+                double dy = p.pos[3*(size_t) a + 1] - p.pos[3*(size_t) b + 1];
+                double dz = p.pos[3*(size_t) a + 2] - p.pos[3*(size_t) b + 2];
+                dx -= p.dLx*floor(dx*p.dInvLx + 0.5); dy -= p.dLy*floor(dy*p.dInvLy + 0.5); dz -= p.dLz*floor(dz*p.dInvLz + 0.5);
+                const double r2 = dx*dx + dy*dy + dz*dz;
+                const double invR = rsqrt(r2);
+                const double ar = p.alphaD*r2*invR;
+                const double2 la = p.ljd[a], lb = p.ljd[b];
+                const double sig = la.x + lb.x;
+                double s2 = sig*invR; s2 *= s2;
+                const double s6 = s2*s2*s2;
+                en += CFX_ONE_4PI_EPS0*p.q[a]*p.q[b]*invR*erfc(ar) + s6*(la.y*lb.y)*(s6 - 1.0);
             }
-            const float r2 = dx*dx + dy*dy + dz*dz;
-            bool in = validI && (k < n) && (uj != ui) && (r2 <= p.rc2);
-            if (validI && (k < n) && (uj != ui) && fabsf(r2 - p.rc2) < p.band)
-                in = exactInCutoff(p.pos, ui, uj, p.dLx, p.dLy, p.dLz, p.rc2d);
-            if (in && uj >= exLo && uj <= exHi)
-                for (int e = exBeg; e < exEnd; e++)
-                    if (p.exclCols[e] == uj) { in = false; break; }
-            if (in) {
+            __syncwarp();
+        };
+
+        // One tile = the 32 ring entries from `base` (0 or 32) of ring `LJ`; entries past the end n of a last, partial
+        // tile hold far-away positions with zero charge and well depth (min-image tiles, which would fold them back
+        // into the box, test the entry index against n as well). Each lane takes two consecutive entries per iteration
+        // and evaluates them with packed FP32 instructions (FFMA2 / FMUL2 / FADD2 of sm_100: one issue slot for two
+        // pairs; the kernel is issue-bound, not FMA-pipe-bound). Straight-line code: out-of-cutoff pairs are masked,
+        // not branched.
+        auto processTile = [&](auto ljTag, auto imgTag, int base, int n) {
+            constexpr bool LJ = decltype(ljTag)::value, IMG = decltype(imgTag)::value;
+            const float* ring = &sRing[warp][LJ][0][0] + base;
+            const float2* tX = reinterpret_cast<const float2*>(ring);
+            const float2* tY = reinterpret_cast<const float2*>(ring + P_JCAP);
+            const float2* tZ = reinterpret_cast<const float2*>(ring + 2*P_JCAP);
+            const float2* tQ = reinterpret_cast<const float2*>(ring + 3*P_JCAP);
+            const int* tUser = reinterpret_cast<const int*>(ring + 4*P_JCAP);
+            const float2* tSig = reinterpret_cast<const float2*>(ring + 5*P_JCAP);
+            const float2* tEps = reinterpret_cast<const float2*>(ring + 6*P_JCAP);
+            __syncwarp();
+            #pragma unroll (kPairUnroll)
+            for (int c = part; c < P_JTILE/2; c += 4) {
+                const float2 xj = tX[c], yj = tY[c], zj = tZ[c], qj = tQ[c];
+                float2 dx = __ffma2_rn(xj, pk(-1.f), pk(pix));                 // pos[i] - pos[j], two j atoms
+                float2 dy = __ffma2_rn(yj, pk(-1.f), pk(piy));
+                float2 dz = __ffma2_rn(zj, pk(-1.f), pk(piz));
+                if (IMG) {
+                    dx.x -= p.Lx*rintf(dx.x*p.invLx); dy.x -= p.Ly*rintf(dy.x*p.invLy); dz.x -= p.Lz*rintf(dz.x*p.invLz);
+                    dx.y -= p.Lx*rintf(dx.y*p.invLx); dy.y -= p.Ly*rintf(dy.y*p.invLy); dz.y -= p.Lz*rintf(dz.y*p.invLz);
+                }
+                const float2 r2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
+                bool in0 = r2.x <= rc2i, in1 = r2.y <= rc2i;
+                if (IMG) { in0 = in0 && 2*c < n; in1 = in1 && 2*c + 1 < n; }
+                // rare: within the band around rc2 (FP64 re-test, bit-exact neighbour set), or at bonded-neighbour
+                // separation (excluded pair? self pair?). Lanes without an i atom have negative thresholds.
+                const float2 off = __fadd2_rn(r2, pk(-rc2i));
+                const bool rare0 = ((r2.x <= r2close) | (fabsf(off.x) < band)) & (!IMG || 2*c < n);
+                const bool rare1 = ((r2.y <= r2close) | (fabsf(off.y) < band)) & (!IMG || 2*c + 1 < n);
+                if (rare0 | rare1) {
+                    if (rare0) in0 = rareInCutoff(&p, ui, tUser[2*c], r2.x, r2close) != 0;
+                    if (rare1) in1 = rareInCutoff(&p, ui, tUser[2*c + 1], r2.y, r2close) != 0;
+                }
                 if (FORCES || EMODE == 1) {
-                    const float2 ljj = tLJ[k];
-                    const float invR = rsqrtf(r2);
-                    const float r = r2*invR;
-                    const float ar = p.alpha*r;
-                    const float ar2 = ar*ar;
-                    const float erfcv = erfcFast(ar, ar2);
-                    const float coul = keqi*pj.w*invR;
-                    const float sig = lji.x + ljj.x;
-                    float s2 = sig*invR; s2 *= s2;
-                    const float s6 = s2*s2*s2;
-                    const float es6 = s6*(lji.y*ljj.y);
+                    const float2 invR = make_float2(rsqrtFtz(r2.x), rsqrtFtz(r2.y));
+                    const float2 invR2 = __fmul2_rn(invR, invR);
+                    const float2 ar = __fmul2_rn(__fmul2_rn(r2, pk(alpha)), invR);
+                    const float2 ge = __fmul2_rn(r2, pk(alpha2*-1.4426950408889634f));
+                    const float2 gauss = make_float2(ex2Ftz(ge.x), ex2Ftz(ge.y));      // exp(-(alpha r)^2)
+                    const float2 td = __ffma2_rn(ar, pk(0.3275911f), pk(1.f));
+                    const float2 t = make_float2(rcpFtz(td.x), rcpFtz(td.y));
+                    float2 pl = __ffma2_rn(t, pk(-1.438181028e-01f), pk(5.078454972e-01f));
+                    pl = __ffma2_rn(t, pl, pk(-4.250064424e-01f));
+                    pl = __ffma2_rn(t, pl, pk(4.706512873e-01f));
+                    pl = __ffma2_rn(t, pl, pk(1.636827149e-02f));
+                    pl = __ffma2_rn(t, pl, pk(2.085574698e-01f));
+                    pl = __ffma2_rn(t, pl, pk(1.803253944e-01f));
+                    pl = __ffma2_rn(t, pl, pk(1.850765712e-01f));
+                    const float2 erfcv = __fmul2_rn(__fmul2_rn(t, pl), gauss);
+                    const float2 coul = __fmul2_rn(__fmul2_rn(qj, pk(keqi)), invR);
+                    float2 es6 = pk(0.f), s6 = pk(0.f);
+                    if (LJ) {
+                        const float2 sig = __fadd2_rn(tSig[c], pk(ljix));
+                        float2 s2 = __fmul2_rn(sig, invR);
+                        s2 = __fmul2_rn(s2, s2);
+                        s6 = __fmul2_rn(__fmul2_rn(s2, s2), s2);
+                        es6 = __fmul2_rn(s6, __fmul2_rn(tEps[c], pk(ljiy)));
+                    }
                     if (FORCES) {
-                        const float ex = __expf(-ar2);
-                        const float invR2 = invR*invR;
-                        const float dEdR = (coul*(erfcv + ar*ex*1.1283791671f) + es6*(12.f*s6 - 6.f))*invR2;
-                        fx = fmaf(dEdR, dx, fx); fy = fmaf(dEdR, dy, fy); fz = fmaf(dEdR, dz, fz);
-                        dq = fmaf((float) CFX_ONE_4PI_EPS0*pj.w*invR, erfcv, dq);
+                        const float2 gterm = __ffma2_rn(__fmul2_rn(ar, gauss), pk(1.1283791671f), erfcv);
+                        float2 dEdR = __fmul2_rn(coul, gterm);
+                        if (LJ) dEdR = __ffma2_rn(es6, __ffma2_rn(s6, pk(12.f), pk(-6.f)), dEdR);
+                        dEdR = __fmul2_rn(dEdR, invR2);
+                        float2 v = __fmul2_rn(invR, erfcv);
+                        dEdR.x = in0 ? dEdR.x : 0.f; dEdR.y = in1 ? dEdR.y : 0.f;
+                        v.x = in0 ? v.x : 0.f; v.y = in1 ? v.y : 0.f;
+                        fx2 = __ffma2_rn(dEdR, dx, fx2); fy2 = __ffma2_rn(dEdR, dy, fy2); fz2 = __ffma2_rn(dEdR, dz, fz2);
+                        dq2 = __ffma2_rn(qj, v, dq2);
                     }
-                    if (EMODE == 1) enf += coul*erfcv + es6*(s6 - 1.f);      // discarded partial energy: FP32 per lane
-                }
-                if (ui < uj) {
-                    nPairs++;
-                    if (EMIT) {
-                        const unsigned long long slot = atomicAdd(p.counters + 2, 1ull);
-                        if (slot < p.pairCapacity) p.pairBuffer[slot] = make_int2(ui, uj);
+                    if (EMODE == 1) {                                         // discarded partial energy: FP32 per lane
+                        float2 e = __fmul2_rn(coul, erfcv);
+                        if (LJ) e = __ffma2_rn(es6, __fadd2_rn(s6, pk(-1.f)), e);
+                        e.x = in0 ? e.x : 0.f; e.y = in1 ? e.y : 0.f;
+                        enf2 = __fadd2_rn(enf2, e);
                     }
                 }
-            }
-            if (EMODE == 2) {
-                const bool want = in && ui < uj;
-                const unsigned int m = __ballot_sync(0xffffffffu, want);
-                if (want) eq[qCount + __popc(m & ((1u << lane) - 1u))] = make_int2(ui, uj);
-                qCount += __popc(m);
-                if (qCount >= 32) {
-                    energyBatch(32);
-                    const int rest = qCount - 32;
-                    int2 mv = make_int2(0, 0);
-                    if (lane < rest) mv = eq[32 + lane];
-                    __syncwarp();
-                    if (lane < rest) eq[lane] = mv;
-                    qCount = rest;
-                }
-            }
-        }
-        nCand += (unsigned int) min(n, P_JTILE);
-        __syncwarp();
-    };
-
-    // z run in unwrapped cell units [zlo, zlo+nZ-1] -> at most two contiguous wrapped segments
-    const int zlo = c0z + loZ;
-    const int zloW = modPos(zlo, p.ncz);
-    int segLo[2], segHi[2], segShift[2], nSeg = 1;
-    segLo[0] = zloW; segShift[0] = zlo - zloW;
-    if (zloW + nZ - 1 < p.ncz) segHi[0] = zloW + nZ - 1;
-    else { segHi[0] = p.ncz - 1; segLo[1] = 0; segHi[1] = zloW + nZ - 1 - p.ncz; segShift[1] = zlo - zloW + p.ncz; nSeg = 2; }
-
-    for (int ax = 0; ax < nX; ax++) {
-        const int offx = loX + ax;
-        const int cx = modPos(c0x + offx, p.ncx);
-        for (int ay = 0; ay < nY; ay++) {
-            if (p.jSplits > 1 && (ax*nY + ay) % p.jSplits != (int) blockIdx.y) continue;
-            const int offy = loY + ay;
-            const int cy = modPos(c0y + offy, p.ncy);
-            const int rowCell = (cx*p.ncy + cy)*p.ncz;
-            const float shx = offx*p.csx, shy = offy*p.csy;
-            for (int sg = 0; sg < nSeg; sg++) {
-                const int s0 = p.cellStart[rowCell + segLo[sg]], s1 = p.cellStart[rowCell + segHi[sg] + 1];
-                const int zShift = segShift[sg] - c0z;
-                for (int base = s0; base < s1; base += 32) {
-                    const int s = base + lane;
-                    bool pass = false;
-                    float4 pj = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (s < s1) {
-                        const float4 l4 = p.sortedLocal[s];
-                        const int cz = p.sortedCell[s] >> (2*CELL_BITS);
-                        pj = make_float4(l4.x + shx, l4.y + shy, l4.z + (cz + zShift)*p.csz, l4.w);
-                        if (minImage) pass = true;
-                        else {
-                            const float ex = fmaxf(0.f, fmaxf(bminx - pj.x, pj.x - bmaxx));
-                            const float ey = fmaxf(0.f, fmaxf(bminy - pj.y, pj.y - bmaxy));
-                            const float ez = fmaxf(0.f, fmaxf(bminz - pj.z, pj.z - bmaxz));
-                            pass = ex*ex + ey*ey + ez*ez <= p.rc2*1.0001f;
+                nIn += (in0 ? 1u : 0u) + (in1 ? 1u : 0u);
+                if (EMIT || EMODE == 2) {
+                    #pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const int uj = tUser[2*c + h];
+                        const bool want = (h ? in1 : in0) && ui < uj;
+                        if (EMIT && want) {
+                            const unsigned long long slot = atomicAdd(p.counters + 2, 1ull);
+                            if (slot < p.pairCapacity) p.pairBuffer[slot] = make_int2(ui, uj);
+                        }
+                        if (EMODE == 2) {
+                            const unsigned int m = __ballot_sync(0xffffffffu, want);
+                            if (want) eq[qCount + __popc(m & lt)] = make_int2(ui, uj);
+                            qCount += __popc(m);
+                            if (qCount >= 32) {
+                                energyBatch(32);
+                                const int rest = qCount - 32;
+                                int2 mv = make_int2(0, 0);
+                                if (lane < rest) mv = eq[32 + lane];
+                                __syncwarp();
+                                if (lane < rest) eq[lane] = mv;
+                                qCount = rest;
+                            }
                         }
                     }
-                    const unsigned int m = __ballot_sync(0xffffffffu, pass);
-                    if (pass) {
-                        const int slot = count + __popc(m & ((1u << lane) - 1u));
-                        tPos[slot] = pj;
-                        tLJ[slot] = p.sortedLJ[s];
-                        tUser[slot] = p.sortedUser[s];
-                    }
-                    count += __popc(m);
-                    if (count >= P_JTILE) {
-                        processTile(P_JTILE);
-                        // move the overflow (< 32 entries) to the front
-                        const int rest = count - P_JTILE;
-                        float4 a; float2 b; int c;
-                        if (lane < rest) { a = tPos[P_JTILE + lane]; b = tLJ[P_JTILE + lane]; c = tUser[P_JTILE + lane]; }
-                        __syncwarp();
-                        if (lane < rest) { tPos[lane] = a; tLJ[lane] = b; tUser[lane] = c; }
-                        count = rest;
+                }
+            }
+            __syncwarp();
+        };
+
+        // ring state per class: entries [base, base + count) mod 64 are waiting; base is 0 or 32
+        int base0 = 0, count0 = 0, base1 = 0, count1 = 0;
+        // a full tile, or (last == true, after the last chunk) the partial one, padded
+        auto flush = [&](bool last) {
+            if (count0 >= P_JTILE || (last && count0 > 0)) {
+                const int n = min(count0, P_JTILE);
+                if (lane >= n) {
+                    float* e = &sRing[warp][0][0][(base0 + lane) & (P_JCAP - 1)];
+                    e[0] = 1e4f; e[P_JCAP] = 1e4f; e[2*P_JCAP] = 1e4f; e[3*P_JCAP] = 0.f;
+                }
+                if (minImage) processTile(std::false_type{}, std::true_type{}, base0, n); else processTile(std::false_type{}, std::false_type{}, base0, n);
+                base0 ^= P_JTILE; count0 -= P_JTILE;
+            }
+            if (count1 >= P_JTILE || (last && count1 > 0)) {
+                const int n = min(count1, P_JTILE);
+                if (lane >= n) {
+                    float* e = &sRing[warp][1][0][(base1 + lane) & (P_JCAP - 1)];
+                    e[0] = 1e4f; e[P_JCAP] = 1e4f; e[2*P_JCAP] = 1e4f; e[3*P_JCAP] = 0.f; e[5*P_JCAP] = 0.f; e[6*P_JCAP] = 0.f;
+                }
+                if (minImage) processTile(std::true_type{}, std::true_type{}, base1, n); else processTile(std::true_type{}, std::false_type{}, base1, n);
+                base1 ^= P_JTILE; count1 -= P_JTILE;
+            }
+        };
+
+        // walk the stencil columns (x outer, y inner); column `col` belongs to share col % jSplits
+        int cxw = FAST ? wrapOnce(c0x + loX, p.ncx) : modPos(c0x + loX, p.ncx);
+        const int cyw0 = FAST ? wrapOnce(c0y + loY, p.ncy) : modPos(c0y + loY, p.ncy);
+        int shareCtr = 0;
+        for (int ax = 0; ax < nX; ax++) {
+            const float shx = (loX + ax)*p.csx;
+            const float ex0 = fmaxf(0.f, fmaxf(shx - bmaxx, bminx - (shx + p.csx)));
+            int cyw = cyw0;
+            for (int ay = 0; ay < nY; ay++) {
+                const int cyCur = cyw;
+                const bool mine = shareCtr == share;
+                if (++cyw == p.ncy) cyw = 0;
+                if (++shareCtr == p.jSplits) shareCtr = 0;
+                if (!mine) continue;
+                const float shy = (loY + ay)*p.csy;
+                // z range of this column: the cells cut by the sphere of radius rc around the bounding box
+                int zRel0 = loZ, zCount = nZ;
+                if (!minImage) {
+                    const float ey0 = fmaxf(0.f, fmaxf(shy - bmaxy, bminy - (shy + p.csy)));
+                    const float d2 = fmaf(ey0, ey0, ex0*ex0);
+                    if (d2 > rcut2) continue;
+                    const float dzMax = sqrtf(rcut2 - d2) + 1e-4f;
+                    const int za = max(loZ, (int) floorf((bminz - dzMax)*p.invCsz));
+                    const int zb = min(loZ + nZ - 1, (int) floorf((bmaxz + dzMax)*p.invCsz));
+                    zRel0 = za; zCount = zb - za + 1;
+                    if (zCount <= 0) continue;
+                }
+                const int rowCell = (cxw*p.ncy + cyCur)*p.ncz;
+                // unwrapped cell units [zlo, zlo + zCount - 1] -> at most two contiguous wrapped segments
+                const int zlo = c0z + zRel0;
+                const int zloW = FAST ? wrapOnce(zlo, p.ncz) : modPos(zlo, p.ncz);
+                const int nSeg = (zloW + zCount - 1 < p.ncz) ? 1 : 2;
+                for (int sg = 0; sg < nSeg; sg++) {
+                    const int segLo = sg == 0 ? zloW : 0;
+                    const int segHi = sg == 0 ? min(zloW + zCount - 1, p.ncz - 1) : zloW + zCount - 1 - p.ncz;
+                    const int zShift = (sg == 0 ? zlo - zloW : zlo - zloW + p.ncz) - c0z;
+                    const int s1 = p.cellStart[rowCell + segHi + 1];
+                    for (int sb = p.cellStart[rowCell + segLo]; sb < s1; sb += 32) {
+                        const int s = sb + lane;
+                        bool pass = false, cls = false;
+                        float4 pj = farAway, mj = farAway;
+                        if (s < s1) {
+                            const float4 l4 = p.sortedLocal[s];
+                            mj = p.sortedMeta[s];
+                            const int cz = __float_as_int(mj.w) >> (2*CELL_BITS);
+                            pj = make_float4(l4.x + shx, l4.y + shy, fmaf((float) (cz + zShift), p.csz, l4.z), l4.w);
+                            if (minImage) pass = true;
+                            else {
+                                const float ex = fmaxf(0.f, fmaxf(bminx - pj.x, pj.x - bmaxx));
+                                const float ey = fmaxf(0.f, fmaxf(bminy - pj.y, pj.y - bmaxy));
+                                const float ez = fmaxf(0.f, fmaxf(bminz - pj.z, pj.z - bmaxz));
+                                pass = fmaf(ez, ez, fmaf(ey, ey, ex*ex)) <= rcut2;
+                            }
+                            cls = anyLJi && mj.y != 0.f;
+                        }
+                        const unsigned int m1 = __ballot_sync(0xffffffffu, pass && cls);
+                        const unsigned int m0 = __ballot_sync(0xffffffffu, pass && !cls);
+                        if (pass) {
+                            const int slot = cls ? ((base1 + count1 + __popc(m1 & lt)) & (P_JCAP - 1)) : ((base0 + count0 + __popc(m0 & lt)) & (P_JCAP - 1));
+                            float* e = &sRing[warp][cls][0][slot];
+                            e[0] = pj.x; e[P_JCAP] = pj.y; e[2*P_JCAP] = pj.z; e[3*P_JCAP] = pj.w; e[4*P_JCAP] = mj.z;
+                            if (cls) { e[5*P_JCAP] = mj.x; e[6*P_JCAP] = mj.y; }
+                        }
+                        count0 += __popc(m0); count1 += __popc(m1);
+                        nCand += (unsigned int) __popc(m0 | m1);
+                        flush(false);
                     }
                 }
             }
+            if (++cxw == p.ncx) cxw = 0;
         }
-    }
-    if (count > 0) processTile(count);
-    if (EMODE == 2 && qCount > 0) energyBatch(qCount);
+        flush(true);
+        if (EMODE == 2 && qCount > 0) energyBatch(qCount);
 
-    // reduce over the 4 lanes of each i atom (warp shuffles), one fixed-point atomic per output
-    if (FORCES) {
+        // reduce over the 4 lanes of each i atom (warp shuffles), one fixed-point atomic per output
+        if (FORCES) {
+            float fx = fx2.x + fx2.y, fy = fy2.x + fy2.y, fz = fz2.x + fz2.y, dq = dq2.x + dq2.y;
+            #pragma unroll
+            for (int o = 1; o <= 2; o <<= 1) {
+                fx += __shfl_xor_sync(0xffffffffu, fx, o); fy += __shfl_xor_sync(0xffffffffu, fy, o);
+                fz += __shfl_xor_sync(0xffffffffu, fz, o); dq += __shfl_xor_sync(0xffffffffu, dq, o);
+            }
+            if (validI && part == 0) {
+                atomicAddFixed(p.forceFixed + ui, (double) fx);
+                atomicAddFixed(p.forceFixed + p.Npad + ui, (double) fy);
+                atomicAddFixed(p.forceFixed + 2*(size_t) p.Npad + ui, (double) fz);
+                atomicAddFixed(p.dedqFixed + ui, (double) ((float) CFX_ONE_4PI_EPS0*dq));
+            }
+        }
+        if (EMODE != 0) {
+            if (EMODE == 1) en = (double) (enf2.x + enf2.y);
+            en = warpSum(en);
+            // FP64 queue: each i<j pair once. FP32 terms: every pair is seen from both sides.
+            if (lane == 0) atomicAddEnergy(p.energyFixed + CFX_E_DIRECT, EMODE == 2 ? en : 0.5*en);
+        }
         #pragma unroll
-        for (int o = 1; o <= 2; o <<= 1) {
-            fx += __shfl_xor_sync(0xffffffffu, fx, o); fy += __shfl_xor_sync(0xffffffffu, fy, o);
-            fz += __shfl_xor_sync(0xffffffffu, fz, o); dq += __shfl_xor_sync(0xffffffffu, dq, o);
+        for (int o = 16; o > 0; o >>= 1) nIn += __shfl_xor_sync(0xffffffffu, nIn, o);
+        if (lane == 0) {
+            atomicAdd(p.counters + 0, (unsigned long long) nIn);        // ordered pairs: the host halves it
+            atomicAdd(p.counters + 1, (unsigned long long) nCand*P_ITILE);
         }
-        if (validI && part == 0) {
-            atomicAddFixed(p.forceFixed + ui, (double) fx);
-            atomicAddFixed(p.forceFixed + p.Npad + ui, (double) fy);
-            atomicAddFixed(p.forceFixed + 2*(size_t) p.Npad + ui, (double) fz);
-            atomicAddFixed(p.dedqFixed + ui, (double) dq);
-        }
-    }
-    if (EMODE != 0) {
-        if (EMODE == 1) en = (double) enf;
-        en = warpSum(en);
-        // FP64 queue: each i<j pair once. FP32 terms: every pair is seen from both sides.
-        if (lane == 0) atomicAddEnergy(p.energyFixed + CFX_E_DIRECT, EMODE == 2 ? en : 0.5*en);
-    }
-    #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) nPairs += __shfl_xor_sync(0xffffffffu, nPairs, o);
-    if (lane == 0) {
-        atomicAdd(p.counters + 0, (unsigned long long) nPairs);
-        atomicAdd(p.counters + 1, (unsigned long long) nCand*P_ITILE);
+        __syncwarp();
     }
 }
 
-template <bool EMIT>
-void dispatchPair(const PairParams& pp, bool forces, int emode, dim3 blocks, cudaStream_t s) {
+template <bool FAST, bool EMIT>
+void dispatchPair(const PairParams& pp, bool forces, int emode, int blocks, cudaStream_t s) {
     const int t = P_WARPS*32;
     if (forces) {
-        if (emode == 2)      pairKernel<true, 2, EMIT><<<blocks, t, 0, s>>>(pp);
-        else if (emode == 1) pairKernel<true, 1, EMIT><<<blocks, t, 0, s>>>(pp);
-        else                 pairKernel<true, 0, EMIT><<<blocks, t, 0, s>>>(pp);
+        if (emode == 2)      pairKernel<FAST, true, 2, EMIT><<<blocks, t, 0, s>>>(pp);
+        else if (emode == 1) pairKernel<FAST, true, 1, EMIT><<<blocks, t, 0, s>>>(pp);
+        else                 pairKernel<FAST, true, 0, EMIT><<<blocks, t, 0, s>>>(pp);
     }
     else {
-        if (emode == 2)      pairKernel<false, 2, EMIT><<<blocks, t, 0, s>>>(pp);
-        else if (emode == 1) pairKernel<false, 1, EMIT><<<blocks, t, 0, s>>>(pp);
-        else                 pairKernel<false, 0, EMIT><<<blocks, t, 0, s>>>(pp);
+        if (emode == 2)      pairKernel<FAST, false, 2, EMIT><<<blocks, t, 0, s>>>(pp);
+        else if (emode == 1) pairKernel<FAST, false, 1, EMIT><<<blocks, t, 0, s>>>(pp);
+        else                 pairKernel<FAST, false, 0, EMIT><<<blocks, t, 0, s>>>(pp);
     }
 }
 
@@ -464,7 +611,7 @@ void planCells(State& st) {
         c.csd[d] = st.box.L[d]/n;
         c.cs[d] = (float) c.csd[d];
         c.ncells *= n;
-        if (n < 7) c.smallBox = true;      // informational: tiles will fall back to per-pair min image
+        if (n < 7) c.smallBox = true;      // the 5-cell stencil wraps onto itself: generic pair kernel (per-pair min image)
     }
     CFX_CUDA(cudaMalloc(&st.cellOfAtom, sizeof(int)*st.Npad));
     CFX_CUDA(cudaMalloc(&st.cellCount, sizeof(int)*(c.ncells + 1)));
@@ -472,18 +619,21 @@ void planCells(State& st) {
     CFX_CUDA(cudaMalloc(&st.cellFill, sizeof(int)*(c.ncells + 1)));
     CFX_CUDA(cudaMalloc(&st.userLocal, sizeof(float4)*st.Npad));
     CFX_CUDA(cudaMalloc(&st.sortedLocal, sizeof(float4)*st.Npad));
-    CFX_CUDA(cudaMalloc(&st.sortedCell, sizeof(int)*st.Npad));
-    CFX_CUDA(cudaMalloc(&st.sortedLJ, sizeof(float2)*st.Npad));
-    CFX_CUDA(cudaMalloc(&st.sortedUser, sizeof(int)*st.Npad));
+    CFX_CUDA(cudaMalloc(&st.sortedMeta, sizeof(float4)*st.Npad));
     CFX_CUDA(cudaMalloc(&st.filledUser, sizeof(int)*st.Npad));
-    CFX_CUDA(cudaMalloc(&st.pairCounters, sizeof(unsigned long long)*4));
+    CFX_CUDA(cudaMalloc(&st.pairCounters, sizeof(unsigned long long)*8));
+    CFX_CUDA(cudaMemset(st.pairCounters, 0, sizeof(unsigned long long)*8));
 }
 
+// pairCounters (8 x u64): [0] in-cutoff ordered pairs, [1] distance tests, [2] emitted pairs, [4] float bits of the largest
+// excluded-pair r2 (flux.cu), [5] / [6] work-item counters of the fast / generic pair kernel, [7] clusters the fast kernel
+// left to the generic one.
 void launchDirect(State& st, const double* dPos, bool forces, int emode, bool emitPairs, long long* dForce, long long* dDedq, cudaStream_t s) {
     if (!forces && emode == 0 && !emitPairs) return;
     CellPlan& c = st.cells;
     CellParams cp{st.N, c.nc[0], c.nc[1], c.nc[2], c.ncells, 1.0/st.box.L[0], 1.0/st.box.L[1], 1.0/st.box.L[2], c.csd[0], c.csd[1], c.csd[2]};
     CFX_CUDA(cudaMemsetAsync(st.cellCount, 0, sizeof(int)*(c.ncells + 1), s));
+    CFX_CUDA(cudaMemsetAsync(st.pairCounters + 5, 0, sizeof(unsigned long long)*3, s));
     cellAssignKernel<<<(st.N + 255)/256, 256, 0, s>>>(cp, dPos, st.qf, st.cellOfAtom, st.userLocal, st.cellCount);
     CFX_LAUNCH_CHECK(); st.launches++;
     cellScanKernel<<<1, 1024, 0, s>>>(c.ncells, st.cellCount, st.cellStart, st.cellFill);
@@ -491,24 +641,25 @@ void launchDirect(State& st, const double* dPos, bool forces, int emode, bool em
     cellFillKernel<<<(st.N + 255)/256, 256, 0, s>>>(st.N, st.cellOfAtom, st.cellFill, st.filledUser);
     CFX_LAUNCH_CHECK(); st.launches++;
     cellRankGatherKernel<<<(st.N + 255)/256, 256, 0, s>>>(st.N, c.nc[1], c.nc[2], st.filledUser, st.cellOfAtom, st.cellStart,
-            st.userLocal, st.lj, st.sortedUser, st.sortedLocal, st.sortedCell, st.sortedLJ);
+            st.userLocal, st.lj, st.sortedLocal, st.sortedMeta);
     CFX_LAUNCH_CHECK(); st.launches++;
     mark(st, "cell_build", s);
 
     PairParams pp;
     pp.N = st.N; pp.Npad = st.Npad;
     pp.numGroups = (st.N + P_ITILE - 1)/P_ITILE;
-    // spatial sharding: contiguous ranges of i-tiles in cell order are spatial slabs
+    // spatial sharding: contiguous ranges of i-clusters in cell order are spatial slabs
     pp.groupLo = (int) ((int64_t) pp.numGroups*st.shardRank/st.shardCount);
     pp.groupHi = (int) ((int64_t) pp.numGroups*(st.shardRank + 1)/st.shardCount);
     pp.ncx = c.nc[0]; pp.ncy = c.nc[1]; pp.ncz = c.nc[2];
-    pp.csx = c.cs[0]; pp.csy = c.cs[1]; pp.csz = c.cs[2];
+    pp.csx = c.cs[0]; pp.csy = c.cs[1]; pp.csz = c.cs[2]; pp.invCsz = 1.0f/c.cs[2];
     pp.Lx = (float) st.box.L[0]; pp.Ly = (float) st.box.L[1]; pp.Lz = (float) st.box.L[2];
     pp.invLx = (float) (1.0/st.box.L[0]); pp.invLy = (float) (1.0/st.box.L[1]); pp.invLz = (float) (1.0/st.box.L[2]);
     pp.dLx = st.box.L[0]; pp.dLy = st.box.L[1]; pp.dLz = st.box.L[2];
     pp.rc2d = st.cutoff*st.cutoff;
-    pp.rc2 = (float) pp.rc2d; pp.alpha = (float) st.alpha; pp.band = (float) (1e-5*pp.rc2d);
-    pp.sortedLocal = st.sortedLocal; pp.sortedCell = st.sortedCell; pp.sortedLJ = st.sortedLJ; pp.sortedUser = st.sortedUser;
+    pp.rc2 = (float) pp.rc2d; pp.alpha = (float) st.alpha; pp.alpha2 = (float) (st.alpha*st.alpha); pp.band = (float) (1e-5*pp.rc2d);
+    pp.exclMaxR2Bits = reinterpret_cast<const unsigned int*>(st.pairCounters + 4);
+    pp.sortedLocal = st.sortedLocal; pp.sortedMeta = st.sortedMeta;
     pp.cellStart = st.cellStart; pp.exclPtr = st.exclPtr; pp.exclCols = st.exclCols; pp.pos = dPos;
     pp.q = st.q; pp.ljd = st.ljd; pp.alphaD = st.alpha;
     pp.dInvLx = 1.0/st.box.L[0]; pp.dInvLy = 1.0/st.box.L[1]; pp.dInvLz = 1.0/st.box.L[2];
@@ -516,18 +667,31 @@ void launchDirect(State& st, const double* dPos, bool forces, int emode, bool em
     pp.counters = st.pairCounters; pp.pairBuffer = st.pairBuffer; pp.pairCapacity = (unsigned long long) st.pairCapacity;
     const int groups = pp.groupHi - pp.groupLo;
     if (groups <= 0) return;
-    const int blocks = (groups + P_WARPS - 1)/P_WARPS;
-    // Deal each i-tile's stencil columns over several CTAs until ~10 CTAs per SM exist (5 with the FP64 energy queue,
-    // whose 32-pair batches fill more slowly when split): a shard with few i-tiles would otherwise run at single-CTA
-    // latency (~0.1 ms), and at one GPU 2 splits smooth the last wave (0.247 -> 0.222 ms at C3).
+    // Work items = (i-cluster, share of its stencil columns), handed to persistent warps by an atomic counter. One share
+    // per cluster unless that leaves fewer than ~28 items per SM -- small systems, shards -- (the partial sums of the
+    // shares meet in the fixed-point atomics).
     int numSM = 148;
     cudaDeviceGetAttribute(&numSM, cudaDevAttrMultiProcessorCount, st.device);
-    pp.jSplits = std::max(1, std::min(8, ((emode == 2 ? 5 : 10)*numSM + blocks - 1)/blocks));
+    pp.jSplits = std::max(1, std::min(8, (28*numSM + groups - 1)/groups));
     if (const char* e = getenv("CFX_PAIR_JSPLITS")) pp.jSplits = std::max(1, std::min(8, atoi(e)));     // experiments
     if (emitPairs) pp.jSplits = 1;
-    const dim3 grid(blocks, pp.jSplits);
-    if (emitPairs) dispatchPair<true>(pp, forces, emode, grid, s);
-    else           dispatchPair<false>(pp, forces, emode, grid, s);
+    const int items = groups*pp.jSplits;
+    const bool fast = !c.smallBox;
+    if (fast) {
+        pp.onlyMinImage = 0;
+        pp.workCounter = reinterpret_cast<unsigned int*>(st.pairCounters + 5);
+        const int grid = std::min((items + P_WARPS - 1)/P_WARPS, P_FAST_MINBLOCKS*numSM);
+        if (emitPairs) dispatchPair<true, true>(pp, forces, emode, grid, s);
+        else           dispatchPair<true, false>(pp, forces, emode, grid, s);
+        CFX_LAUNCH_CHECK(); st.launches++;
+    }
+    // every cluster (small boxes), or the few whose stencil wraps onto itself in a large box (it exits at once when
+    // the fast kernel skipped none)
+    pp.onlyMinImage = fast ? 1 : 0;
+    pp.workCounter = reinterpret_cast<unsigned int*>(st.pairCounters + 6);
+    const int grid = std::min((items + P_WARPS - 1)/P_WARPS, 4*numSM);
+    if (emitPairs) dispatchPair<false, true>(pp, forces, emode, grid, s);
+    else           dispatchPair<false, false>(pp, forces, emode, grid, s);
     CFX_LAUNCH_CHECK(); st.launches++;
     mark(st, "direct_pairs", s);
 }

@@ -153,18 +153,24 @@ __global__ void __launch_bounds__(256) chainRuleKernel(int P, int Npad, const in
 
 // One thread per unique excluded pair (i<j). Periodic: remove the reciprocal-space image of the pair
 // (erf term, no cutoff test, no LJ). Non-periodic: subtract the full Coulomb + LJ pair.
+// maxR2Bits (periodic): the largest squared separation of any excluded pair, as float bits rounded up -- the pair
+// kernel only probes the exclusion lists for pairs at or below it. With accumulate == false (ranks > 0 of a sharded
+// evaluation) that is all the kernel produces.
 __global__ void __launch_bounds__(128) exclusionKernel(int numExcl, int Npad, const int2* __restrict__ pairs,
         const double* __restrict__ pos, const double* __restrict__ q, const double2* __restrict__ lj,
-        BoxD box, bool pbc, double alpha, bool forces, bool energy,
-        long long* __restrict__ forceFixed, long long* __restrict__ dedqFixed, long long* __restrict__ energyFixed) {
+        BoxD box, bool pbc, double alpha, bool forces, bool energy, bool accumulate,
+        long long* __restrict__ forceFixed, long long* __restrict__ dedqFixed, long long* __restrict__ energyFixed,
+        unsigned int* __restrict__ maxR2Bits) {
     __shared__ double scratch[32];
     const int e = blockIdx.x*blockDim.x + threadIdx.x;
     const double ke = CFX_ONE_4PI_EPS0;
     double en = 0.0;
+    float r2up = 0.f;
     if (e < numExcl) {
         const int i = pairs[e].x, j = pairs[e].y;
         double3 d = deltaPeriodic(pos, j, i, box, pbc);            // pos[i] - pos[j]
         const double r2 = dot3(d);
+        r2up = __double2float_ru(r2);
         const double r = sqrt(r2), invR = 1.0/r;
         const double qi = q[i], qj = q[j];
         double dEdR, dqi, dqj;                                       // contributions to subtract
@@ -186,7 +192,7 @@ __global__ void __launch_bounds__(128) exclusionKernel(int numExcl, int Npad, co
             dqj = ke*qi*invR;
             en = energy ? -(ke*qi*qj*invR + es6*(s6 - 1)) : 0.0;
         }
-        if (forces) {
+        if (forces && accumulate) {
             atomicAddFixed(forceFixed + i,          -dEdR*d.x);
             atomicAddFixed(forceFixed + Npad + i,   -dEdR*d.y);
             atomicAddFixed(forceFixed + 2*Npad + i, -dEdR*d.z);
@@ -197,6 +203,12 @@ __global__ void __launch_bounds__(128) exclusionKernel(int numExcl, int Npad, co
             atomicAddFixed(dedqFixed + j, -dqj);
         }
     }
+    if (maxR2Bits) {                                                 // non-negative floats order like their bit patterns
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r2up = fmaxf(r2up, __shfl_xor_sync(0xffffffffu, r2up, o));
+        if ((threadIdx.x & 31) == 0 && r2up > 0.f) atomicMax(maxR2Bits, __float_as_uint(r2up));
+    }
+    if (!accumulate) return;                                         // (uniform over the grid)
     en = blockSum(en, scratch);
     if (threadIdx.x == 0) atomicAddEnergy(energyFixed + CFX_E_EXCL, en);
 }
@@ -298,10 +310,14 @@ void launchChainRule(State& st, long long* dForce, const long long* dDedq, cudaS
     mark(st, "chain_rule", s);
 }
 
+// Periodic branch. Must run BEFORE launchDirect on the same stream: it leaves the largest excluded-pair r2 in
+// pairCounters[4] for the pair kernel (every rank of a sharded evaluation needs that; only rank 0 accumulates).
 void launchExclusionCorrection(State& st, const double* dPos, bool forces, long long* dForce, long long* dDedq, cudaStream_t s) {
-    if (st.numExcl == 0 || st.shardRank != 0) return;
+    CFX_CUDA(cudaMemsetAsync(st.pairCounters + 4, 0, sizeof(unsigned long long), s));
+    if (st.numExcl == 0) return;
     exclusionKernel<<<(st.numExcl + 127)/128, 128, 0, s>>>(st.numExcl, st.Npad, st.exclPairs, dPos, st.q, st.ljd,
-            boxOf(st), st.pbc, st.alpha, forces, true, dForce, dDedq, st.energyFixed);
+            boxOf(st), st.pbc, st.alpha, forces, true, st.shardRank == 0, dForce, dDedq, st.energyFixed,
+            reinterpret_cast<unsigned int*>(st.pairCounters + 4));
     CFX_LAUNCH_CHECK(); st.launches++;
     mark(st, "exclusion_corr", s);
 }
@@ -313,7 +329,7 @@ void launchNoCutoff(State& st, const double* dPos, bool forces, bool energy, lon
     mark(st, "nocutoff_pairs", s);
     if (st.numExcl > 0) {
         exclusionKernel<<<(st.numExcl + 127)/128, 128, 0, s>>>(st.numExcl, st.Npad, st.exclPairs, dPos, st.q, st.ljd,
-                boxOf(st), false, 0.0, forces, energy, dForce, dDedq, st.energyFixed);
+                boxOf(st), false, 0.0, forces, energy, true, dForce, dDedq, st.energyFixed, nullptr);
         CFX_LAUNCH_CHECK(); st.launches++;
         mark(st, "nocutoff_excl", s);
     }

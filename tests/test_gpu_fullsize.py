@@ -1,9 +1,11 @@
 """GPU: size-independent properties at BASELINE.json's full 32k-atom configuration, plus the parts
 of the oracle that finish in seconds at that size (everything except the explicit k-sum)."""
+import os
+
 import numpy as np
 import pytest
 
-from conftest import E_RTOL, F_RTOL, rel_rms
+from conftest import E_RTOL, F_RTOL, GOLDEN_DIR, rel_rms
 from openmm_chargeflux_b200 import _abi, runtime, synthetic
 from oracle import Oracle
 
@@ -76,3 +78,70 @@ def test_c3_reproducible(c3):
     pos, box, force, ctx, e, f, comps = c3
     e2, f2, _ = ctx.evaluate(pos)
     assert e2 == e and np.array_equal(f2, f)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Full k lattice at the benchmark sizes. tests/golden/{c3,c4}_fullk.npz hold the oracle's energies and forces
+# with its explicit k-sum spread over the host cores (tests/golden/make_golden_fullsize.py, oracle/slabs.py).
+# ---------------------------------------------------------------------------------------------------------
+def _fullk(name):
+    path = os.path.join(GOLDEN_DIR, name + "_fullk.npz")
+    if not os.path.exists(path):
+        pytest.skip(name + "_fullk.npz not generated")
+    data = np.load(path)
+    pos, box, force = synthetic.config(name)
+    assert abs(float((pos * np.arange(1, 4)[None, :]).sum()) - float(data["pos_checksum"])) <= 1e-9 * abs(float(data["pos_checksum"]))
+    return data, pos, box, force
+
+
+def _check_fullk(ctx, data, pos, include_energy):
+    e, f, comps = ctx.evaluate(pos, True, include_energy)
+    eg = data["energy"]
+    if include_energy:
+        assert abs(e - eg[4]) <= E_RTOL * abs(eg[4]), (e, eg)
+        assert np.abs(comps[:4] - eg[:4]).max() <= E_RTOL * abs(eg[4])
+    else:
+        # the reference returns self + direct + exclusion when includeEnergy is false (no reciprocal term)
+        partial = eg[0] + eg[2] + eg[3]
+        assert abs(e - partial) <= 5e-5 * abs(partial)
+    assert rel_rms(f, data["forces_f32"].astype(np.float64)) <= F_RTOL
+    probe = data["probe"]
+    assert rel_rms(f[probe], data["forces_probe"]) <= F_RTOL
+    assert rel_rms(ctx.kernel.dedq()[probe], data["dedq_probe"]) <= F_RTOL
+    assert ctx.kernel.stats().pairs_in_cutoff == int(data["pairs_in_cutoff"])
+
+
+@pytest.mark.parametrize("include_energy", [True, False])
+def test_c3_full_kmax27_against_the_oracle(c3, include_energy):
+    """C3 at its real kmax = (27,27,27), 74,438 k-vectors: energy 1e-6, forces 1e-5 relative RMS. The forces-only call
+    is the per-MD-step call of the benchmark (tensor-core structure factors + tensor-core gather)."""
+    data, pos, box, force = _fullk("c3")
+    ctx = c3[3]
+    assert tuple(data["kmax"]) == ctx.kernel.ewald_params()[1] == (27, 27, 27)
+    _check_fullk(ctx, data, pos, include_energy)
+
+
+def test_c3_full_kmax27_live_oracle_over_the_host_cores(c3):
+    """The same comparison against the oracle run HERE, its k-sum in parallel slabs (about a minute of CPU time)."""
+    from oracle.slabs import execute_parallel, host_cores
+    if host_cores() < 4:
+        pytest.skip("needs a few host cores")
+    pos, box, force, ctx, e, f, comps = c3
+    eo, fo, dedq, kmax = execute_parallel(force, box, pos)
+    assert kmax == (27, 27, 27)
+    assert abs(e - eo[4]) <= E_RTOL * abs(eo[4])
+    assert np.abs(comps[:4] - eo[:4]).max() <= E_RTOL * abs(eo[4])
+    assert rel_rms(f, fo) <= F_RTOL
+    e2, f2, _ = ctx.evaluate(pos, True, False)
+    assert rel_rms(f2, fo) <= F_RTOL
+    assert rel_rms(ctx.kernel.dedq(), dedq) <= F_RTOL
+
+
+@pytest.mark.parametrize("include_energy", [True, False])
+def test_c4_262k_atoms_kmax55_against_the_oracle(build_native, include_energy):
+    """C4 (262,143 atoms, kmax 55, 647,514 k-vectors): the <1,64> gather and <128,1> structure-factor variants."""
+    data, pos, box, force = _fullk("c4")
+    ctx = runtime.CoulContext(force, box)
+    assert tuple(data["kmax"]) == ctx.kernel.ewald_params()[1] == (55, 55, 55)
+    _check_fullk(ctx, data, pos, include_energy)
+    ctx.kernel.close()

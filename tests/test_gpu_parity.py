@@ -209,3 +209,41 @@ def test_update_parameters_equals_a_fresh_handle(build_native):
     _, _, smaller = synthetic.water_box(125, seed=3, cutoff=0.9, ewald_tol=1e-5)
     with pytest.raises(runtime.CfxError):
         live.kernel.copyParametersToContext(box, smaller)
+
+
+def test_sharded_handle_needs_a_periodic_system(build_native):
+    """The non-periodic all-pairs branch is not partitioned: a sharded handle for it would count every pair on every rank."""
+    pos, box, force = synthetic.config("c1")
+    k = runtime.CalcCoulForceKernel(shard_rank=0, shard_count=2)
+    with pytest.raises(runtime.CfxError, match="periodic"):
+        k.initialize(box, force)
+
+
+def test_failed_create_reports_and_leaves_the_library_usable(build_native):
+    pos, box, force = synthetic.water_box(64, seed=5, cutoff=0.6)
+    k = runtime.CalcCoulForceKernel(device=99)
+    with pytest.raises(runtime.CfxError, match="device"):
+        k.initialize(box, force)
+    ctx = runtime.CoulContext(force, box)                 # the failed create released everything it had allocated
+    assert np.isfinite(ctx.evaluate(pos)[0])
+
+
+def test_pinned_caller_buffers_give_the_staged_result(build_native):
+    """CFX_OPT_PIN_CALLER_BUFFERS: arrays passed repeatedly are page-locked in place (DMA-read positions, forces
+    accumulated into the caller's array by the GPU); results are identical to the default staging path."""
+    pos, box, force = synthetic.water_box(216, seed=9, cutoff=0.9)
+    staged = runtime.CalcCoulForceKernel()
+    staged.initialize(box, force)
+    pinned = runtime.CalcCoulForceKernel(pin_caller_buffers=True)
+    pinned.initialize(box, force)
+    f_ref = np.zeros_like(pos)
+    e_ref = staged.execute(pos, box, f_ref)
+    f_pin = np.zeros_like(pos)
+    for call in range(4):                                  # registered from the second sighting on
+        f_pin[:] = 1.0                                     # forces are ADDED to what the array holds
+        e = pinned.execute(pos, box, f_pin)
+        assert e == e_ref and np.array_equal(f_pin - 1.0, (f_ref + 1.0) - 1.0), call
+    other = pos + 0.0                                      # a different array: unregisters the first one
+    f2 = np.zeros_like(pos)
+    assert pinned.execute(other, box, f2) == e_ref and np.array_equal(f2, f_ref)
+    pinned.close(); staged.close()

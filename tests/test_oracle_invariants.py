@@ -113,3 +113,16 @@ def test_kmax_and_alpha_follow_the_reference_rule(build_native):
         alpha, k, n = Oracle(f, np.diag([box_len] * 3)).ewald_params()
         assert k == (kmax,) * 3 and n == nk
         assert abs(alpha - np.sqrt(-np.log(2 * tol))) < 1e-12
+
+
+def test_parallel_k_slabs_reproduce_the_single_threaded_oracle(build_native):
+    """oracle/slabs.py (used for the full-size parity pins): slab sum == one-thread evaluation to rounding."""
+    from oracle.slabs import execute_parallel
+    pos, box, force = synthetic.water_box(216, seed=3, cutoff=0.9, ewald_tol=1e-5)
+    o = Oracle(force, box)
+    e, f = o.execute(pos, box, True, True)
+    e2, f2, d2, kmax = execute_parallel(force, box, pos, workers=3)
+    assert kmax == o.ewald_params()[1]
+    assert np.abs(e - e2).max() <= 1e-12 * np.abs(e[:4]).max()
+    assert np.sqrt(((f - f2) ** 2).sum() / (f ** 2).sum()) <= 1e-13
+    assert np.sqrt(((o.dedq() - d2) ** 2).sum() / (d2 ** 2).sum()) <= 1e-13

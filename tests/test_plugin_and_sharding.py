@@ -173,6 +173,8 @@ def test_execute_shard_fills_the_reduction_buffer_like_execute_device(flags, bui
     buf = total.cpu().numpy()
     fs = buf[:3 * npad].reshape(3, npad)[:, :n].T / FIXED_SCALE
     es = buf[3 * npad:3 * npad + 5] / ENERGY_SCALE
-    assert abs(es[4] - e) <= 1e-8 * max(abs(e), 1e-3 * np.abs(comps[:4]).max())
+    # includeEnergy=False: the partial energy OpenMM discards is summed from FP32 pair terms, and a shard deals its
+    # clusters' stencil columns over more CTAs than the whole evaluation does (different FP32 partial sums)
+    assert abs(es[4] - e) <= (1e-8 if flags[1] else 1e-6) * max(abs(e), 1e-3 * np.abs(comps[:4]).max())
     assert abs(es[:4].sum() - es[4]) <= 1e-6
     assert rel_rms(fs, f) <= 2e-6
