@@ -3,11 +3,12 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c4] [--impl reference]
 
-One "step" = one CalcCoulForceKernel::execute(includeForces=true, includeEnergy=false) -- the call OpenMM makes
-once per MD time step: charge-flux assembly, Ewald direct + explicit-k reciprocal + self + excluded-pair
-correction and the dE/dq.dq/dx chain rule, on the synthetic flexible-water box named in `config.workload`.
-The energy+forces call (what a reporter / minimiser makes) is measured the same way and reported beside it as
-`energy_and_forces`; both arms (`--impl reference` too) use the same flags.
+One "step" = one CalcCoulForceKernel::execute(includeForces=true, includeEnergy=true), BASELINE.md's definition of a
+force evaluation: charge-flux assembly, Ewald direct + explicit-k reciprocal + self + excluded-pair correction and the
+dE/dq.dq/dx chain rule, energy and forces, on the synthetic flexible-water box named in `config.workload`. Both arms
+(`--impl reference` too) use these flags. The forces-only call OpenMM makes once per MD time step (includeEnergy=false) is
+measured the same way and reported at top level as `value_forces_only` / `ms_per_step_forces_only`; `ns_per_day` derives
+from it.
 
   value     whole-job force-evals/s with positions resident in HBM, CUDA events around every step,
             L2 flushed between steps, max over ranks.
@@ -21,9 +22,12 @@ The energy+forces call (what a reporter / minimiser makes) is measured the same 
   cpu_baseline  the plugin's Reference-platform kernel (oracle/_ref when present, else the oracle port)
             on one host core, bounded sample, extrapolated in the number of k-vectors.
 
-`--impl reference` times that CPU implementation alone (the reference platform is single-threaded).
-N > 1 (launched by torchrun): k-vectors and direct-space i-tiles sharded over the ranks, one NCCL
-all-reduce of the fixed-point forces per step; total work fixed => "scaling": "strong".
+`--impl reference` times that CPU implementation alone: one full evaluation at the real kmax, no extrapolation (the
+reference platform is single-threaded; ~90 s at C3).
+N > 1 (launched by torchrun): k-vectors and direct-space i-clusters sharded over the ranks, one NCCL all-reduce of the
+fixed-point reduction buffer per step, issued by the library inside the step's CUDA graph (cfx_comm_init /
+cfx_execute_sharded); total work fixed => "scaling": "strong". The line adds `parity_vs_single` (sharded against the same
+evaluation on one GPU) and a `c4` block: the 262k-atom box at N GPUs and on one.
 """
 import argparse
 import json
@@ -46,7 +50,8 @@ WORKLOADS = {
     "c4": "c4: 262,143-atom periodic flexible-water box, cutoff 1.0 nm, Ewald tol 1e-5, bond+angle charge flux",
 }
 TIMESTEP_FS = 0.5
-INCLUDE_ENERGY = False          # the headline step is the MD-step call: forces only
+INCLUDE_ENERGY = True           # one force eval = one full execute, energy + forces
+FLAGS_NOTE = "includeForces=1 includeEnergy=1 (BASELINE.md: one force eval = energy + forces)"
 
 
 def ns_per_day(evals_per_s):
@@ -208,32 +213,28 @@ def existing_cuda_baseline(workload, our_ms):
 
 
 def run_reference_arm(args, pos, box, force, workload):
+    """The reference's own CPU implementation (oracle/_ref: the plugin's unmodified platforms/reference sources; else the
+    oracle port), ONE full, un-extrapolated evaluation at the real kmax, timed once: a C3 evaluation takes ~90 s on one
+    core and the reference platform has no threading, so K + W repetitions would not fit a bench run. `steps` reports
+    what was actually timed."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     kind, make = _cpu_factory()
-    total_calls = args.steps + args.warmup
-    t_nonk, _, _, nfull = cpu_reference_sample(pos, box, force, 1, make)
-    budget = max(150.0 / max(total_calls, 1) - t_nonk, 0.3)
-    n = len(pos)
-    target = 3
-    for km in (5, 7, 9, 11):
-        if (((2 * km - 1) ** 3 - 1) // 2) * n * 9.0e-8 <= budget:
-            target = km
-    times, ks_used, kmax_used = [], None, None
-    for it in range(total_calls):
-        t_s, ks, kmax_s, nfull = cpu_reference_sample(pos, box, force, target, make)
-        if it >= args.warmup:
-            times.append(t_nonk + max(t_s - t_nonk, 0.0) * nfull / max(ks, 1))
-        ks_used, kmax_used = ks, kmax_s
-    t_full = float(np.mean(times))
+    h = make(force, box)
+    alpha, kmax, nk = h.ewald_params()
+    t = time.perf_counter()
+    h.execute(pos, box, True, INCLUDE_ENERGY)
+    t_full = time.perf_counter() - t
     value = 1.0 / t_full
-    sample = ("each step: one execute of the CPU reference with kmax=%s (%d of %d k-vectors), k part scaled by %d/%d, "
-              "non-k part %.2f s measured once; single thread" % (tuple(kmax_used), ks_used, nfull, nfull, ks_used, t_nonk))
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * t_full, "higher_is_better": True, "scaling": "strong",
+    n = len(pos)
+    sample = ("one full execute(includeForces=1, includeEnergy=1) at the real kmax=%s (%d half-space k-vectors), timed once, no "
+              "extrapolation; requested --steps %d --warmup %d not repeated (%.0f s per evaluation); single thread: the reference "
+              "platform has no threading" % (tuple(kmax), nk, args.steps, args.warmup, t_full))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": 1,
+            "warmup": 0, "ms_per_step": 1e3 * t_full, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload, "atoms": n, "kvectors": int(nfull), "flags": "includeForces=1 includeEnergy=0"},
+            "config": {"workload": workload, "atoms": n, "kvectors": int(nk), "flags": FLAGS_NOTE},
             "ns_per_day": ns_per_day(value),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -249,8 +250,9 @@ def algorithmic_flops(n_atoms, n_k, pairs, n_terms, n_rows, n_excl):
             "total": 12.0 * n_atoms * n_k + 80.0 * pairs + 150.0 * n_terms + 6.0 * n_rows + 40.0 * n_excl + 4.0 * n_atoms}
 
 
-def executed_tensor_flops(n_atoms, kmax):
-    """TF32 FLOP the tensor-core k-space kernels execute per launch: three products, padded tiles."""
+def executed_tensor_flops(n_atoms, kmax, energy):
+    """TF32 FLOP the tensor-core k-space kernels execute per launch: three products, padded tiles.
+    Evaluations that return the energy run the FP32 CUDA-core structure-factor kernel instead of the tensor one."""
     kx, ky, kz = kmax
     npad = (n_atoms + 255) // 256 * 256
     out = {}
@@ -260,7 +262,7 @@ def executed_tensor_flops(n_atoms, kmax):
         signed = ky + (kx - 1) * (2 * ky - 1)
         cols = (signed + nt // 4 - 1) // (nt // 4) * nt
         out["kspace_gather"] = 3 * 2.0 * npad * kp * cols
-    if kz <= 64:
+    if kz <= 64 and not energy:
         nn = 64 if kz <= 32 else 128
         rows_per_cta = 32 * (128 // nn)
         rows = (kx * ky + rows_per_cta - 1) // rows_per_cta * rows_per_cta
@@ -268,11 +270,46 @@ def executed_tensor_flops(n_atoms, kmax):
     return out
 
 
+class Rank:
+    """One rank of the bench: a (possibly sharded) kernel handle, device buffers, and the step it times."""
+
+    def __init__(self, torch, dist, force, box, pos, rank, world, local, comm_id=None):
+        from openmm_chargeflux_b200 import runtime
+        self.torch, self.dist, self.world, self.box = torch, dist, world, box
+        self.kernel = runtime.CalcCoulForceKernel(device=local, shard_rank=rank, shard_count=world, pin_caller_buffers=True)
+        self.kernel.initialize(box, force)
+        if world > 1:
+            self.kernel.comm_init(comm_id)
+        self.n, self.npad = len(pos), self.kernel.padded_num_particles()
+        self.d_pos = torch.tensor(pos.reshape(-1), dtype=torch.float64, device="cuda")
+        self.d_buf = torch.zeros(3 * self.npad + 8, dtype=torch.int64, device="cuda")
+        self.stream = torch.cuda.Stream()
+
+    def step(self, include_energy):
+        """One evaluation on device-resident positions: the shard's CUDA graph, and for world > 1 the all-reduce inside it."""
+        fn = self.kernel.execute_sharded if self.world > 1 else self.kernel.execute_shard
+        fn(self.d_pos.data_ptr(), self.box, self.d_buf.data_ptr(), self.stream.cuda_stream, True, include_energy)
+
+    def forces(self):
+        self.stream.synchronize()
+        return self.d_buf[:3 * self.npad].view(3, self.npad)[:, :self.n].t().to(self.torch.float64).cpu().numpy() / 4294967296.0
+
+    def energies(self):
+        self.stream.synchronize()
+        return self.d_buf[3 * self.npad:3 * self.npad + 5].cpu().numpy().astype(np.float64) / 16777216.0
+
+
+def broadcast_comm_id(dist, rank):
+    from openmm_chargeflux_b200 import runtime
+    box_ = [runtime.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box_, src=0)
+    return box_[0]
+
+
 def run_ours(args, pos, box, force, workload):
     import torch
     import torch.distributed as dist
-    from openmm_chargeflux_b200 import runtime
-    from openmm_chargeflux_b200.parallel import ShardedCoulContext
+    from openmm_chargeflux_b200 import runtime, synthetic
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -280,17 +317,17 @@ def run_ours(args, pos, box, force, workload):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: there is no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    nccl_log = None
     if world > 1:
-        # rank 0 must print exactly one JSON line: NCCL's banner / debug output (NCCL_DEBUG >= VERSION) goes to a file
-        if "CFX_NCCL_DEBUG" in os.environ:
-            os.environ["NCCL_DEBUG"] = os.environ["CFX_NCCL_DEBUG"]
-        else:
-            os.environ.pop("NCCL_DEBUG", None)
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/cfx_nccl_%h_%p.log")
+        # NCCL's INFO log (rank count, transports, NVLS) stays available to whoever runs this: it goes to a per-process
+        # file and rank 0 copies every rank's file to stderr after the JSON line, so that stdout holds the one JSON line
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        nccl_log = "/tmp/cfx_nccl_%d" % os.getppid()
+        os.environ["NCCL_DEBUG_FILE"] = nccl_log + ".%h.%p.log"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n = len(pos)
-    ctx = ShardedCoulContext(force, box, rank=rank, world=world, device=local)
-    ctx.d_pos.copy_(torch.from_numpy(pos.reshape(-1)))
+    comm_id = broadcast_comm_id(dist, rank) if world > 1 else None
+    me = Rank(torch, dist, force, box, pos, rank, world, local, comm_id)
     torch.cuda.synchronize()
     flush = torch.empty(384 << 20, dtype=torch.uint8, device="cuda")        # > 126 MB L2
 
@@ -300,95 +337,138 @@ def run_ours(args, pos, box, force, workload):
             dist.barrier()
             torch.cuda.synchronize()
 
-    def timed(include_energy):
+    def timed(r, include_energy, steps):
         for _ in range(max(args.warmup, 3)):
-            ctx.evaluate_device(True, include_energy)
+            r.step(include_energy)
         barrier()
-        ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-        ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
         barrier()
-        for i in range(args.steps):
-            with torch.cuda.stream(ctx.stream):
+        for i in range(steps):
+            with torch.cuda.stream(r.stream):
                 flush.zero_()
-                ev0[i].record(ctx.stream)
-            ctx.evaluate_device(True, include_energy)
-            ev1[i].record(ctx.stream)
+                ev0[i].record(r.stream)
+            r.step(include_energy)
+            ev1[i].record(r.stream)
         barrier()
         ms = torch.tensor([sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))], device="cuda", dtype=torch.float64)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()) / args.steps
+        return float(ms.item()) / steps
 
-    ms_ef = timed(True)                                       # energy + forces, reported beside the headline
+    ms_f = timed(me, False, args.steps)                      # forces only: the per-MD-step call, reported beside the headline
     sampler = ClockSampler(local) if rank == 0 else None
     t_start = time.perf_counter()
-    ms_per_step = timed(INCLUDE_ENERGY)
-    launches_per_eval = ctx.kernel.stats().kernel_launches
+    ms_per_step = timed(me, INCLUDE_ENERGY, args.steps)      # headline: energy + forces
+    launches_per_eval = me.kernel.stats().kernel_launches
+    me.step(INCLUDE_ENERGY)
+    f_sharded, e_sharded = me.forces(), me.energies()
 
-    # end to end through the reference-facing call (host buffers in, host buffers out)
-    e2e_times = []
-    forces_host = np.zeros_like(pos)
-    for i in range(args.steps + 3):
-        flush.zero_()
-        barrier()
-        t = time.perf_counter()
-        if world == 1:
+    # end to end through the reference-facing call: host positions in, host energy + forces out (every rank passes the same
+    # positions and receives the whole result; sharded handles all-reduce inside the library call)
+    def e2e(include_energy):
+        times = []
+        forces_host = np.zeros_like(pos)
+        for i in range(args.steps + 3):
+            flush.zero_()
+            barrier()
+            t = time.perf_counter()
             forces_host[:] = 0.0
-            if i == 0:
-                k1 = runtime.CalcCoulForceKernel(device=local)
-                k1.initialize(box, force)
-            k1.execute(pos, box, forces_host, True, INCLUDE_ENERGY)
-        else:
-            ctx.evaluate(pos, True, INCLUDE_ENERGY)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t
-        if i >= 3:
-            e2e_times.append(dt)
-    clocks = sampler.stop(t_start, time.perf_counter()) if sampler else None     # timed loop + e2e loop, both under load
-    e2e_t = torch.tensor([float(np.mean(e2e_times))], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_s = float(e2e_t.item())
+            me.kernel.execute(pos, box, forces_host, True, include_energy)
+            dt = time.perf_counter() - t
+            if i >= 3:
+                times.append(dt)
+        tt = torch.tensor([float(np.mean(times))], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
 
+    e2e_s = e2e(INCLUDE_ENERGY)
+    clocks = sampler.stop(t_start, time.perf_counter()) if sampler else None     # timed loop + e2e loop, both under load
+    e2e_f_s = e2e(False)
+
+    alpha, kmax, nk = me.kernel.ewald_params()
     line = None
     if rank == 0:
-        alpha, kmax, nk = ctx.kernel.ewald_params()
-        st = ctx.kernel.stats()
-        pairs = st.pairs_in_cutoff if world == 1 else None
         value = 1e3 / ms_per_step
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32 (f64 energies/accumulation, int64 fixed-point forces)", "data": "synthetic",
                 "config": {"workload": workload, "atoms": n, "kmax": list(kmax), "kvectors": int(nk), "alpha": alpha,
-                           "flags": "includeForces=1 includeEnergy=0 (the per-MD-step call)",
-                           "l2": "384 MiB buffer written between timed steps (L2 flush); working set < L2",
-                           "parallelism": "k-vector rows + direct-space i-tiles sharded x%d, NCCL all-reduce of int64 forces" % world
-                           if world > 1 else "single GPU"},
-                "ns_per_day": ns_per_day(value),
-                "energy_and_forces": {"value": 1e3 / ms_ef, "unit": UNIT, "ms_per_step": ms_ef,
-                                      "note": "includeEnergy=1: FP64 pair energies and the FP32 (round-to-nearest) structure-factor kernel"},
+                           "flags": FLAGS_NOTE,
+                           "l2": "384 MiB buffer written between timed steps (L2 flush)"
+                                 + ("; working set < L2" if n < 100000 else "; phase tables (0.5 GB) stream from HBM"),
+                           "parallelism": "k-vector rows + direct-space i-clusters sharded x%d, one NCCL all-reduce of the int64 "
+                                          "reduction buffer inside the library's CUDA graph" % world if world > 1 else "single GPU"},
+                "value_forces_only": 1e3 / ms_f, "ms_per_step_forces_only": ms_f,
+                "forces_only_note": "includeForces=1 includeEnergy=0: the call OpenMM makes once per MD step (tcgen05 structure "
+                                    "factors, FP32 pair terms); ns_per_day is derived from it",
+                "ns_per_day": ns_per_day(1e3 / ms_f),
                 "e2e": {"value": 1.0 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 24 * n, "d2h_bytes_per_step": 24 * n + 40,
-                        "ns_per_day": ns_per_day(1.0 / e2e_s)},
+                        "forces_only": {"value": 1.0 / e2e_f_s, "ns_per_day": ns_per_day(1.0 / e2e_f_s)}},
                 "gpu_launches": int(launches_per_eval) * args.steps,
                 "clocks": clocks}
+
+    if world > 1:
+        # parity of the sharded evaluation against the same evaluation on ONE GPU (rank 0's), and the 256k-atom box
+        par = {}
+        if rank == 0:
+            single = Rank(torch, dist, force, box, pos, 0, 1, local)
+            single.step(INCLUDE_ENERGY)
+            f1, e1 = single.forces(), single.energies()
+            par = {"forces_rel_rms": float(np.sqrt(((f_sharded - f1) ** 2).sum() / (f1 ** 2).sum())),
+                   "energy_rel": float(abs(e_sharded[4] - e1[4]) / abs(e1[4])), "energy_sharded": float(e_sharded[4]), "energy_single": float(e1[4])}
+            single.kernel.close()
+        barrier()
+        c4 = None
+        if not args.no_c4:
+            pos4, box4, force4 = synthetic.config("c4")
+            r4 = Rank(torch, dist, force4, box4, pos4, rank, world, local, broadcast_comm_id(dist, rank))
+            ms4_f, ms4_ef = timed(r4, False, 10), timed(r4, True, 10)
+            r4.step(False)
+            f4 = r4.forces()
+            r4.kernel.close()
+            if rank == 0:
+                s4 = Rank(torch, dist, force4, box4, pos4, 0, 1, local)
+                one_f = one_ef = None
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+                for k, inc_e in enumerate((False, True)):
+                    for _ in range(3):
+                        s4.step(inc_e)
+                    ev[2 * k].record(s4.stream)
+                    for _ in range(5):
+                        s4.step(inc_e)
+                    ev[2 * k + 1].record(s4.stream)
+                torch.cuda.synchronize()
+                one_f, one_ef = ev[0].elapsed_time(ev[1]) / 5, ev[2].elapsed_time(ev[3]) / 5
+                s4.step(False)
+                g = s4.forces()
+                c4 = {"workload": WORKLOADS["c4"], "atoms": len(pos4), "n_gpus": world,
+                      "ms_per_step_forces_only": ms4_f, "ms_per_step": ms4_ef,
+                      "ms_per_step_forces_only_1gpu": one_f, "ms_per_step_1gpu": one_ef,
+                      "speedup_forces_only": one_f / ms4_f, "speedup": one_ef / ms4_ef,
+                      "parity_vs_single_forces_rel_rms": float(np.sqrt(((f4 - g) ** 2).sum() / (g ** 2).sum())),
+                      "note": "1-GPU figures measured in this run on rank 0's GPU (no L2 flush at this size: the tables exceed L2)"}
+                s4.kernel.close()
+            barrier()
+        if rank == 0:
+            line["parity_vs_single"] = par
+            line["c4"] = c4
+            line["comm"] = {"nranks": me.kernel.comm_size(), "backend": "NCCL (dlopen'ed by libcfx_b200.so), int64 sum all-reduce of %d bytes"
+                            % (8 * (3 * me.npad + 8))}
+
     if world == 1:
         # per-kernel durations (CUDA events on the launching stream) and the roofline of the dominant one
         tf_peak, _ = runtime.measure_fp32_peak(local, 5)
         tf32_peak = runtime.measure_tf32_peak(local)
-        kt = ctx.kernel.time_kernels(ctx.d_pos.data_ptr(), box, 10, True, INCLUDE_ENERGY)
-        kt_ef = ctx.kernel.time_kernels(ctx.d_pos.data_ptr(), box, 10, True, True)
-        ctx.evaluate_device(True, INCLUDE_ENERGY)
-        torch.cuda.synchronize()
-        pairs = ctx.kernel.stats().pairs_in_cutoff
+        kt = me.kernel.time_kernels(me.d_pos.data_ptr(), box, 10, True, INCLUDE_ENERGY)
+        kt_f = me.kernel.time_kernels(me.d_pos.data_ptr(), box, 10, True, False)
+        pairs = me.kernel.stats().pairs_in_cutoff
         fl = algorithmic_flops(n, nk, pairs, force.getNumFluxBonds() + force.getNumFluxAngles() + force.getNumFluxWaters(),
                                4 * force.getNumFluxBonds() + 9 * force.getNumFluxAngles() + 9 * force.getNumFluxWaters(),
                                force.getNumExceptions())
-        ex = executed_tensor_flops(n, kmax)
-        top = max(kt, key=kt.get)
-        total_kernel_ms = sum(kt.values())
-        achieved = fl.get(top, 0.0) / (kt[top] * 1e-3) / 1e12
         try:
-            traffic_db = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json"))) if args.workload == "c3" else {}
+            traffic_db = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json"))) if args.workload == "c3" else {}
         except (OSError, ValueError):
             traffic_db = {}
 
@@ -396,51 +476,68 @@ def run_ours(args, pos, box, force, workload):
             tr = traffic_db.get(name)
             return tr["dram_read_bytes"] + tr["dram_write_bytes"] if tr else None
 
-        kernels = []
-        for name in ("direct_pairs", "kspace_gather", "structure_factor"):
-            if name not in kt:
-                continue
-            tensor = name in ex
-            peak = tf32_peak if tensor else tf_peak
-            a = fl[name] / (kt[name] * 1e-3) / 1e12
-            row = {"kernel": name, "bound": "tensor" if tensor else "fp32", "ms": kt[name], "share_of_step": kt[name] / total_kernel_ms,
-                   "algorithmic_flop_per_launch": fl[name], "achieved": a, "peak": peak, "unit": "TFLOP/s", "frac": a / peak,
-                   "traffic": traffic_of(name)}
-            if tensor:
-                row["executed_tf32_flop_per_launch"] = ex[name]
-                row["executed_tflops"] = ex[name] / (kt[name] * 1e-3) / 1e12
-                row["executed_frac"] = row["executed_tflops"] / peak
-                row["fp32_equivalent_frac_of_fp32_peak"] = a / tf_peak
-            kernels.append(row)
-        line["roofline"] = {"bound": "fp32", "kernel": top, "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
-                            "frac": achieved / tf_peak, "traffic": traffic_of(top),
+        def kernel_rows(times, energy):
+            ex = executed_tensor_flops(n, kmax, energy)
+            total = sum(times.values())
+            rows = []
+            for name in ("direct_pairs", "kspace_gather", "structure_factor"):
+                if name not in times:
+                    continue
+                tensor = name in ex
+                peak = tf32_peak if tensor else tf_peak
+                a = fl[name] / (times[name] * 1e-3) / 1e12
+                row = {"kernel": name, "bound": "tensor" if tensor else "fp32", "ms": times[name], "share_of_step": times[name] / total,
+                       "algorithmic_flop_per_launch": fl[name], "achieved": a, "peak": peak, "unit": "TFLOP/s", "frac": a / peak,
+                       "traffic": traffic_of(name + ("_energy" if energy else ""))}
+                if tensor:
+                    row["executed_tf32_flop_per_launch"] = ex[name]
+                    row["executed_tflops"] = ex[name] / (times[name] * 1e-3) / 1e12
+                    row["executed_frac"] = row["executed_tflops"] / peak
+                    row["fp32_equivalent_frac_of_fp32_peak"] = a / tf_peak
+                rows.append(row)
+            return rows
+
+        rows = kernel_rows(kt, INCLUDE_ENERGY)
+        top = max(rows, key=lambda r: r["ms"])
+        line["roofline"] = {"bound": top["bound"], "kernel": top["kernel"], "achieved": top["achieved"], "peak": top["peak"],
+                            "unit": "TFLOP/s", "frac": top["frac"], "traffic": top["traffic"],
                             "traffic_note": "DRAM bytes per launch of this kernel from the committed ncu capture (profiles/); far below "
-                                            "the algorithmic FLOP x 4 B: the kernel is instruction-issue / SFU bound, not HBM bound",
-                            "peak_source": "FP32 FMA microbenchmark run in this process (cfx_measure_fp32_peak); "
-                                           "theoretical 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4. TF32 peak: tcgen05 kind::tf32 "
-                                           "128x128x8 microbenchmark run in this process (cfx_measure_tf32_peak)",
-                            "kernel_ms": kt[top], "kernel_share_of_step": kt[top] / total_kernel_ms,
-                            "algorithmic_flop_per_launch": fl.get(top, 0.0),
-                            "kernels": kernels,
+                                            "the algorithmic FLOP x 4 B: the kernel is instruction-issue bound, not HBM bound",
+                            "peak_source": "NOT in MEASURED_PEAKS.json (it holds HBM and bf16 figures only): FP32 FMA microbenchmark run "
+                                           "in this process (cfx_measure_fp32_peak; theoretical 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4) "
+                                           "and tcgen05 kind::tf32 128x128x8 microbenchmark run in this process (cfx_measure_tf32_peak)",
+                            "kernel_ms": top["ms"], "kernel_share_of_step": top["share_of_step"],
+                            "algorithmic_flop_per_launch": top["algorithmic_flop_per_launch"],
+                            "kernels": rows,
+                            "kernels_forces_only": kernel_rows(kt_f, False),
                             "whole_step": {"achieved": fl["total"] / (ms_per_step * 1e-3) / 1e12,
                                            "frac": fl["total"] / (ms_per_step * 1e-3) / 1e12 / tf_peak,
+                                           "frac_forces_only": fl["total"] / (ms_f * 1e-3) / 1e12 / tf_peak,
                                            "algorithmic_flop": fl["total"],
                                            "note": "algorithmic FP32-equivalent FLOP of the whole evaluation / step time, against the "
-                                                   "FP32 FMA peak; the reciprocal-space part runs on tensor cores"}}
+                                                   "FP32 FMA peak; the reciprocal-space gather (and, forces only, the structure factors) run on tensor cores"}}
         line["kernels_ms"] = {k: round(v, 5) for k, v in kt.items()}
-        line["energy_and_forces"]["kernels_ms"] = {k: round(v, 5) for k, v in kt_ef.items()}
+        line["kernels_ms_forces_only"] = {k: round(v, 5) for k, v in kt_f.items()}
         line["peaks"] = {"fp32_fma_tflops": tf_peak, "tf32_tcgen05_tflops": tf32_peak}
         line["config"]["pairs_in_cutoff"] = int(pairs)
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(pos, box, force)
         if args.md_steps > 0:
+            me.kernel.close()
             line["md_nve"] = md_leg(args)
         # second reported baseline of north_star: the plugin's EXISTING CUDA kernels on this GPU
         line["existing_cuda_baseline"] = existing_cuda_baseline(args.workload, ms_per_step)
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+        if rank == 0 and nccl_log:
+            import glob
+            for path in sorted(glob.glob(nccl_log + ".*.log")):
+                with open(path) as fh:
+                    sys.stderr.write(fh.read())
+                os.unlink(path)
 
 
 def main():
@@ -452,6 +549,7 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--md-steps", type=int, default=2000, help="length of the NVE MD leg (0 = skip)")
+    ap.add_argument("--no-c4", action="store_true", help="N > 1: skip the 262k-atom strong-scaling block")
     args = ap.parse_args()
     from openmm_chargeflux_b200 import synthetic
     pos, box, force = synthetic.config(args.workload)

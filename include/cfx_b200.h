@@ -74,6 +74,10 @@ typedef struct cfx_system_desc {
  * into it directly, and unregisters it when a different array arrives or at cfx_destroy. Without the flag (default)
  * every call stages through the handle's own pinned buffers and caller memory is only touched during the call. */
 #define CFX_OPT_PIN_CALLER_BUFFERS 1
+/* SKIP_DISCARDED_ENERGY: with include_energy == 0 the reference still returns self + direct + exclusion energy, a value
+ * OpenMM discards; by default it is reproduced (FP32 pair terms). With this flag such calls
+ * return 0 for the direct component and skip its arithmetic. */
+#define CFX_OPT_SKIP_DISCARDED_ENERGY 2
 
 /* Execution options (all optional; pass NULL for defaults). */
 typedef struct cfx_options {
@@ -138,6 +142,36 @@ int  cfx_execute_device(cfx_handle* h, const double* d_positions, const double* 
  * plus one sum all-reduce of d_reduce (NCCL over NVLink); integer sums make the result independent of the order. */
 int  cfx_execute_shard(cfx_handle* h, const double* d_positions, const double* box,
                        int include_forces, int include_energy, long long* d_reduce, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Multi-GPU. The reference has none (its CUDA platform binds contexts[0] only,
+ * platforms/cuda/src/CudaCoulKernelFactory.cpp:40). An evaluation is split over the ranks of an NCCL communicator
+ * -- each rank owns a block of k-vector rows and a slab of direct-space i-clusters -- and completed by one sum
+ * all-reduce of the int64 fixed-point reduction buffer over NVLink (integer sums: any reduction order gives the same bits).
+ * NCCL is dlopen'ed (libnccl.so.2) on first use.
+ *
+ * One process (or thread) per GPU: every rank creates its handle with (shard_rank, shard_count), rank 0 draws an id
+ * with cfx_comm_get_unique_id and the launcher (MPI, torchrun, ...) hands it to every rank's cfx_comm_init, a collective
+ * call. After that cfx_execute() works on the sharded handle -- every rank passes the same positions and receives the
+ * whole energy and forces -- and cfx_execute_sharded() is cfx_execute_shard() followed by the in-place all-reduce of
+ * d_reduce on `stream`, both replayed as one CUDA graph. */
+#define CFX_COMM_ID_BYTES 128
+int  cfx_comm_get_unique_id(void* id /*[CFX_COMM_ID_BYTES]*/);
+int  cfx_comm_init(cfx_handle* h, const void* id /*[CFX_COMM_ID_BYTES]*/);
+int  cfx_comm_size(const cfx_handle* h);                  /* ranks of the handle's communicator, 0 = none */
+int  cfx_execute_sharded(cfx_handle* h, const double* d_positions, const double* box,
+                         int include_forces, int include_energy, long long* d_reduce, void* stream);
+
+/* One process, several GPUs -- what a plugin inside a single OpenMM process can use (the reference's stub of it:
+ * CudaCoulKernels.cpp:477-481). The multi-handle owns one sharded handle and one communicator rank per device;
+ * cfx_multi_execute has the contract of cfx_execute. cfx_multi_handle(m, i) exposes rank i's handle to the getters. */
+typedef struct cfx_multi cfx_multi;
+int  cfx_multi_create(const cfx_system_desc* desc, const int32_t* devices, int32_t num_devices, cfx_multi** out);
+void cfx_multi_destroy(cfx_multi* m);
+int  cfx_multi_num_devices(const cfx_multi* m);
+cfx_handle* cfx_multi_handle(cfx_multi* m, int32_t index);
+int  cfx_multi_execute(cfx_multi* m, const double* positions, const double* box,
+                       int include_forces, int include_energy, double* energy, double* forces);
 
 int  cfx_padded_num_particles(const cfx_handle* h);
 int  cfx_get_ewald_params(const cfx_handle* h, cfx_ewald_params* out);

@@ -8,6 +8,8 @@ import ctypes as C
 
 CFX_OK, CFX_ERR_ARGUMENT, CFX_ERR_CUDA, CFX_ERR_STATE = 0, 1, 2, 3
 OPT_PIN_CALLER_BUFFERS = 1
+OPT_SKIP_DISCARDED_ENERGY = 2
+COMM_ID_BYTES = 128
 E_SELF, E_RECIP, E_DIRECT, E_EXCL, E_TOTAL, E_COUNT = 0, 1, 2, 3, 4, 5
 ONE_4PI_EPS0 = 138.935456
 
@@ -45,6 +47,8 @@ class Stats(C.Structure):
 # every symbol include/cfx_b200.h declares (tests check the built library exports all of them)
 EXPORTED_SYMBOLS = [
     "cfx_last_error", "cfx_device_count", "cfx_create", "cfx_destroy", "cfx_update_parameters", "cfx_execute", "cfx_execute_device", "cfx_execute_shard",
+    "cfx_comm_get_unique_id", "cfx_comm_init", "cfx_comm_size", "cfx_execute_sharded",
+    "cfx_multi_create", "cfx_multi_destroy", "cfx_multi_num_devices", "cfx_multi_handle", "cfx_multi_execute",
     "cfx_padded_num_particles", "cfx_get_ewald_params", "cfx_get_stats", "cfx_get_charges", "cfx_get_dedq",
     "cfx_num_jacobian_rows", "cfx_get_jacobian", "cfx_get_neighbor_pairs", "cfx_get_exclusions",
     "cfx_time_device", "cfx_time_kernels", "cfx_measure_fp32_peak", "cfx_measure_tf32_peak",

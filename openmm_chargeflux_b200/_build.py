@@ -18,7 +18,8 @@ REF = os.environ.get("CFX_REFERENCE_DIR", "/root/reference")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared",
               # keep the statically linked CUDA runtime private: plugin loaders dlopen with RTLD_GLOBAL
-              "-Xlinker", "--exclude-libs=ALL"]
+              "-Xlinker", "--exclude-libs=ALL",
+              "-ldl"]                                   # NCCL is dlopen'ed (comm.cu): no link-time dependency
 if os.environ.get("CFX_PTXAS_V"):
     NVCC_FLAGS += ["-Xptxas", "-v"]
 
@@ -32,7 +33,7 @@ def _newer(target, sources):
 
 def build_cuda(force=False, verbose=False):
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    sources = [os.path.join(CSRC, f) for f in ("api.cu", "flux.cu", "kspace.cu", "kspace_tc.cu", "direct.cu", "md.cu")]
+    sources = [os.path.join(CSRC, f) for f in ("api.cu", "flux.cu", "kspace.cu", "kspace_tc.cu", "direct.cu", "md.cu", "comm.cu")]
     deps = sources + [os.path.join(CSRC, "cfx_internal.cuh"), os.path.join(CSRC, "ptx_sm100.cuh"), os.path.join(ROOT, "include", "cfx_b200.h")]
     if not force and not _newer(LIB, deps):
         return LIB

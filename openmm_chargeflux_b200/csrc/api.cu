@@ -143,7 +143,7 @@ void enqueueEvaluation(State& st, const double* dPos, bool includeForces, bool i
         CFX_CUDA(cudaMemsetAsync(st.pairCounters, 0, sizeof(unsigned long long)*4, s));
         // reference quirks mirrored: reciprocal energy only with includeEnergy; direct,
         // self and exclusion energies always; pair/recip forces and dE/dq only with includeForces
-        const int emode = includeEnergy ? 2 : (skipDiscardedEnergy ? 0 : 1);
+        const int emode = includeEnergy ? 2 : ((skipDiscardedEnergy || st.skipDiscardedEnergy) ? 0 : 1);
         if (st.overlapBranches && !st.timing) {
             // The reciprocal-space and direct-space branches only meet in the fixed-point accumulators
             // (atomics), so the direct branch is forked onto a side stream: its small kernels and its tail
@@ -242,6 +242,7 @@ int cfx_create(const cfx_system_desc* d, const cfx_options* opts, cfx_handle** o
     if (st.shardRank < 0 || st.shardRank >= st.shardCount) throw ArgError("shard_rank out of range");
     st.useGraph = opts ? (opts->use_graph != 0) : true;
     st.pinCallerBuffers = opts && (opts->flags & CFX_OPT_PIN_CALLER_BUFFERS);
+    st.skipDiscardedEnergy = opts && (opts->flags & CFX_OPT_SKIP_DISCARDED_ENERGY);
     if (d->use_pbc == 0 && st.shardCount != 1)
         throw ArgError("sharded handles need a periodic system: the non-periodic all-pairs branch is not partitioned");
     st.N = N;
@@ -377,6 +378,7 @@ void cfx_destroy(cfx_handle* h) {
     cudaSetDevice(st.device);
     if (st.stream) cudaStreamSynchronize(st.stream);
     dropGraphs(st);
+    commDestroy(st);
     if (st.posReg.registered) { cudaHostUnregister(const_cast<void*>(st.posReg.ptr)); cudaGetLastError(); }
     if (st.forceReg.registered) { cudaHostUnregister(const_cast<void*>(st.forceReg.ptr)); cudaGetLastError(); }
     if (st.devGraph) cudaGraphExecDestroy(st.devGraph);
@@ -402,7 +404,10 @@ int cfx_execute(cfx_handle* h, const double* positions, const double* box, int i
     CFX_TRY
     if (!h) throw ArgError("null handle");
     State& st = h->st;
-    if (st.shardCount != 1) throw ArgError("cfx_execute evaluates whole systems; sharded handles use cfx_execute_device");
+    const bool sharded = st.shardCount != 1;
+    if (sharded && !st.comm)
+        throw ArgError("cfx_execute on a sharded handle needs a communicator (cfx_comm_init); without one use cfx_execute_shard "
+                       "and reduce the buffers yourself");
     if (st.N == 0) {
         if (energy) for (int k = 0; k < CFX_E_COUNT; k++) energy[k] = 0.0;
         return CFX_OK;
@@ -423,9 +428,23 @@ int cfx_execute(cfx_handle* h, const double* positions, const double* box, int i
     st.launches = 0;
     auto enqueueAll = [&]() {
         CFX_CUDA(cudaMemcpyAsync(st.pos, regP ? positions : st.hPos, vecBytes, cudaMemcpyHostToDevice, s));
-        CFX_CUDA(cudaMemsetAsync(st.forceFixed, 0, sizeof(long long)*3*st.Npad, s));
-        enqueueEvaluation(st, st.pos, incF, incE, st.forceFixed, s, false);
-        launchFinalize(st, st.forceFixed, s);
+        if (!sharded) {
+            CFX_CUDA(cudaMemsetAsync(st.forceFixed, 0, sizeof(long long)*3*st.Npad, s));
+            enqueueEvaluation(st, st.pos, incF, incE, st.forceFixed, s, false);
+            launchFinalize(st, st.forceFixed, st.energyFixed, s);
+        }
+        else {
+            // this rank's shard into the reduction buffer (forces 2^32, energies 2^24 appended), one sum all-reduce over
+            // the communicator, then every rank converts the whole result
+            long long* acc = st.reduceBuf;
+            const size_t count = 3*(size_t) st.Npad + 8;
+            CFX_CUDA(cudaMemsetAsync(acc, 0, sizeof(long long)*count, s));
+            enqueueEvaluation(st, st.pos, incF, incE, acc, s, false);
+            appendEnergyFixedKernel<<<1, 32, 0, s>>>(st.energyFixed, acc + 3*(size_t) st.Npad);
+            CFX_LAUNCH_CHECK(); st.launches++;
+            commAllReduce(st, acc, count, s);
+            launchFinalize(st, acc, acc + 3*(size_t) st.Npad, s);
+        }
         if (regF) {
             addToMappedKernel<<<(3*st.N + 255)/256, 256, 0, s>>>(3*st.N, st.forceOut, static_cast<double*>(st.forceReg.dev));
             CFX_LAUNCH_CHECK(); st.launches++;
@@ -469,7 +488,8 @@ int cfx_execute(cfx_handle* h, const double* positions, const double* box, int i
 // shared body of cfx_execute_device and cfx_execute_shard (shard: d_force_fixed is the [3*Npad + 8] reduction buffer,
 // zeroed here, energies appended as 2^24 fixed point)
 static int executeDeviceImpl(cfx_handle* h, const double* d_positions, const double* box, int include_forces, int include_energy,
-                             long long* d_force_fixed, long long* d_dedq_fixed, double* d_energy, void* stream, bool shard) {
+                             long long* d_force_fixed, long long* d_dedq_fixed, double* d_energy, void* stream, bool shard,
+                             bool reduce = false) {
     CFX_TRY
     if (!h) throw ArgError("null handle");
     State& st = h->st;
@@ -496,13 +516,15 @@ static int executeDeviceImpl(cfx_handle* h, const double* d_positions, const dou
             appendEnergyFixedKernel<<<1, 32, 0, s>>>(st.energyFixed, d_force_fixed + 3*(size_t) st.Npad);
             CFX_LAUNCH_CHECK(); st.launches++;
         }
+        if (reduce) commAllReduce(st, d_force_fixed, 3*(size_t) st.Npad + 8, s);
     };
     st.launches = 0;
     // the legacy default stream cannot be captured: plain launches there
     const bool capturable = s != nullptr && s != cudaStreamLegacy;
     if (st.useGraph && capturable) {
         State::DeviceGraphKey key{d_positions, d_force_fixed, d_dedq_fixed, d_energy,
-                                  (include_forces ? 1 : 0) | (include_energy ? 2 : 0) | (shard ? 4 : 0), {st.box.L[0], st.box.L[1], st.box.L[2]}};
+                                  (include_forces ? 1 : 0) | (include_energy ? 2 : 0) | (shard ? 4 : 0) | (reduce ? 8 : 0),
+                                  {st.box.L[0], st.box.L[1], st.box.L[2]}};
         const State::DeviceGraphKey& old = st.devKey;
         const bool same = old.pos == key.pos && old.force == key.force && old.dedq == key.dedq && old.energy == key.energy &&
                           old.flags == key.flags && old.L[0] == key.L[0] && old.L[1] == key.L[1] && old.L[2] == key.L[2];
@@ -537,6 +559,12 @@ int cfx_execute_device(cfx_handle* h, const double* d_positions, const double* b
 int cfx_execute_shard(cfx_handle* h, const double* d_positions, const double* box, int include_forces, int include_energy,
                       long long* d_reduce, void* stream) {
     return executeDeviceImpl(h, d_positions, box, include_forces, include_energy, d_reduce, nullptr, nullptr, stream, true);
+}
+
+int cfx_execute_sharded(cfx_handle* h, const double* d_positions, const double* box, int include_forces, int include_energy,
+                        long long* d_reduce, void* stream) {
+    if (h && !h->st.comm) { g_lastError = "cfx_execute_sharded needs a communicator (cfx_comm_init)"; return CFX_ERR_STATE; }
+    return executeDeviceImpl(h, d_positions, box, include_forces, include_energy, d_reduce, nullptr, nullptr, stream, true, true);
 }
 
 int cfx_padded_num_particles(const cfx_handle* h) { return h ? h->st.Npad : 0; }

@@ -123,6 +123,9 @@ struct State {
     double cutoff = 0, tol = 0, alpha = 0;
     int device = 0, shardRank = 0, shardCount = 1;
     bool useGraph = true;
+    void* comm = nullptr;               // ncclComm_t of a sharded handle (comm.cu), owned
+    long long* reduceBuf = nullptr;     // [3*Npad + 8] reduction buffer of the host-buffer sharded path
+    bool skipDiscardedEnergy = false;   // cfx_options.flags & CFX_OPT_SKIP_DISCARDED_ENERGY
     bool pinCallerBuffers = false;      // cfx_options.flags & CFX_OPT_PIN_CALLER_BUFFERS
     KSpacePlan ks;
     CellPlan cells;
@@ -207,7 +210,9 @@ void launchFluxAssembly(State& st, const double* dPos, cudaStream_t s);         
 void launchChainRule(State& st, long long* dForce, const long long* dDedq, cudaStream_t s);   // piece (5)
 void launchExclusionCorrection(State& st, const double* dPos, bool forces, long long* dForce, long long* dDedq, cudaStream_t s);
 void launchNoCutoff(State& st, const double* dPos, bool forces, bool energy, long long* dForce, long long* dDedq, cudaStream_t s);
-void launchFinalize(State& st, const long long* dForce, cudaStream_t s);
+void launchFinalize(State& st, const long long* dForce, const long long* dEnergyFixed, cudaStream_t s);
+void commAllReduce(State& st, long long* buf, size_t count, cudaStream_t s);           // comm.cu: in-place int64 sum over the ranks
+void commDestroy(State& st);
 void planKSpace(State& st);
 void launchKSpace(State& st, const double* dPos, bool forces, bool energy, long long* dForce, long long* dDedq, cudaStream_t s);  // piece (3)
 bool structureTensorEligible(const State& st);                                          // kspace_tc.cu

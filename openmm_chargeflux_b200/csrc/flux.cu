@@ -335,8 +335,8 @@ void launchNoCutoff(State& st, const double* dPos, bool forces, bool energy, lon
     }
 }
 
-void launchFinalize(State& st, const long long* dForce, cudaStream_t s) {
-    finalizeKernel<<<(st.N + 255)/256, 256, 0, s>>>(st.N, st.Npad, dForce, st.energyFixed, st.forceOut, st.energyOut);
+void launchFinalize(State& st, const long long* dForce, const long long* dEnergyFixed, cudaStream_t s) {
+    finalizeKernel<<<(st.N + 255)/256, 256, 0, s>>>(st.N, st.Npad, dForce, dEnergyFixed, st.forceOut, st.energyOut);
     CFX_LAUNCH_CHECK(); st.launches++;
     mark(st, "finalize", s);
 }

@@ -42,6 +42,17 @@ def load_library():
     lib.cfx_execute_device.argtypes = [C.c_void_p, C.c_void_p, _abi.c_double_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p]
     lib.cfx_execute_shard.argtypes = [C.c_void_p, C.c_void_p, _abi.c_double_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.cfx_execute_sharded.argtypes = [C.c_void_p, C.c_void_p, _abi.c_double_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.cfx_comm_get_unique_id.argtypes = [C.c_char_p]
+    lib.cfx_comm_init.argtypes = [C.c_void_p, C.c_char_p]
+    lib.cfx_comm_size.argtypes = [C.c_void_p]
+    lib.cfx_multi_create.argtypes = [C.POINTER(_abi.SystemDesc), _abi.c_int32_p, C.c_int32, C.POINTER(C.c_void_p)]
+    lib.cfx_multi_destroy.argtypes = [C.c_void_p]
+    lib.cfx_multi_destroy.restype = None
+    lib.cfx_multi_num_devices.argtypes = [C.c_void_p]
+    lib.cfx_multi_handle.argtypes = [C.c_void_p, C.c_int32]
+    lib.cfx_multi_handle.restype = C.c_void_p
+    lib.cfx_multi_execute.argtypes = [C.c_void_p, _abi.c_double_p, _abi.c_double_p, C.c_int, C.c_int, _abi.c_double_p, _abi.c_double_p]
     lib.cfx_padded_num_particles.argtypes = [C.c_void_p]
     lib.cfx_get_ewald_params.argtypes = [C.c_void_p, C.POINTER(_abi.EwaldParams)]
     lib.cfx_get_stats.argtypes = [C.c_void_p, C.POINTER(_abi.Stats)]
@@ -77,13 +88,15 @@ class CalcCoulForceKernel:
     def Name():
         return "CalcCoulForce"      # CoulKernels.h:17-19
 
-    def __init__(self, device=-1, shard_rank=0, shard_count=1, use_graph=True, pin_caller_buffers=False):
+    def __init__(self, device=-1, shard_rank=0, shard_count=1, use_graph=True, pin_caller_buffers=False,
+                 skip_discarded_energy=False):
         """pin_caller_buffers: the caller keeps the positions / forces arrays it passes to execute() alive until it passes
         different ones or closes the kernel; they are then page-locked in place (CFX_OPT_PIN_CALLER_BUFFERS)."""
         self._lib = load_library()
         self._opts = _abi.Options(device=device, shard_rank=shard_rank, shard_count=shard_count,
                                   use_graph=1 if use_graph else 0,
-                                  flags=_abi.OPT_PIN_CALLER_BUFFERS if pin_caller_buffers else 0)
+                                  flags=(_abi.OPT_PIN_CALLER_BUFFERS if pin_caller_buffers else 0)
+                                  | (_abi.OPT_SKIP_DISCARDED_ENERGY if skip_discarded_energy else 0))
         self._h = None
         self.num_particles = 0
 
@@ -139,6 +152,19 @@ class CalcCoulForceKernel:
         """Sharded step: zero + fill the int64 reduction buffer [3*Npad + 8] (forces 2^32, energies 2^24); asynchronous."""
         self._check(self._lib.cfx_execute_shard(self._h, d_positions, _dp(_box9(box)), int(includeForces), int(includeEnergy),
                                                 d_reduce, stream or None))
+
+    # -- multi-GPU: one process per GPU, NCCL communicator owned by the handle (include/cfx_b200.h) ------------
+    def comm_init(self, unique_id):
+        """Collective over the shard_count ranks: `unique_id` is the 128-byte id rank 0 drew with comm_unique_id()."""
+        self._check(self._lib.cfx_comm_init(self._h, bytes(unique_id)))
+
+    def comm_size(self):
+        return self._lib.cfx_comm_size(self._h)
+
+    def execute_sharded(self, d_positions, box, d_reduce, stream=0, includeForces=True, includeEnergy=True):
+        """execute_shard + in-place sum all-reduce of d_reduce over the communicator, one CUDA graph; asynchronous."""
+        self._check(self._lib.cfx_execute_sharded(self._h, d_positions, _dp(_box9(box)), int(includeForces), int(includeEnergy),
+                                                  d_reduce, stream or None))
 
     # -- derived parameters, counters, parity getters --------------------------------------------
     def padded_num_particles(self):
@@ -204,6 +230,52 @@ class CalcCoulForceKernel:
         if self._h is not None:
             self._lib.cfx_destroy(self._h)
             self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def comm_unique_id():
+    """128-byte NCCL id for comm_init (rank 0 draws it, the launcher broadcasts it)."""
+    lib = load_library()
+    buf = C.create_string_buffer(_abi.COMM_ID_BYTES)
+    if lib.cfx_comm_get_unique_id(buf) != 0:
+        raise CfxError(lib.cfx_last_error().decode())
+    return buf.raw
+
+
+class MultiGpuCoulKernel:
+    """One process, several GPUs (cfx_multi_*): the kernel a plugin inside a single OpenMM process would hold.
+    ``execute`` has the contract of CalcCoulForceKernel.execute."""
+
+    def __init__(self, default_box, force, devices):
+        self._lib = load_library()
+        desc, keep = force.to_desc(_box9(default_box).reshape(3, 3))
+        devs = np.asarray(devices, dtype=np.int32)
+        h = C.c_void_p()
+        if self._lib.cfx_multi_create(C.byref(desc), devs.ctypes.data_as(_abi.c_int32_p), len(devs), C.byref(h)) != 0:
+            raise CfxError(self._lib.cfx_last_error().decode())
+        self._m = h
+        self.num_particles = force.getNumParticles()
+        del keep
+
+    def execute(self, positions, box, forces=None, includeForces=True, includeEnergy=True, components=None):
+        pos = np.ascontiguousarray(positions, dtype=np.float64).reshape(-1)
+        e5 = np.zeros(_abi.E_COUNT)
+        fptr = _dp(forces) if forces is not None else None
+        if self._lib.cfx_multi_execute(self._m, _dp(pos), _dp(_box9(box)), int(includeForces), int(includeEnergy), _dp(e5), fptr) != 0:
+            raise CfxError(self._lib.cfx_last_error().decode())
+        if components is not None:
+            components[:] = e5
+        return float(e5[_abi.E_TOTAL])
+
+    def close(self):
+        if self._m is not None:
+            self._lib.cfx_multi_destroy(self._m)
+            self._m = None
 
     def __del__(self):
         try:

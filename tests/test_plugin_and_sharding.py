@@ -178,3 +178,45 @@ def test_execute_shard_fills_the_reduction_buffer_like_execute_device(flags, bui
     assert abs(es[4] - e) <= (1e-8 if flags[1] else 1e-6) * max(abs(e), 1e-3 * np.abs(comps[:4]).max())
     assert abs(es[:4].sum() - es[4]) <= 1e-6
     assert rel_rms(fs, f) <= 2e-6
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Multi-GPU inside the C ABI (comm.cu): single-process multi-device handle, NCCL owned by the library.
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("ndev", [1, 2])
+def test_multi_device_handle_matches_the_single_gpu_evaluation(ndev, build_native):
+    """cfx_multi_create(devices): one sharded handle + one NCCL rank per device in ONE process; cfx_multi_execute has
+    the contract of cfx_execute (host positions in, energy + forces added to the caller's array out)."""
+    import torch
+    from openmm_chargeflux_b200 import runtime
+    if torch.cuda.device_count() < ndev:
+        pytest.skip("needs %d GPUs" % ndev)
+    pos, box, force = synthetic.config("c2")
+    whole = runtime.CoulContext(force, box)
+    multi = runtime.MultiGpuCoulKernel(box, force, list(range(ndev)))
+    for flags in ((True, True), (True, False)):
+        e, f, comps = whole.evaluate(pos, *flags)
+        fm = np.full_like(pos, 0.5)
+        cm = np.zeros(_abi.E_COUNT)
+        em = multi.execute(pos, box, fm, *flags, components=cm)
+        assert abs(em - e) <= (1e-8 if flags[1] else 1e-6) * max(abs(e), 1e-3 * np.abs(comps[:4]).max())
+        assert rel_rms(fm - 0.5, f) <= 2e-6
+    multi.close()
+
+
+@pytest.mark.gpu
+def test_comm_entry_points_fail_cleanly_without_a_communicator(build_native):
+    import torch
+    from openmm_chargeflux_b200 import runtime
+    pos, box, force = synthetic.config("c2")
+    k = runtime.CalcCoulForceKernel(shard_rank=0, shard_count=2)
+    k.initialize(box, force)
+    assert k.comm_size() == 0
+    with pytest.raises(runtime.CfxError, match="communicator"):
+        k.execute(pos, box, np.zeros_like(pos))
+    d_pos = torch.tensor(pos.reshape(-1), device="cuda")
+    d_red = torch.zeros(3 * k.padded_num_particles() + 8, dtype=torch.int64, device="cuda")
+    with pytest.raises(runtime.CfxError, match="communicator"):
+        k.execute_sharded(d_pos.data_ptr(), box, d_red.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert len(runtime.comm_unique_id()) == 128
