@@ -136,6 +136,19 @@ int  cfx_execute_device(cfx_handle* h, const double* d_positions, const double* 
                         int include_forces, int include_energy,
                         long long* d_force_fixed, long long* d_dedq_fixed, double* d_energy, void* stream);
 
+/* Evaluation inside a CUDA-platform host (replaces platforms/cuda/src/CudaCoulKernels.cpp:523-660 and
+ * kernels/PBCForce.cu:817-825). d_posq: the platform's `real4 posq[padded_num_atoms]` (float4, or double4 when
+ * posq_is_double) in the PLATFORM's atom order; d_posq_correction: NULL, or the float4 array of low-order position bits
+ * a mixed-precision platform keeps beside a float4 posq; d_atom_index[slot] = user particle index
+ * (CudaContext::getAtomIndexArray). d_force_buffers: the platform's 64-bit fixed-point force buffer [3][padded_num_atoms]
+ * (value*2^32, PBCForce.cu:336-338), platform order, ADDED to. d_energy_buffer: NULL, or the platform's energy buffer
+ * (double when energy_is_double, else float): the total is ADDED to its element 0. Asynchronous on `stream`; the gather
+ * into user order, the evaluation and the scatter are replayed as one CUDA graph. */
+int  cfx_execute_platform(cfx_handle* h, const void* d_posq, int posq_is_double, const void* d_posq_correction,
+                          const int32_t* d_atom_index, int32_t padded_num_atoms, const double* box,
+                          int include_forces, int include_energy, unsigned long long* d_force_buffers,
+                          void* d_energy_buffer, int energy_is_double, void* stream);
+
 /* The same evaluation for a sharded (multi-GPU) step: d_reduce is this rank's reduction buffer, int64
  * [3*Npad + 8] = fixed-point forces (value*2^32) followed by the CFX_E_* energies as value*2^24 (3 spare slots).
  * The buffer is ZEROED and filled inside the call's CUDA graph, so one step of a sharded evaluation is this call

@@ -46,7 +46,7 @@ class Stats(C.Structure):
 
 # every symbol include/cfx_b200.h declares (tests check the built library exports all of them)
 EXPORTED_SYMBOLS = [
-    "cfx_last_error", "cfx_device_count", "cfx_create", "cfx_destroy", "cfx_update_parameters", "cfx_execute", "cfx_execute_device", "cfx_execute_shard",
+    "cfx_last_error", "cfx_device_count", "cfx_create", "cfx_destroy", "cfx_update_parameters", "cfx_execute", "cfx_execute_device", "cfx_execute_shard", "cfx_execute_platform",
     "cfx_comm_get_unique_id", "cfx_comm_init", "cfx_comm_size", "cfx_execute_sharded",
     "cfx_multi_create", "cfx_multi_destroy", "cfx_multi_num_devices", "cfx_multi_handle", "cfx_multi_execute",
     "cfx_padded_num_particles", "cfx_get_ewald_params", "cfx_get_stats", "cfx_get_charges", "cfx_get_dedq",

@@ -33,7 +33,7 @@ def _newer(target, sources):
 
 def build_cuda(force=False, verbose=False):
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    sources = [os.path.join(CSRC, f) for f in ("api.cu", "flux.cu", "kspace.cu", "kspace_tc.cu", "direct.cu", "md.cu", "comm.cu")]
+    sources = [os.path.join(CSRC, f) for f in ("api.cu", "flux.cu", "kspace.cu", "kspace_tc.cu", "direct.cu", "md.cu", "comm.cu", "platform.cu")]
     deps = sources + [os.path.join(CSRC, "cfx_internal.cuh"), os.path.join(CSRC, "ptx_sm100.cuh"), os.path.join(ROOT, "include", "cfx_b200.h")]
     if not force and not _newer(LIB, deps):
         return LIB
@@ -53,14 +53,15 @@ def build_plugin(force=False, verbose=False):
     if not os.path.isdir(api_inc) or not os.path.exists(os.path.join(api_out, "libOpenMMCoul.so")):
         return PLUGIN_LIB if os.path.exists(PLUGIN_LIB) else None
     src_dir = os.path.join(PKG, "plugin")
-    sources = [os.path.join(src_dir, f) for f in ("B200CoulKernels.cpp", "B200CoulKernelFactory.cpp")]
-    deps = sources + [os.path.join(src_dir, "B200CoulKernels.h"), os.path.join(src_dir, "B200CoulKernelFactory.h"),
-                      os.path.join(ROOT, "include", "cfx_b200.h")]
+    sources = [os.path.join(src_dir, f) for f in ("B200CoulKernels.cpp", "B200CudaCoulKernels.cpp", "B200CoulKernelFactory.cpp")]
+    deps = sources + [os.path.join(src_dir, "B200CoulKernels.h"), os.path.join(src_dir, "B200CudaCoulKernels.h"),
+                      os.path.join(src_dir, "B200CoulKernelFactory.h"), os.path.join(ROOT, "include", "cfx_b200.h")]
     if not force and not _newer(PLUGIN_LIB, deps):
         return PLUGIN_LIB
+    cuda_home = os.environ.get("CUDA_HOME", "/usr/local/cuda")
     cmd = ["g++", "-O2", "-fPIC", "-std=c++17", "-shared", "-I" + os.path.join(ROOT, "shim"), "-I" + api_inc,
-           "-I" + os.path.join(ROOT, "include"), "-o", PLUGIN_LIB] + sources + [
-           "-L" + api_out, "-lOpenMMCoul", "-lOpenMMShim", "-L" + PKG, "-lcfx_b200",
+           "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(cuda_home, "include"), "-o", PLUGIN_LIB] + sources + [
+           "-L" + api_out, "-lOpenMMCoul", "-lOpenMMCudaShim", "-lOpenMMShim", "-L" + PKG, "-lcfx_b200",
            "-Wl,-rpath,$ORIGIN/../../shim/_build", "-Wl,-rpath,$ORIGIN/.."]
     if verbose:
         print(" ".join(cmd))

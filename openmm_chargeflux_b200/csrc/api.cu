@@ -69,6 +69,7 @@ void freeCells(State& st) {
     cudaFree(st.cellOfAtom); cudaFree(st.cellCount); cudaFree(st.cellStart); cudaFree(st.cellFill);
     cudaFree(st.userLocal); cudaFree(st.sortedLocal); cudaFree(st.sortedMeta);
     cudaFree(st.pairCounters); cudaFree(st.filledUser); st.filledUser = nullptr;
+    cudaFree(st.wrapList); st.wrapList = nullptr;
     st.cellOfAtom = st.cellCount = st.cellStart = st.cellFill = nullptr;
     st.userLocal = st.sortedLocal = st.sortedMeta = nullptr; st.pairCounters = nullptr;
 }
@@ -78,6 +79,7 @@ void dropGraphs(State& st) {
     for (int k = 0; k < 4; k++)
         if (st.graphs[k]) { cudaGraphExecDestroy(st.graphs[k]); st.graphs[k] = nullptr; }
     if (st.devGraph) { cudaGraphExecDestroy(st.devGraph); st.devGraph = nullptr; }
+    if (st.platGraph) { cudaGraphExecDestroy(st.platGraph); st.platGraph = nullptr; }
 }
 
 __global__ void addFixedKernel(int n, const long long* __restrict__ src, long long* __restrict__ dst) {
@@ -338,6 +340,8 @@ int cfx_create(const cfx_system_desc* d, const cfx_options* opts, cfx_handle** o
     CFX_CUDA(cudaMemset(st.qf, 0, sizeof(float)*st.Npad));
     CFX_CUDA(cudaMalloc(&st.forceFixed, sizeof(long long)*3*st.Npad));
     CFX_CUDA(cudaMalloc(&st.dedqFixed, sizeof(long long)*st.Npad));
+    CFX_CUDA(cudaMalloc(&st.exclMaxR2, sizeof(unsigned int)*st.Npad));
+    CFX_CUDA(cudaMemset(st.exclMaxR2, 0, sizeof(unsigned int)*st.Npad));
     CFX_CUDA(cudaMalloc(&st.energyFixed, sizeof(long long)*8));
     CFX_CUDA(cudaMalloc(&st.forceOut, sizeof(double)*3*std::max(N, 1)));
     CFX_CUDA(cudaMalloc(&st.energyOut, sizeof(double)*CFX_E_COUNT));
@@ -386,7 +390,7 @@ void cfx_destroy(cfx_handle* h) {
     void* ptrs[] = {st.q0, st.lj, st.ljd, st.termIdx, st.termPar, st.qcsrPtr, st.qcsrSlot, st.qcsrCoef, st.rowDq, st.rowDx, st.exclPairs,
                     st.exclPtr, st.exclCols, st.pos, st.dqSlot, st.rowVal, st.q, st.qf, st.forceFixed, st.dedqFixed, st.energyFixed,
                     st.forceOut, st.energyOut, st.rowS, st.colX, st.colY, st.colZ4, st.sPart, st.gCoef, st.gRowInfo,
-                    st.ks_signedStart, st.pairBuffer, st.zSplit, st.coefT, st.gRowData, st.gGroupInfo, st.gtTrace};
+                    st.ks_signedStart, st.pairBuffer, st.exclMaxR2, st.zSplit, st.coefT, st.gRowData, st.gGroupInfo, st.gtTrace};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (st.hPos) cudaFreeHost(st.hPos);
     if (st.hForce) cudaFreeHost(st.hForce);

@@ -173,7 +173,9 @@ struct State {
     float4* userLocal = nullptr;        // [N] local xyz in own cell + q, user order (scratch of the cell build)
     float4* sortedLocal = nullptr;      // [N] atoms sorted by cell, z inside the cell: local xyz + q
     float4* sortedMeta = nullptr;       // [N] (sigma/2, 2 sqrt(eps), user index, packed cell coordinates)
+    int* wrapList = nullptr;            // clusters the fast pair kernel left to the generic one
     int* filledUser = nullptr;          // cell fill in arrival order (input of the rank pass)
+    unsigned int* exclMaxR2 = nullptr;  // [Npad] float bits: per atom, largest r2 to an excluded partner (this evaluation)
     unsigned long long* pairCounters = nullptr;   // [4]: pairs in cutoff, candidates, emitted, overflow
     int2* pairBuffer = nullptr; int64_t pairCapacity = 0;
     // pinned host staging
@@ -192,6 +194,11 @@ struct State {
     cudaGraphExec_t devGraph = nullptr;
     DeviceGraphKey devKey = {nullptr, nullptr, nullptr, nullptr, -1, {0, 0, 0}};
     int64_t devGraphLaunches = 0;
+    // cached graph of the CUDA-platform entry (cfx_execute_platform)
+    struct PlatformGraphKey { const void* posq; const void* corr; const void* index; void* force; void* energy; int padded; int flags; uint64_t planGen; };
+    cudaGraphExec_t platGraph = nullptr;
+    PlatformGraphKey platKey = {nullptr, nullptr, nullptr, nullptr, nullptr, 0, -1, 0};
+    int64_t platGraphLaunches = 0;
     bool evaluated = false;
     bool stagedPosCurrent = false;      // st.pos holds the positions of the last evaluation (host entry point only)
     uint64_t planGeneration = 0;        // bumped whenever box-dependent plans / buffers change (external graphs must re-capture)

@@ -23,8 +23,8 @@
 //               MUFU.EX2 (shared with the force's Gaussian term), 7 FFMA.
 //  exactness    the in-cutoff predicate of a pair whose FP32 r2 falls within 1e-5 of rc2 is re-evaluated in FP64 on the
 //               original coordinates with the reference's operation order, so the neighbour set is bit-exact.
-//  exclusions   the excluded-pair kernel (flux.cu), which runs first, leaves the largest r2 of any excluded pair in a
-//               device scalar; only pairs at or below that separation (bonded neighbours; also the self pair at
+//  exclusions   the excluded-pair kernel (flux.cu), which runs first, leaves for every atom the largest r2 to any of its
+//               excluded partners; only pairs of that atom at or below it (bonded neighbours; also the self pair at
 //               r2 = 0) take the rare branch that probes the per-atom exclusion CSR.
 //
 // FP32 pair arithmetic for forces and dE/dq, int64 fixed-point accumulation. Pair ENERGIES are evaluated in FP64:
@@ -176,11 +176,12 @@ struct PairParams {
     const float4* sortedLocal; const float4* sortedMeta;
     const int* cellStart;
     const int* exclPtr; const int* exclCols;
-    const unsigned int* exclMaxR2Bits;       // float bits of the largest r2 over the excluded pairs (exclusionKernel)
+    const unsigned int* exclMaxR2Bits;       // [N] per user atom: float bits of the largest r2 to an excluded partner (exclusionKernel)
     const double* pos; const double* q; const double2* ljd; double alphaD, dInvLx, dInvLy, dInvLz;
     long long* forceFixed; long long* dedqFixed; long long* energyFixed;
     unsigned long long* counters; int2* pairBuffer; unsigned long long pairCapacity;
     unsigned int* workCounter;               // dynamic work distribution: next (cluster, column share) item
+    int* wrapList;                           // clusters the fast kernel left to the generic one (counters[7] of them)
 };
 
 __device__ __forceinline__ int wrapNearest(int d, int nc) {
@@ -251,8 +252,11 @@ __global__ void __launch_bounds__(P_WARPS*32, FAST ? P_FAST_MINBLOCKS : 4) pairK
     const float alpha = p.alpha, alpha2 = p.alpha2, band = p.band;
     const float rcut2 = p.rc2*1.0001f;
     const float4 farAway = make_float4(1e4f, 1e4f, 1e4f, 0.f);
-    const unsigned int totalItems = (unsigned int) (p.groupHi - p.groupLo)*(unsigned int) p.jSplits;
-    if (!FAST && p.onlyMinImage && p.counters[7] == 0ull) return;     // the fast kernel skipped nothing
+    // The generic kernel behind a fast one only sees the clusters listed in wrapList (usually none: it exits at once);
+    // there are few of them, so each is dealt over 256 shares (one stencil column per warp) to keep its latency short.
+    const bool listed = !FAST && p.onlyMinImage;
+    const int nShares = listed ? 256 : p.jSplits;
+    const unsigned int totalItems = (listed ? (unsigned int) p.counters[7] : (unsigned int) (p.groupHi - p.groupLo))*(unsigned int) nShares;
 
     // persistent warps: work items (i-cluster, share of its stencil columns) are handed out by an atomic counter, so the
     // GPU stays full whatever the item count (no partial last wave)
@@ -261,8 +265,8 @@ __global__ void __launch_bounds__(P_WARPS*32, FAST ? P_FAST_MINBLOCKS : 4) pairK
         if (lane == 0) item = atomicAdd(p.workCounter, 1u);
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= totalItems) break;
-        const int g = p.groupLo + (int) (item/(unsigned int) p.jSplits);
-        const int share = (int) (item % (unsigned int) p.jSplits);
+        const int share = (int) (item % (unsigned int) nShares);
+        const int g = listed ? p.wrapList[item/(unsigned int) nShares] : p.groupLo + (int) (item/(unsigned int) nShares);
 
         const int i0 = g*P_ITILE;
         const int ni = min(P_ITILE, p.N - i0);
@@ -285,7 +289,7 @@ __global__ void __launch_bounds__(P_WARPS*32, FAST ? P_FAST_MINBLOCKS : 4) pairK
         // per-lane copies of the thresholds: lanes without an i atom (last cluster) never see a pair
         const float rc2i = validI ? p.rc2 : -1.f;
         // (floor 1e-8 nm^2: the self pair is r2 = 0 up to rounding when a small box folds the stencil onto itself)
-        const float r2close = validI ? fmaxf(__uint_as_float(*p.exclMaxR2Bits)*1.0001f, 1e-8f) : -1.f;
+        const float r2close = validI ? fmaxf(__uint_as_float(p.exclMaxR2Bits[ui])*1.0001f, 1e-8f) : -1.f;
         const bool anyLJi = __any_sync(0xffffffffu, validI && ljiy != 0.f);
 
         // bounding box of the i-cluster and its cell-offset range (warp reductions)
@@ -308,10 +312,9 @@ __global__ void __launch_bounds__(P_WARPS*32, FAST ? P_FAST_MINBLOCKS : 4) pairK
         const int loZ = ominz - 2, nZ = min(omaxz - ominz + 5, p.ncz);
         const bool wraps = (omaxx - ominx + 5 > p.ncx) || (omaxy - ominy + 5 > p.ncy) || (omaxz - ominz + 5 > p.ncz);
         if (FAST && wraps) {                            // left to the generic kernel launched behind this one
-            if (lane == 0 && share == 0) atomicAdd(p.counters + 7, 1ull);
+            if (lane == 0 && share == 0) p.wrapList[atomicAdd(p.counters + 7, 1ull)] = g;
             continue;
         }
-        if (!FAST && p.onlyMinImage && !wraps) continue;
         const bool minImage = FAST ? false : wraps;
 
         float2 fx2 = pk(0.f), fy2 = pk(0.f), fz2 = pk(0.f), dq2 = pk(0.f), enf2 = pk(0.f);     // two partial sums each
@@ -490,7 +493,7 @@ __global__ void __launch_bounds__(P_WARPS*32, FAST ? P_FAST_MINBLOCKS : 4) pairK
                 const int cyCur = cyw;
                 const bool mine = shareCtr == share;
                 if (++cyw == p.ncy) cyw = 0;
-                if (++shareCtr == p.jSplits) shareCtr = 0;
+                if (++shareCtr == nShares) shareCtr = 0;
                 if (!mine) continue;
                 const float shy = (loY + ay)*p.csy;
                 // z range of this column: the cells cut by the sphere of radius rc around the bounding box
@@ -621,12 +624,12 @@ void planCells(State& st) {
     CFX_CUDA(cudaMalloc(&st.sortedLocal, sizeof(float4)*st.Npad));
     CFX_CUDA(cudaMalloc(&st.sortedMeta, sizeof(float4)*st.Npad));
     CFX_CUDA(cudaMalloc(&st.filledUser, sizeof(int)*st.Npad));
+    CFX_CUDA(cudaMalloc(&st.wrapList, sizeof(int)*(st.Npad/P_ITILE + 1)));
     CFX_CUDA(cudaMalloc(&st.pairCounters, sizeof(unsigned long long)*8));
     CFX_CUDA(cudaMemset(st.pairCounters, 0, sizeof(unsigned long long)*8));
 }
 
-// pairCounters (8 x u64): [0] in-cutoff ordered pairs, [1] distance tests, [2] emitted pairs, [4] float bits of the largest
-// excluded-pair r2 (flux.cu), [5] / [6] work-item counters of the fast / generic pair kernel, [7] clusters the fast kernel
+// pairCounters (8 x u64): [0] in-cutoff ordered pairs, [1] distance tests, [2] emitted pairs, [5] / [6] work-item counters of the fast / generic pair kernel, [7] clusters the fast kernel
 // left to the generic one.
 void launchDirect(State& st, const double* dPos, bool forces, int emode, bool emitPairs, long long* dForce, long long* dDedq, cudaStream_t s) {
     if (!forces && emode == 0 && !emitPairs) return;
@@ -658,12 +661,13 @@ void launchDirect(State& st, const double* dPos, bool forces, int emode, bool em
     pp.dLx = st.box.L[0]; pp.dLy = st.box.L[1]; pp.dLz = st.box.L[2];
     pp.rc2d = st.cutoff*st.cutoff;
     pp.rc2 = (float) pp.rc2d; pp.alpha = (float) st.alpha; pp.alpha2 = (float) (st.alpha*st.alpha); pp.band = (float) (1e-5*pp.rc2d);
-    pp.exclMaxR2Bits = reinterpret_cast<const unsigned int*>(st.pairCounters + 4);
+    pp.exclMaxR2Bits = st.exclMaxR2;
     pp.sortedLocal = st.sortedLocal; pp.sortedMeta = st.sortedMeta;
     pp.cellStart = st.cellStart; pp.exclPtr = st.exclPtr; pp.exclCols = st.exclCols; pp.pos = dPos;
     pp.q = st.q; pp.ljd = st.ljd; pp.alphaD = st.alpha;
     pp.dInvLx = 1.0/st.box.L[0]; pp.dInvLy = 1.0/st.box.L[1]; pp.dInvLz = 1.0/st.box.L[2];
     pp.forceFixed = dForce; pp.dedqFixed = dDedq; pp.energyFixed = st.energyFixed;
+    pp.wrapList = st.wrapList;
     pp.counters = st.pairCounters; pp.pairBuffer = st.pairBuffer; pp.pairCapacity = (unsigned long long) st.pairCapacity;
     const int groups = pp.groupHi - pp.groupLo;
     if (groups <= 0) return;
@@ -685,8 +689,8 @@ void launchDirect(State& st, const double* dPos, bool forces, int emode, bool em
         else           dispatchPair<true, false>(pp, forces, emode, grid, s);
         CFX_LAUNCH_CHECK(); st.launches++;
     }
-    // every cluster (small boxes), or the few whose stencil wraps onto itself in a large box (it exits at once when
-    // the fast kernel skipped none)
+    // every cluster (small boxes), or the few whose stencil wraps onto itself in a large box -- a cluster stretched over
+    // a sparse region -- which the fast kernel listed (it exits at once when there are none)
     pp.onlyMinImage = fast ? 1 : 0;
     pp.workCounter = reinterpret_cast<unsigned int*>(st.pairCounters + 6);
     const int grid = std::min((items + P_WARPS - 1)/P_WARPS, 4*numSM);

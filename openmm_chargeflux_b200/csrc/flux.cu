@@ -153,9 +153,9 @@ __global__ void __launch_bounds__(256) chainRuleKernel(int P, int Npad, const in
 
 // One thread per unique excluded pair (i<j). Periodic: remove the reciprocal-space image of the pair
 // (erf term, no cutoff test, no LJ). Non-periodic: subtract the full Coulomb + LJ pair.
-// maxR2Bits (periodic): the largest squared separation of any excluded pair, as float bits rounded up -- the pair
-// kernel only probes the exclusion lists for pairs at or below it. With accumulate == false (ranks > 0 of a sharded
-// evaluation) that is all the kernel produces.
+// maxR2Bits (periodic): per atom, the largest squared separation to any of its excluded partners, as float bits rounded
+// up -- the pair kernel only probes the exclusion lists for pairs of that atom at or below it. With accumulate == false
+// (ranks > 0 of a sharded evaluation) that is all the kernel produces.
 __global__ void __launch_bounds__(128) exclusionKernel(int numExcl, int Npad, const int2* __restrict__ pairs,
         const double* __restrict__ pos, const double* __restrict__ q, const double2* __restrict__ lj,
         BoxD box, bool pbc, double alpha, bool forces, bool energy, bool accumulate,
@@ -203,10 +203,9 @@ __global__ void __launch_bounds__(128) exclusionKernel(int numExcl, int Npad, co
             atomicAddFixed(dedqFixed + j, -dqj);
         }
     }
-    if (maxR2Bits) {                                                 // non-negative floats order like their bit patterns
-        #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) r2up = fmaxf(r2up, __shfl_xor_sync(0xffffffffu, r2up, o));
-        if ((threadIdx.x & 31) == 0 && r2up > 0.f) atomicMax(maxR2Bits, __float_as_uint(r2up));
+    if (maxR2Bits && e < numExcl) {                                  // non-negative floats order like their bit patterns
+        atomicMax(maxR2Bits + pairs[e].x, __float_as_uint(r2up));
+        atomicMax(maxR2Bits + pairs[e].y, __float_as_uint(r2up));
     }
     if (!accumulate) return;                                         // (uniform over the grid)
     en = blockSum(en, scratch);
@@ -310,14 +309,14 @@ void launchChainRule(State& st, long long* dForce, const long long* dDedq, cudaS
     mark(st, "chain_rule", s);
 }
 
-// Periodic branch. Must run BEFORE launchDirect on the same stream: it leaves the largest excluded-pair r2 in
-// pairCounters[4] for the pair kernel (every rank of a sharded evaluation needs that; only rank 0 accumulates).
+// Periodic branch. Must run BEFORE launchDirect on the same stream: it leaves every atom's largest excluded-partner r2
+// in exclMaxR2 for the pair kernel (every rank of a sharded evaluation needs that; only rank 0 accumulates).
 void launchExclusionCorrection(State& st, const double* dPos, bool forces, long long* dForce, long long* dDedq, cudaStream_t s) {
-    CFX_CUDA(cudaMemsetAsync(st.pairCounters + 4, 0, sizeof(unsigned long long), s));
+    CFX_CUDA(cudaMemsetAsync(st.exclMaxR2, 0, sizeof(unsigned int)*st.Npad, s));
     if (st.numExcl == 0) return;
     exclusionKernel<<<(st.numExcl + 127)/128, 128, 0, s>>>(st.numExcl, st.Npad, st.exclPairs, dPos, st.q, st.ljd,
             boxOf(st), st.pbc, st.alpha, forces, true, st.shardRank == 0, dForce, dDedq, st.energyFixed,
-            reinterpret_cast<unsigned int*>(st.pairCounters + 4));
+            st.exclMaxR2);
     CFX_LAUNCH_CHECK(); st.launches++;
     mark(st, "exclusion_corr", s);
 }

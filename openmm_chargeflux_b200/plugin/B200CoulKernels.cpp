@@ -1,4 +1,5 @@
 #include "B200CoulKernels.h"
+#include "B200CudaCoulKernels.h"
 #include "CoulForce.h"
 #include "openmm/OpenMMException.h"
 #include "openmm/internal/ContextImpl.h"
@@ -22,39 +23,8 @@ B200CalcCoulForceKernel::~B200CalcCoulForceKernel() {
 
 void B200CalcCoulForceKernel::initialize(const System& system, const CoulForce& force) {
     numParticles = system.getNumParticles();
-    if (force.getNumParticles() != numParticles)
-        throw OpenMMException("CoulForce must have exactly as many particles as the System it belongs to.");
-    // Flatten the CoulForce storage through its public getters (openmmapi/src/CoulForce.cpp:28-136).
-    vector<double> charge(numParticles), sigma(numParticles), epsilon(numParticles);
-    for (int i = 0; i < numParticles; i++)
-        force.getParticleParameters(i, charge[i], sigma[i], epsilon[i]);
-    vector<int> excl(2*force.getNumExceptions());
-    for (int i = 0; i < force.getNumExceptions(); i++)
-        force.getExceptionParameters(i, excl[2*i], excl[2*i+1]);
-    vector<int> bondIdx(2*force.getNumFluxBonds()), angleIdx(3*force.getNumFluxAngles()), waterIdx(3*force.getNumFluxWaters());
-    vector<double> bondPar(2*force.getNumFluxBonds()), anglePar(2*force.getNumFluxAngles()), waterPar(5*force.getNumFluxWaters());
-    for (int i = 0; i < force.getNumFluxBonds(); i++)
-        force.getFluxBondParameters(i, bondIdx[2*i], bondIdx[2*i+1], bondPar[2*i], bondPar[2*i+1]);
-    for (int i = 0; i < force.getNumFluxAngles(); i++)
-        force.getFluxAngleParameters(i, angleIdx[3*i], angleIdx[3*i+1], angleIdx[3*i+2], anglePar[2*i], anglePar[2*i+1]);
-    for (int i = 0; i < force.getNumFluxWaters(); i++)
-        force.getFluxWaterParameters(i, waterIdx[3*i], waterIdx[3*i+1], waterIdx[3*i+2], waterPar[5*i], waterPar[5*i+1],
-                                     waterPar[5*i+2], waterPar[5*i+3], waterPar[5*i+4]);
-    cfx_system_desc d;
-    d.num_particles = numParticles;
-    d.charge = charge.data(); d.sigma = sigma.data(); d.epsilon = epsilon.data();
-    d.num_exceptions = force.getNumExceptions(); d.exception_pairs = excl.data();
-    d.num_flux_bonds = force.getNumFluxBonds(); d.flux_bond_idx = bondIdx.data(); d.flux_bond_params = bondPar.data();
-    d.num_flux_angles = force.getNumFluxAngles(); d.flux_angle_idx = angleIdx.data(); d.flux_angle_params = anglePar.data();
-    d.num_flux_waters = force.getNumFluxWaters(); d.flux_water_idx = waterIdx.data(); d.flux_water_params = waterPar.data();
-    d.cutoff = force.getCutoffDistance();
-    d.ewald_tol = force.getEwaldErrorTolerance();
-    d.use_pbc = force.usesPeriodicBoundaryConditions() ? 1 : 0;
-    Vec3 box[3];
-    system.getDefaultPeriodicBoxVectors(box[0], box[1], box[2]);
-    for (int a = 0; a < 3; a++)
-        for (int c = 0; c < 3; c++)
-            d.default_box[3*a+c] = box[a][c];
+    B200CoulDescriptor descriptor(system, force);
+    cfx_system_desc& d = descriptor.desc;
     // The platform's position and force vectors live as long as the Context and are handed to every execute(): let the
     // library page-lock them in place instead of staging (include/cfx_b200.h, CFX_OPT_PIN_CALLER_BUFFERS).
     cfx_options opts;

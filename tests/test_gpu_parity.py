@@ -247,3 +247,20 @@ def test_pinned_caller_buffers_give_the_staged_result(build_native):
     f2 = np.zeros_like(pos)
     assert pinned.execute(other, box, f2) == e_ref and np.array_equal(f2, f_ref)
     pinned.close(); staged.close()
+
+
+def test_slab_with_vacuum_clusters_stretched_over_empty_cells(build_native):
+    """A liquid slab in a box three times as long: the last atoms of a z-ordered column and the first atoms of the next
+    one form i-clusters stretched over the empty cells, whose stencil wraps onto itself. The fast pair kernel lists them
+    for the generic (min-image) one; neighbour list and forces must not notice."""
+    pos, box, force = synthetic.water_box(400, seed=21, cutoff=0.6, ewald_tol=1e-4)
+    box = np.diag([box[0, 0], box[1, 1], 3.0 * box[2, 2]])
+    o = Oracle(force, box)
+    ctx = runtime.CoulContext(force, box)
+    assert min(ctx.kernel.stats().cells) >= 7                       # large enough for the fast kernel
+    for inc_e in (True, False):
+        eo, fo = o.execute(pos, box, True, inc_e)
+        e, f, comps = ctx.evaluate(pos, True, inc_e)
+        assert abs(e - eo[4]) <= (E_RTOL if inc_e else E_RTOL_DISCARDED) * max(abs(eo[4]), 1e-3 * np.abs(eo[:4]).max())
+        assert rel_rms(f, fo) <= F_RTOL
+    assert np.array_equal(ctx.kernel.neighbor_pairs(), o.neighbor_pairs())

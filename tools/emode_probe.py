@@ -17,3 +17,10 @@ p, _ = sim.get_state()
 sim.set_state(p, sim.maxwell_boltzmann(300.0, seed=7))
 sim.step(50, 0.0005)
 print("MD ms/step", sim.step(1000, 0.0005)/1000)
+p, _ = sim.get_state()
+sim.close()
+dpos2 = torch.tensor(p.reshape(-1), device='cuda')
+k = runtime.CalcCoulForceKernel(skip_discarded_energy=True)
+k.initialize(box, force)
+kt = k.time_kernels(dpos2.data_ptr(), box, 20, True, False)
+print("thermalised positions: device step %.4f ms  kernels %s" % (k.time_device(dpos2.data_ptr(), box, 50, True, False), {a: round(b, 4) for a, b in kt.items()}))

@@ -14,10 +14,13 @@ name = sys.argv[1] if len(sys.argv) > 1 else "c3"
 energy = len(sys.argv) > 2 and sys.argv[2] == "energy"
 count = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 pos, box, force = synthetic.config(name)
+if os.environ.get("CFX_PROBE_POSITIONS"):
+    pos = np.load(os.environ["CFX_PROBE_POSITIONS"])
 k = runtime.CalcCoulForceKernel(use_graph=False)
 k.initialize(box, force)
 f = np.zeros_like(pos)
 for _ in range(count):
     f[:] = 0
     e = k.execute(pos, box, f, True, energy)
-print(name, "E", e, "|F|rms", float(np.sqrt((f ** 2).mean())), "pairs", k.stats().pairs_in_cutoff)
+st = k.stats()
+print(name, "E", e, "|F|rms", float(np.sqrt((f ** 2).mean())), "pairs", st.pairs_in_cutoff, "distance tests", st.pair_candidates)
