@@ -32,15 +32,29 @@ def _newer(target, sources):
 
 
 def build_cuda(force=False, verbose=False):
+    """Each .cu is compiled to its own object (in parallel, rebuilt only when it or a header changed), then linked."""
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    sources = [os.path.join(CSRC, f) for f in ("api.cu", "flux.cu", "kspace.cu", "kspace_tc.cu", "direct.cu", "md.cu", "comm.cu", "platform.cu")]
-    deps = sources + [os.path.join(CSRC, "cfx_internal.cuh"), os.path.join(CSRC, "ptx_sm100.cuh"), os.path.join(ROOT, "include", "cfx_b200.h")]
-    if not force and not _newer(LIB, deps):
-        return LIB
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + sources
-    if verbose:
-        print(" ".join(cmd))
-    subprocess.run(cmd, check=True)
+    names = ("api.cu", "flux.cu", "kspace.cu", "kspace_tc.cu", "direct.cu", "md.cu", "comm.cu", "platform.cu")
+    headers = [os.path.join(CSRC, "cfx_internal.cuh"), os.path.join(CSRC, "ptx_sm100.cuh"), os.path.join(ROOT, "include", "cfx_b200.h")]
+    objdir = os.path.join(PKG, "_obj")
+    os.makedirs(objdir, exist_ok=True)
+    compile_flags = [f for f in NVCC_FLAGS if f not in ("-shared", "-ldl")]
+    compile_flags = [f for i, f in enumerate(compile_flags) if f not in ("-Xlinker", "--exclude-libs=ALL")]
+    jobs, objects = [], []
+    for n in names:
+        src, obj = os.path.join(CSRC, n), os.path.join(objdir, n[:-3] + ".o")
+        objects.append(obj)
+        if force or _newer(obj, [src] + headers):
+            jobs.append([nvcc] + compile_flags + ["-c", "-o", obj, src])
+    def run(cmd):
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.run(cmd, check=True)
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        list(ex.map(run, jobs))
+    if jobs or not os.path.exists(LIB):
+        run([nvcc] + NVCC_FLAGS + ["-o", LIB] + objects)
     return LIB
 
 

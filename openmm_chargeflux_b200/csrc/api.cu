@@ -70,6 +70,8 @@ void freeCells(State& st) {
     cudaFree(st.userLocal); cudaFree(st.sortedLocal); cudaFree(st.sortedMeta);
     cudaFree(st.pairCounters); cudaFree(st.filledUser); st.filledUser = nullptr;
     cudaFree(st.wrapList); st.wrapList = nullptr;
+    cudaFree(st.userLocalD); cudaFree(st.sortedLocalD); cudaFree(st.sortedLjD);
+    st.userLocalD = st.sortedLocalD = nullptr; st.sortedLjD = nullptr;
     st.cellOfAtom = st.cellCount = st.cellStart = st.cellFill = nullptr;
     st.userLocal = st.sortedLocal = st.sortedMeta = nullptr; st.pairCounters = nullptr;
 }

@@ -173,6 +173,9 @@ struct State {
     float4* userLocal = nullptr;        // [N] local xyz in own cell + q, user order (scratch of the cell build)
     float4* sortedLocal = nullptr;      // [N] atoms sorted by cell, z inside the cell: local xyz + q
     float4* sortedMeta = nullptr;       // [N] (sigma/2, 2 sqrt(eps), user index, packed cell coordinates)
+    double4* userLocalD = nullptr; double4* sortedLocalD = nullptr;   // the same in double (+ charge): FP64 pair energies
+    double2* sortedLjD = nullptr;       // [N] (sigma/2, 2 sqrt(eps)) in double, sorted order
+    double ePoly[25] = {0}; double eTScale = 0; int ePolyOK = 0;   // polynomial of the FP64 pair energies (direct.cu)
     int* wrapList = nullptr;            // clusters the fast pair kernel left to the generic one
     int* filledUser = nullptr;          // cell fill in arrival order (input of the rank pass)
     unsigned int* exclMaxR2 = nullptr;  // [Npad] float bits: per atom, largest r2 to an excluded partner (this evaluation)

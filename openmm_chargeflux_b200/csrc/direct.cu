@@ -34,6 +34,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <cmath>
 #include <type_traits>
 
@@ -52,14 +53,15 @@ struct CellParams {
 
 // wrap, bin, cell-local coordinates; counts per cell
 __global__ void __launch_bounds__(256) cellAssignKernel(CellParams p, const double* __restrict__ pos, const float* __restrict__ qf,
-        int* __restrict__ cellOfAtom, float4* __restrict__ userLocal, int* __restrict__ cellCount) {
+        const double* __restrict__ qd, int* __restrict__ cellOfAtom, float4* __restrict__ userLocal, double4* __restrict__ userLocalD,
+        int* __restrict__ cellCount) {
     const int i = blockIdx.x*blockDim.x + threadIdx.x;
     if (i >= p.N) return;
     double u[3] = {pos[3*(size_t) i]*p.invLx, pos[3*(size_t) i + 1]*p.invLy, pos[3*(size_t) i + 2]*p.invLz};
     const int nc[3] = {p.ncx, p.ncy, p.ncz};
     const double cs[3] = {p.csx, p.csy, p.csz};
     int c[3];
-    float loc[3];
+    double loc[3];
     #pragma unroll
     for (int d = 0; d < 3; d++) {
         double f = u[d] - floor(u[d]);          // [0,1)
@@ -67,11 +69,12 @@ __global__ void __launch_bounds__(256) cellAssignKernel(CellParams p, const doub
         int k = (int) g;
         if (k >= nc[d]) k = nc[d] - 1;
         c[d] = k;
-        loc[d] = (float) ((g - k)*cs[d]);
+        loc[d] = (g - k)*cs[d];
     }
     const int cell = (c[0]*p.ncy + c[1])*p.ncz + c[2];
     cellOfAtom[i] = cell;
-    userLocal[i] = make_float4(loc[0], loc[1], loc[2], qf[i]);
+    userLocal[i] = make_float4((float) loc[0], (float) loc[1], (float) loc[2], qf[i]);
+    userLocalD[i] = make_double4(loc[0], loc[1], loc[2], qd[i]);    // FP64 copy: pair energies (EMODE 2)
     atomicAdd(cellCount + cell, 1);
 }
 
@@ -128,7 +131,9 @@ __global__ void __launch_bounds__(256) cellFillKernel(int N, const int* __restri
 // packed cell coordinates).
 __global__ void __launch_bounds__(256) cellRankGatherKernel(int N, int ncy, int ncz, const int* __restrict__ filledUser,
         const int* __restrict__ cellOfAtom, const int* __restrict__ cellStart, const float4* __restrict__ userLocal,
-        const float2* __restrict__ lj, float4* __restrict__ sortedLocal, float4* __restrict__ sortedMeta) {
+        const float2* __restrict__ lj, float4* __restrict__ sortedLocal, float4* __restrict__ sortedMeta,
+        const double4* __restrict__ userLocalD, const double2* __restrict__ ljd, double4* __restrict__ sortedLocalD,
+        double2* __restrict__ sortedLjD) {
     const int s = blockIdx.x*blockDim.x + threadIdx.x;
     if (s >= N) return;
     const int u = filledUser[s];
@@ -145,6 +150,8 @@ __global__ void __launch_bounds__(256) cellRankGatherKernel(int N, int ncy, int 
     const int cz = cell % ncz, cy = (cell/ncz) % ncy, cx = cell/(ncz*ncy);
     const float2 l = lj[u];
     sortedLocal[dst] = mine;
+    sortedLocalD[dst] = userLocalD[u];
+    sortedLjD[dst] = ljd[u];
     sortedMeta[dst] = make_float4(l.x, l.y, __int_as_float(u), __int_as_float(cx | (cy << CELL_BITS) | (cz << (2*CELL_BITS))));
 }
 
@@ -157,11 +164,17 @@ __global__ void __launch_bounds__(256) cellRankGatherKernel(int N, int ncy, int 
 #ifndef P_FAST_MINBLOCKS
 #define P_FAST_MINBLOCKS 5     // resident CTAs per SM the fast kernel is compiled for (register cap 96)
 #endif
-#define R_COMPS 7
+#define R_COMPS 8
+#define RD_COMPS 6
+#define E_POLY_DEG 20
 #ifndef P_UNROLL
 #define P_UNROLL 1        // the packed loop already carries two independent pairs per iteration
 #endif
 constexpr int kPairUnroll = P_UNROLL;
+#ifndef P_EUNROLL
+#define P_EUNROLL 1       // FP64 energy passes
+#endif
+constexpr int kEnergyUnroll = P_EUNROLL;
 #define P_JCAP 64            // ring capacity: < 32 waiting entries + one 32-candidate chunk
 
 struct PairParams {
@@ -178,10 +191,17 @@ struct PairParams {
     const int* exclPtr; const int* exclCols;
     const unsigned int* exclMaxR2Bits;       // [N] per user atom: float bits of the largest r2 to an excluded partner (exclusionKernel)
     const double* pos; const double* q; const double2* ljd; double alphaD, dInvLx, dInvLy, dInvLz;
+    // FP64 pair energies (EMODE 2): cell-local coordinates + charge and LJ parameters of the sorted atoms in double, and the
+    // polynomial of erf(sqrt z)/sqrt z in t = eTScale s - 1 (see fitEnergyPolynomial)
+    const double4* sortedLocalD; const double2* sortedLjD;
+    double ePoly[E_POLY_DEG + 1]; double eTScale; int ePolyOK;
+    double dcsx, dcsy, dcsz;
     long long* forceFixed; long long* dedqFixed; long long* energyFixed;
     unsigned long long* counters; int2* pairBuffer; unsigned long long pairCapacity;
     unsigned int* workCounter;               // dynamic work distribution: next (cluster, column share) item
-    int* wrapList;                           // clusters the fast kernel left to the generic one (counters[7] of them)
+    int* wrapList;                           // clusters the fast kernel left to the generic one (*wrapCount of them)
+    unsigned long long* wrapCount;
+    int countStats;                          // this pass adds to counters[0..1] (the second pass of an energy+forces call does not)
 };
 
 __device__ __forceinline__ int wrapNearest(int d, int nc) {
@@ -227,6 +247,14 @@ __device__ __noinline__ int rareInCutoff(const PairParams* p, int ui, int uj, fl
     return in ? 1 : 0;
 }
 
+// EMODE 2, fallback when the polynomial of fitEnergyPolynomial does not cover alpha^2 rc^2
+__device__ __noinline__ double closePairEnergy(const PairParams* p, double s, double kqq, double sig, double eps) {
+    const double invR = rsqrt(s);
+    double s2 = sig*invR; s2 *= s2;
+    const double s6 = s2*s2*s2;
+    return kqq*invR*erfc(p->alphaD*s*invR) + eps*s6*(s6 - 1.0);
+}
+
 __device__ __forceinline__ float2 pk(float a) { return make_float2(a, a); }     // scalar broadcast operand of a packed instruction
 __device__ __forceinline__ int modPos(int v, int n) { v %= n; return v < 0 ? v + n : v; }
 // v in (-n, 2n): the fast kernel's cell grids have at least 7 cells per axis and stencils of at most n cells
@@ -237,18 +265,19 @@ __device__ __forceinline__ int wrapOnce(int v, int n) { return v < 0 ? v + n : (
 // EMODE: 0 = no pair energy, 1 = FP32 pair terms (the partial energy the reference returns when
 // includeEnergy is false is discarded by OpenMM; it is still produced, at FP32 accuracy), 2 = FP64 terms.
 template <bool FAST, bool FORCES, int EMODE, bool EMIT>
-__global__ void __launch_bounds__(P_WARPS*32, FAST ? P_FAST_MINBLOCKS : 4) pairKernel(const __grid_constant__ PairParams p) {
+__global__ void __launch_bounds__(P_WARPS*32, (FAST && EMODE != 2) ? P_FAST_MINBLOCKS : 4) pairKernel(const __grid_constant__ PairParams p) {
     // rings of staged j atoms, [0: without LJ well depth, 1: with][warp][slot], one array per component so that a lane
     // fetches the same component of two consecutive entries with one LDS.64 -- the operand layout of the packed
     // (two pairs per instruction) FP32 arithmetic of the inner loop
     // components: 0-2 xyz in the cluster frame, 3 charge, 4 user index (rare paths, pair emission, energy queue),
-    // 5-6 sigma/2 and 2 sqrt(eps) (LJ ring only); one block per warp so that every access is base + constant offset
+    // 5-6 sigma/2 and 2 sqrt(eps) (LJ ring only), 7 sorted index (FP64 energies: a pair is counted from the side of the
+    // atom that comes first in sorted order); one block per warp so that every access is base + constant offset
     __shared__ __align__(16) float sRing[P_WARPS][2][R_COMPS][P_JCAP];
-    __shared__ int2 sEq[EMODE == 2 ? P_WARPS : 1][P_JCAP];   // queue of in-cutoff (ui<uj) pairs awaiting the FP64 energy
+    // EMODE 2: the same entries in double -- 0-2 xyz in the cluster frame, 3 charge, 4-5 sigma/2 and 2 sqrt(eps)
+    __shared__ __align__(16) double sRingD[EMODE == 2 ? P_WARPS : 1][2][EMODE == 2 ? RD_COMPS : 1][EMODE == 2 ? P_JCAP : 2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ii = lane >> 2, part = lane & 3;
     const unsigned int lt = (1u << lane) - 1u;
-    int2* eq = sEq[EMODE == 2 ? warp : 0];
     const float alpha = p.alpha, alpha2 = p.alpha2, band = p.band;
     const float rcut2 = p.rc2*1.0001f;
     const float4 farAway = make_float4(1e4f, 1e4f, 1e4f, 0.f);
@@ -256,7 +285,10 @@ __global__ void __launch_bounds__(P_WARPS*32, FAST ? P_FAST_MINBLOCKS : 4) pairK
     // there are few of them, so each is dealt over 256 shares (one stencil column per warp) to keep its latency short.
     const bool listed = !FAST && p.onlyMinImage;
     const int nShares = listed ? 256 : p.jSplits;
-    const unsigned int totalItems = (listed ? (unsigned int) p.counters[7] : (unsigned int) (p.groupHi - p.groupLo))*(unsigned int) nShares;
+    // energy-only passes count every pair once, from the atom that comes first in sorted order: they scan only the
+    // part of the stencil behind the cluster (half shell: no j-side accumulation is needed for an energy)
+    constexpr bool HALF = !FORCES && EMODE == 2 && !EMIT;
+    const unsigned int totalItems = (listed ? (unsigned int) *p.wrapCount : (unsigned int) (p.groupHi - p.groupLo))*(unsigned int) nShares;
 
     // persistent warps: work items (i-cluster, share of its stencil columns) are handed out by an atomic counter, so the
     // GPU stays full whatever the item count (no partial last wave)
@@ -286,6 +318,13 @@ __global__ void __launch_bounds__(P_WARPS*32, FAST ? P_FAST_MINBLOCKS : 4) pairK
         const float ljix = mi.x, ljiy = mi.y;
         const int ui = __float_as_int(mi.z);
         const float keqi = (float) CFX_ONE_4PI_EPS0*li.w;
+        double pixD = 0.0, piyD = 0.0, pizD = 0.0, kqiD = 0.0, sigiD = 0.0, epsiD = 0.0;
+        if (EMODE == 2) {
+            const double4 ld = p.sortedLocalD[iIdx];
+            const double2 lld = p.sortedLjD[iIdx];
+            pixD = ld.x + ox*p.dcsx; piyD = ld.y + oy*p.dcsy; pizD = ld.z + oz*p.dcsz;
+            kqiD = CFX_ONE_4PI_EPS0*ld.w; sigiD = lld.x; epsiD = lld.y;
+        }
         // per-lane copies of the thresholds: lanes without an i atom (last cluster) never see a pair
         const float rc2i = validI ? p.rc2 : -1.f;
         // (floor 1e-8 nm^2: the self pair is r2 = 0 up to rounding when a small box folds the stencil onto itself)
@@ -312,7 +351,7 @@ __global__ void __launch_bounds__(P_WARPS*32, FAST ? P_FAST_MINBLOCKS : 4) pairK
         const int loZ = ominz - 2, nZ = min(omaxz - ominz + 5, p.ncz);
         const bool wraps = (omaxx - ominx + 5 > p.ncx) || (omaxy - ominy + 5 > p.ncy) || (omaxz - ominz + 5 > p.ncz);
         if (FAST && wraps) {                            // left to the generic kernel launched behind this one
-            if (lane == 0 && share == 0) p.wrapList[atomicAdd(p.counters + 7, 1ull)] = g;
+            if (lane == 0 && share == 0) p.wrapList[atomicAdd(p.wrapCount, 1ull)] = g;
             continue;
         }
         const bool minImage = FAST ? false : wraps;
@@ -320,30 +359,6 @@ __global__ void __launch_bounds__(P_WARPS*32, FAST ? P_FAST_MINBLOCKS : 4) pairK
         float2 fx2 = pk(0.f), fy2 = pk(0.f), fz2 = pk(0.f), dq2 = pk(0.f), enf2 = pk(0.f);     // two partial sums each
         double en = 0.0;
         unsigned int nIn = 0, nCand = 0;                 // in-cutoff ordered pairs seen by this lane; candidates staged by the warp
-        int qCount = 0;                                  // entries waiting in the energy queue
-
-        // Pair energies are evaluated in FP64 on the original coordinates (the direct, self and exclusion
-        // sums cancel to a small fraction of their size, FP32 terms would cost ~1e-3 kJ/mol). In-cutoff
-        // pairs are compacted into a queue so that all 32 lanes do FP64 work together.
-        auto energyBatch = [&](int n) {
-            __syncwarp();
-            if (lane < n) {
-                const int a = eq[lane].x, b = eq[lane].y;
-                double dx = p.pos[3*(size_t) a] - p.pos[3*(size_t) b];
-                double dy = p.pos[3*(size_t) a + 1] - p.pos[3*(size_t) b + 1];
-                double dz = p.pos[3*(size_t) a + 2] - p.pos[3*(size_t) b + 2];
-                dx -= p.dLx*floor(dx*p.dInvLx + 0.5); dy -= p.dLy*floor(dy*p.dInvLy + 0.5); dz -= p.dLz*floor(dz*p.dInvLz + 0.5);
-                const double r2 = dx*dx + dy*dy + dz*dz;
-                const double invR = rsqrt(r2);
-                const double ar = p.alphaD*r2*invR;
-                const double2 la = p.ljd[a], lb = p.ljd[b];
-                const double sig = la.x + lb.x;
-                double s2 = sig*invR; s2 *= s2;
-                const double s6 = s2*s2*s2;
-                en += CFX_ONE_4PI_EPS0*p.q[a]*p.q[b]*invR*erfc(ar) + s6*(la.y*lb.y)*(s6 - 1.0);
-            }
-            __syncwarp();
-        };
 
         // One tile = the 32 ring entries from `base` (0 or 32) of ring `LJ`; entries past the end n of a last, partial
         // tile hold far-away positions with zero charge and well depth (min-image tiles, which would fold them back
@@ -351,7 +366,7 @@ __global__ void __launch_bounds__(P_WARPS*32, FAST ? P_FAST_MINBLOCKS : 4) pairK
         // and evaluates them with packed FP32 instructions (FFMA2 / FMUL2 / FADD2 of sm_100: one issue slot for two
         // pairs; the kernel is issue-bound, not FMA-pipe-bound). Straight-line code: out-of-cutoff pairs are masked,
         // not branched.
-        auto processTile = [&](auto ljTag, auto imgTag, int base, int n) {
+        auto processTile = [&](auto ljTag, auto imgTag, int base, int n, bool doE) {
             constexpr bool LJ = decltype(ljTag)::value, IMG = decltype(imgTag)::value;
             const float* ring = &sRing[warp][LJ][0][0] + base;
             const float2* tX = reinterpret_cast<const float2*>(ring);
@@ -362,15 +377,19 @@ __global__ void __launch_bounds__(P_WARPS*32, FAST ? P_FAST_MINBLOCKS : 4) pairK
             const float2* tSig = reinterpret_cast<const float2*>(ring + 5*P_JCAP);
             const float2* tEps = reinterpret_cast<const float2*>(ring + 6*P_JCAP);
             __syncwarp();
-            #pragma unroll (kPairUnroll)
+            #pragma unroll (EMODE == 2 ? kEnergyUnroll : kPairUnroll)
             for (int c = part; c < P_JTILE/2; c += 4) {
                 const float2 xj = tX[c], yj = tY[c], zj = tZ[c], qj = tQ[c];
                 float2 dx = __ffma2_rn(xj, pk(-1.f), pk(pix));                 // pos[i] - pos[j], two j atoms
                 float2 dy = __ffma2_rn(yj, pk(-1.f), pk(piy));
                 float2 dz = __ffma2_rn(zj, pk(-1.f), pk(piz));
+                float2 imx = pk(0.f), imy = pk(0.f), imz = pk(0.f);               // min-image shifts in box lengths
                 if (IMG) {
-                    dx.x -= p.Lx*rintf(dx.x*p.invLx); dy.x -= p.Ly*rintf(dy.x*p.invLy); dz.x -= p.Lz*rintf(dz.x*p.invLz);
-                    dx.y -= p.Lx*rintf(dx.y*p.invLx); dy.y -= p.Ly*rintf(dy.y*p.invLy); dz.y -= p.Lz*rintf(dz.y*p.invLz);
+                    imx = make_float2(rintf(dx.x*p.invLx), rintf(dx.y*p.invLx));
+                    imy = make_float2(rintf(dy.x*p.invLy), rintf(dy.y*p.invLy));
+                    imz = make_float2(rintf(dz.x*p.invLz), rintf(dz.y*p.invLz));
+                    dx.x -= p.Lx*imx.x; dy.x -= p.Ly*imy.x; dz.x -= p.Lz*imz.x;
+                    dx.y -= p.Lx*imx.y; dy.y -= p.Ly*imy.y; dz.y -= p.Lz*imz.y;
                 }
                 const float2 r2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
                 bool in0 = r2.x <= rc2i, in1 = r2.y <= rc2i;
@@ -383,6 +402,60 @@ __global__ void __launch_bounds__(P_WARPS*32, FAST ? P_FAST_MINBLOCKS : 4) pairK
                 if (rare0 | rare1) {
                     if (rare0) in0 = rareInCutoff(&p, ui, tUser[2*c], r2.x, r2close) != 0;
                     if (rare1) in1 = rareInCutoff(&p, ui, tUser[2*c + 1], r2.y, r2close) != 0;
+                }
+                if (EMODE == 2 && doE) {
+                    // FP64 pair energy (E_direct cancels against E_self + E_excl to a small fraction of its size, FP32 terms
+                    // would cost ~1e-3 kJ/mol): r^2 in double from the double copies of the staged coordinates, the
+                    // Coulomb term as 1/r (FP32 rsqrt + one Newton step in double) minus a degree-20 polynomial in s (no erfc,
+                    // exp, division or table), the LJ term from the same 1/r. Every pair is
+                    // seen from both sides and counted from the side of the atom that comes first in sorted order: tiles
+                    // whose j atoms all precede the cluster (about half of them: doE false) skip this block.
+                    const double* ringD = &sRingD[warp][LJ][0][0] + base;
+                    const double2 xd = reinterpret_cast<const double2*>(ringD)[c];
+                    const double2 yd = reinterpret_cast<const double2*>(ringD + P_JCAP)[c];
+                    const double2 zd = reinterpret_cast<const double2*>(ringD + 2*P_JCAP)[c];
+                    const double2 qd = reinterpret_cast<const double2*>(ringD + 3*P_JCAP)[c];
+                    const int2 sj2 = reinterpret_cast<const int2*>(ring + 7*P_JCAP)[c];
+                    double2 sgd = make_double2(0.0, 0.0), epd = make_double2(0.0, 0.0);
+                    if (LJ) {
+                        sgd = reinterpret_cast<const double2*>(ringD + 4*P_JCAP)[c];
+                        epd = reinterpret_cast<const double2*>(ringD + 5*P_JCAP)[c];
+                    }
+                    #pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        double ddx = pixD - (h ? xd.y : xd.x), ddy = piyD - (h ? yd.y : yd.x), ddz = pizD - (h ? zd.y : zd.x);
+                        if (IMG) {
+                            ddx -= p.dLx*(double) (h ? imx.y : imx.x); ddy -= p.dLy*(double) (h ? imy.y : imy.x);
+                            ddz -= p.dLz*(double) (h ? imz.y : imz.x);
+                        }
+                        const double sD = fma(ddz, ddz, fma(ddy, ddy, ddx*ddx));
+                        const float r2f = h ? r2.y : r2.x;
+                        bool on = (h ? in1 : in0) && (h ? sj2.y : sj2.x) > iIdx;
+                        const double qq = kqiD*(h ? qd.y : qd.x);                  // ONE_4PI_EPS0 q_i q_j
+                        if (HALF && on) nIn += 2u;
+                        if (!p.ePolyOK && on) {                                     // exotic tolerance (alpha rc > 4): libm erfc
+                            en += closePairEnergy(&p, sD, qq, sigiD + (h ? sgd.y : sgd.x), epsiD*(h ? epd.y : epd.x));
+                            on = false;
+                        }
+                        // 1/r: FP32 rsqrt refined once in double (relative error ~1e-13)
+                        const double y0 = (double) rsqrtFtz(fmaxf(r2f, 1e-12f));      // (the self pair of a folded stencil: finite)
+                        const double ey = fma(-(sD*y0), y0, 1.0);
+                        const double y = fma(0.5*y0, ey, y0);
+                        // erfc(alpha r)/r = 1/r - alpha G(alpha^2 s), G(z) = erf(sqrt z)/sqrt z entire in z: one polynomial
+                        const double t = fma(sD, p.eTScale, -1.0);
+                        double g = p.ePoly[E_POLY_DEG];
+                        #pragma unroll
+                        for (int k = E_POLY_DEG - 1; k >= 0; k--) g = fma(g, t, p.ePoly[k]);
+                        const double fv = fma(-p.alphaD, g, y);
+                        en = fma(on ? qq : 0.0, fv, en);
+                        if (LJ) {
+                            const double yy = y*y;
+                            const double sg = sigiD + (h ? sgd.y : sgd.x);
+                            const double s2 = sg*sg*yy, s6 = s2*s2*s2;
+                            const double elj = epsiD*(h ? epd.y : epd.x)*s6*(s6 - 1.0);
+                            en += on ? elj : 0.0;
+                        }
+                    }
                 }
                 if (FORCES || EMODE == 1) {
                     const float2 invR = make_float2(rsqrtFtz(r2.x), rsqrtFtz(r2.y));
@@ -427,29 +500,14 @@ __global__ void __launch_bounds__(P_WARPS*32, FAST ? P_FAST_MINBLOCKS : 4) pairK
                         enf2 = __fadd2_rn(enf2, e);
                     }
                 }
-                nIn += (in0 ? 1u : 0u) + (in1 ? 1u : 0u);
-                if (EMIT || EMODE == 2) {
+                if (!HALF) nIn += (in0 ? 1u : 0u) + (in1 ? 1u : 0u);
+                if (EMIT) {
                     #pragma unroll
                     for (int h = 0; h < 2; h++) {
                         const int uj = tUser[2*c + h];
-                        const bool want = (h ? in1 : in0) && ui < uj;
-                        if (EMIT && want) {
+                        if ((h ? in1 : in0) && ui < uj) {
                             const unsigned long long slot = atomicAdd(p.counters + 2, 1ull);
                             if (slot < p.pairCapacity) p.pairBuffer[slot] = make_int2(ui, uj);
-                        }
-                        if (EMODE == 2) {
-                            const unsigned int m = __ballot_sync(0xffffffffu, want);
-                            if (want) eq[qCount + __popc(m & lt)] = make_int2(ui, uj);
-                            qCount += __popc(m);
-                            if (qCount >= 32) {
-                                energyBatch(32);
-                                const int rest = qCount - 32;
-                                int2 mv = make_int2(0, 0);
-                                if (lane < rest) mv = eq[32 + lane];
-                                __syncwarp();
-                                if (lane < rest) eq[lane] = mv;
-                                qCount = rest;
-                            }
                         }
                     }
                 }
@@ -459,6 +517,9 @@ __global__ void __launch_bounds__(P_WARPS*32, FAST ? P_FAST_MINBLOCKS : 4) pairK
 
         // ring state per class: entries [base, base + count) mod 64 are waiting; base is 0 or 32
         int base0 = 0, count0 = 0, base1 = 0, count1 = 0;
+        // largest sorted index among the waiting entries of each ring, and among those of the chunk staged last (what is
+        // left after a flush comes from that chunk): a tile whose j atoms all precede the cluster needs no FP64 energies
+        int hi0 = -1, hi1 = -1, lastHi0 = -1, lastHi1 = -1;
         // a full tile, or (last == true, after the last chunk) the partial one, padded
         auto flush = [&](bool last) {
             if (count0 >= P_JTILE || (last && count0 > 0)) {
@@ -466,18 +527,30 @@ __global__ void __launch_bounds__(P_WARPS*32, FAST ? P_FAST_MINBLOCKS : 4) pairK
                 if (lane >= n) {
                     float* e = &sRing[warp][0][0][(base0 + lane) & (P_JCAP - 1)];
                     e[0] = 1e4f; e[P_JCAP] = 1e4f; e[2*P_JCAP] = 1e4f; e[3*P_JCAP] = 0.f;
+                    if (EMODE == 2) {
+                        double* ed = &sRingD[warp][0][0][(base0 + lane) & (P_JCAP - 1)];
+                        ed[0] = 1e4; ed[P_JCAP] = 1e4; ed[2*P_JCAP] = 1e4; ed[3*P_JCAP] = 0.0;
+                    }
                 }
-                if (minImage) processTile(std::false_type{}, std::true_type{}, base0, n); else processTile(std::false_type{}, std::false_type{}, base0, n);
+                const bool doE = hi0 > i0;
+                if (minImage) processTile(std::false_type{}, std::true_type{}, base0, n, doE); else processTile(std::false_type{}, std::false_type{}, base0, n, doE);
                 base0 ^= P_JTILE; count0 -= P_JTILE;
+                hi0 = count0 > 0 ? lastHi0 : -1;
             }
             if (count1 >= P_JTILE || (last && count1 > 0)) {
                 const int n = min(count1, P_JTILE);
                 if (lane >= n) {
                     float* e = &sRing[warp][1][0][(base1 + lane) & (P_JCAP - 1)];
                     e[0] = 1e4f; e[P_JCAP] = 1e4f; e[2*P_JCAP] = 1e4f; e[3*P_JCAP] = 0.f; e[5*P_JCAP] = 0.f; e[6*P_JCAP] = 0.f;
+                    if (EMODE == 2) {
+                        double* ed = &sRingD[warp][1][0][(base1 + lane) & (P_JCAP - 1)];
+                        ed[0] = 1e4; ed[P_JCAP] = 1e4; ed[2*P_JCAP] = 1e4; ed[3*P_JCAP] = 0.0; ed[4*P_JCAP] = 0.0; ed[5*P_JCAP] = 0.0;
+                    }
                 }
-                if (minImage) processTile(std::true_type{}, std::true_type{}, base1, n); else processTile(std::true_type{}, std::false_type{}, base1, n);
+                const bool doE = hi1 > i0;
+                if (minImage) processTile(std::true_type{}, std::true_type{}, base1, n, doE); else processTile(std::true_type{}, std::false_type{}, base1, n, doE);
                 base1 ^= P_JTILE; count1 -= P_JTILE;
+                hi1 = count1 > 0 ? lastHi1 : -1;
             }
         };
 
@@ -518,15 +591,20 @@ __global__ void __launch_bounds__(P_WARPS*32, FAST ? P_FAST_MINBLOCKS : 4) pairK
                     const int segHi = sg == 0 ? min(zloW + zCount - 1, p.ncz - 1) : zloW + zCount - 1 - p.ncz;
                     const int zShift = (sg == 0 ? zlo - zloW : zlo - zloW + p.ncz) - c0z;
                     const int s1 = p.cellStart[rowCell + segHi + 1];
-                    for (int sb = p.cellStart[rowCell + segLo]; sb < s1; sb += 32) {
+                    for (int sb = HALF ? max(p.cellStart[rowCell + segLo], i0 + 1) : p.cellStart[rowCell + segLo]; sb < s1; sb += 32) {
                         const int s = sb + lane;
                         bool pass = false, cls = false;
                         float4 pj = farAway, mj = farAway;
+                        double4 pjD = make_double4(0.0, 0.0, 0.0, 0.0);
                         if (s < s1) {
                             const float4 l4 = p.sortedLocal[s];
                             mj = p.sortedMeta[s];
                             const int cz = __float_as_int(mj.w) >> (2*CELL_BITS);
                             pj = make_float4(l4.x + shx, l4.y + shy, fmaf((float) (cz + zShift), p.csz, l4.z), l4.w);
+                            if (EMODE == 2) {
+                                const double4 ld = p.sortedLocalD[s];
+                                pjD = make_double4(ld.x + (loX + ax)*p.dcsx, ld.y + (loY + ay)*p.dcsy, ld.z + (cz + zShift)*p.dcsz, ld.w);
+                            }
                             if (minImage) pass = true;
                             else {
                                 const float ex = fmaxf(0.f, fmaxf(bminx - pj.x, pj.x - bmaxx));
@@ -543,8 +621,18 @@ __global__ void __launch_bounds__(P_WARPS*32, FAST ? P_FAST_MINBLOCKS : 4) pairK
                             float* e = &sRing[warp][cls][0][slot];
                             e[0] = pj.x; e[P_JCAP] = pj.y; e[2*P_JCAP] = pj.z; e[3*P_JCAP] = pj.w; e[4*P_JCAP] = mj.z;
                             if (cls) { e[5*P_JCAP] = mj.x; e[6*P_JCAP] = mj.y; }
+                            if (EMODE == 2) {
+                                e[7*P_JCAP] = __int_as_float(s);
+                                double* ed = &sRingD[warp][cls][0][slot];
+                                ed[0] = pjD.x; ed[P_JCAP] = pjD.y; ed[2*P_JCAP] = pjD.z; ed[3*P_JCAP] = pjD.w;
+                                if (cls) { const double2 ljj = p.sortedLjD[s]; ed[4*P_JCAP] = ljj.x; ed[5*P_JCAP] = ljj.y; }
+                            }
                         }
                         count0 += __popc(m0); count1 += __popc(m1);
+                        if (EMODE == 2) {
+                            if (m0) { lastHi0 = sb + 31 - __clz(m0); hi0 = max(hi0, lastHi0); }
+                            if (m1) { lastHi1 = sb + 31 - __clz(m1); hi1 = max(hi1, lastHi1); }
+                        }
                         nCand += (unsigned int) __popc(m0 | m1);
                         flush(false);
                     }
@@ -553,7 +641,6 @@ __global__ void __launch_bounds__(P_WARPS*32, FAST ? P_FAST_MINBLOCKS : 4) pairK
             if (++cxw == p.ncx) cxw = 0;
         }
         flush(true);
-        if (EMODE == 2 && qCount > 0) energyBatch(qCount);
 
         // reduce over the 4 lanes of each i atom (warp shuffles), one fixed-point atomic per output
         if (FORCES) {
@@ -573,12 +660,12 @@ __global__ void __launch_bounds__(P_WARPS*32, FAST ? P_FAST_MINBLOCKS : 4) pairK
         if (EMODE != 0) {
             if (EMODE == 1) en = (double) (enf2.x + enf2.y);
             en = warpSum(en);
-            // FP64 queue: each i<j pair once. FP32 terms: every pair is seen from both sides.
+            // FP32 terms: every pair is seen from both sides. FP64 terms: counted once (from the atom first in sorted order).
             if (lane == 0) atomicAddEnergy(p.energyFixed + CFX_E_DIRECT, EMODE == 2 ? en : 0.5*en);
         }
         #pragma unroll
         for (int o = 16; o > 0; o >>= 1) nIn += __shfl_xor_sync(0xffffffffu, nIn, o);
-        if (lane == 0) {
+        if (lane == 0 && p.countStats) {
             atomicAdd(p.counters + 0, (unsigned long long) nIn);        // ordered pairs: the host halves it
             atomicAdd(p.counters + 1, (unsigned long long) nCand*P_ITILE);
         }
@@ -603,6 +690,48 @@ void dispatchPair(const PairParams& pp, bool forces, int emode, int blocks, cuda
 
 } // namespace
 
+// FP64 pair energies: erfc(alpha r)/r = 1/r - alpha G(alpha^2 s), s = r^2, G(z) = erf(sqrt z)/sqrt z, which is entire in z.
+// G is interpolated at the Chebyshev nodes of [0, Z], Z = alpha^2 rc^2 (1 + 1e-3), by one polynomial of degree E_POLY_DEG
+// in t = 2 z/Z - 1 (monomial form: its coefficients sum to ~1.1 in magnitude, Horner is well conditioned); the fit is
+// checked here against erfl and, should it miss 1e-10 (alpha rc > 4, i.e. Ewald tolerances below 6e-8), the kernel
+// falls back to libm's erfc.
+static void fitEnergyPolynomial(const State& st, double* coef, double* tScale, int* ok) {
+    const int n = E_POLY_DEG + 1;
+    const long double pi = 3.14159265358979323846264338327950288L;
+    const long double Z = (long double) st.alpha*st.alpha*st.cutoff*st.cutoff*1.001L;
+    auto G = [](long double z) -> long double {
+        if (z < 1e-6L) return 2.0L/sqrtl(3.14159265358979323846264338327950288L)*(1.0L - z/3.0L + z*z/10.0L);
+        const long double r = sqrtl(z);
+        return erfl(r)/r;
+    };
+    std::vector<long double> f(n), c(n);
+    for (int j = 0; j < n; j++) f[j] = G(0.5L*Z*(1.0L + cosl(pi*(j + 0.5L)/n)));
+    for (int k = 0; k < n; k++) {
+        long double a = 0;
+        for (int j = 0; j < n; j++) a += f[j]*cosl(pi*k*(j + 0.5L)/n);
+        c[k] = a*(k == 0 ? 1.0L : 2.0L)/n;
+    }
+    std::vector<long double> mono(n, 0.0L), tkm(n, 0.0L), tk(n, 0.0L), tn(n);
+    tkm[0] = 1.0L;                       // T_0
+    tk[1] = 1.0L;                        // T_1
+    for (int i = 0; i < n; i++) mono[i] += c[0]*tkm[i] + (n > 1 ? c[1]*tk[i] : 0.0L);
+    for (int k = 2; k < n; k++) {        // T_k = 2 t T_{k-1} - T_{k-2}
+        for (int i = 0; i < n; i++) tn[i] = (i > 0 ? 2.0L*tk[i-1] : 0.0L) - tkm[i];
+        for (int i = 0; i < n; i++) mono[i] += c[k]*tn[i];
+        tkm = tk; tk = tn;
+    }
+    for (int i = 0; i < n; i++) coef[i] = (double) mono[i];
+    *tScale = (double) (2.0L*st.alpha*st.alpha/Z);
+    long double worst = 0;
+    for (int j = 0; j <= 4000; j++) {
+        const long double z = Z*j/4000.0L, t = 2.0L*z/Z - 1.0L;
+        long double v = coef[n-1];
+        for (int k = n - 2; k >= 0; k--) v = v*t + coef[k];
+        worst = std::max(worst, fabsl(v - G(z)));
+    }
+    *ok = worst < 1e-10L ? 1 : 0;
+}
+
 void planCells(State& st) {
     CellPlan& c = st.cells;
     c.smallBox = false;
@@ -624,27 +753,32 @@ void planCells(State& st) {
     CFX_CUDA(cudaMalloc(&st.sortedLocal, sizeof(float4)*st.Npad));
     CFX_CUDA(cudaMalloc(&st.sortedMeta, sizeof(float4)*st.Npad));
     CFX_CUDA(cudaMalloc(&st.filledUser, sizeof(int)*st.Npad));
-    CFX_CUDA(cudaMalloc(&st.wrapList, sizeof(int)*(st.Npad/P_ITILE + 1)));
-    CFX_CUDA(cudaMalloc(&st.pairCounters, sizeof(unsigned long long)*8));
-    CFX_CUDA(cudaMemset(st.pairCounters, 0, sizeof(unsigned long long)*8));
+    CFX_CUDA(cudaMalloc(&st.userLocalD, sizeof(double4)*st.Npad));
+    CFX_CUDA(cudaMalloc(&st.sortedLocalD, sizeof(double4)*st.Npad));
+    CFX_CUDA(cudaMalloc(&st.sortedLjD, sizeof(double2)*st.Npad));
+    static_assert(E_POLY_DEG + 1 <= sizeof(st.ePoly)/sizeof(double), "State::ePoly too small");
+    fitEnergyPolynomial(st, st.ePoly, &st.eTScale, &st.ePolyOK);
+    CFX_CUDA(cudaMalloc(&st.wrapList, sizeof(int)*2*(st.Npad/P_ITILE + 1)));
+    CFX_CUDA(cudaMalloc(&st.pairCounters, sizeof(unsigned long long)*16));
+    CFX_CUDA(cudaMemset(st.pairCounters, 0, sizeof(unsigned long long)*16));
 }
 
-// pairCounters (8 x u64): [0] in-cutoff ordered pairs, [1] distance tests, [2] emitted pairs, [5] / [6] work-item counters of the fast / generic pair kernel, [7] clusters the fast kernel
-// left to the generic one.
+// pairCounters (16 x u64): [0] in-cutoff ordered pairs, [1] distance tests, [2] emitted pairs; per pass k of an evaluation
+// [5+3k] / [6+3k] work-item counters of the fast / generic pair kernel, [7+3k] clusters the fast kernel left to the generic one.
 void launchDirect(State& st, const double* dPos, bool forces, int emode, bool emitPairs, long long* dForce, long long* dDedq, cudaStream_t s) {
     if (!forces && emode == 0 && !emitPairs) return;
     CellPlan& c = st.cells;
     CellParams cp{st.N, c.nc[0], c.nc[1], c.nc[2], c.ncells, 1.0/st.box.L[0], 1.0/st.box.L[1], 1.0/st.box.L[2], c.csd[0], c.csd[1], c.csd[2]};
     CFX_CUDA(cudaMemsetAsync(st.cellCount, 0, sizeof(int)*(c.ncells + 1), s));
-    CFX_CUDA(cudaMemsetAsync(st.pairCounters + 5, 0, sizeof(unsigned long long)*3, s));
-    cellAssignKernel<<<(st.N + 255)/256, 256, 0, s>>>(cp, dPos, st.qf, st.cellOfAtom, st.userLocal, st.cellCount);
+    CFX_CUDA(cudaMemsetAsync(st.pairCounters + 5, 0, sizeof(unsigned long long)*6, s));
+    cellAssignKernel<<<(st.N + 255)/256, 256, 0, s>>>(cp, dPos, st.qf, st.q, st.cellOfAtom, st.userLocal, st.userLocalD, st.cellCount);
     CFX_LAUNCH_CHECK(); st.launches++;
     cellScanKernel<<<1, 1024, 0, s>>>(c.ncells, st.cellCount, st.cellStart, st.cellFill);
     CFX_LAUNCH_CHECK(); st.launches++;
     cellFillKernel<<<(st.N + 255)/256, 256, 0, s>>>(st.N, st.cellOfAtom, st.cellFill, st.filledUser);
     CFX_LAUNCH_CHECK(); st.launches++;
     cellRankGatherKernel<<<(st.N + 255)/256, 256, 0, s>>>(st.N, c.nc[1], c.nc[2], st.filledUser, st.cellOfAtom, st.cellStart,
-            st.userLocal, st.lj, st.sortedLocal, st.sortedMeta);
+            st.userLocal, st.lj, st.sortedLocal, st.sortedMeta, st.userLocalD, st.ljd, st.sortedLocalD, st.sortedLjD);
     CFX_LAUNCH_CHECK(); st.launches++;
     mark(st, "cell_build", s);
 
@@ -668,6 +802,10 @@ void launchDirect(State& st, const double* dPos, bool forces, int emode, bool em
     pp.dInvLx = 1.0/st.box.L[0]; pp.dInvLy = 1.0/st.box.L[1]; pp.dInvLz = 1.0/st.box.L[2];
     pp.forceFixed = dForce; pp.dedqFixed = dDedq; pp.energyFixed = st.energyFixed;
     pp.wrapList = st.wrapList;
+    pp.sortedLocalD = st.sortedLocalD; pp.sortedLjD = st.sortedLjD;
+    for (int k = 0; k <= E_POLY_DEG; k++) pp.ePoly[k] = st.ePoly[k];
+    pp.eTScale = st.eTScale; pp.ePolyOK = st.ePolyOK;
+    pp.dcsx = c.csd[0]; pp.dcsy = c.csd[1]; pp.dcsz = c.csd[2];
     pp.counters = st.pairCounters; pp.pairBuffer = st.pairBuffer; pp.pairCapacity = (unsigned long long) st.pairCapacity;
     const int groups = pp.groupHi - pp.groupLo;
     if (groups <= 0) return;
@@ -681,22 +819,36 @@ void launchDirect(State& st, const double* dPos, bool forces, int emode, bool em
     if (emitPairs) pp.jSplits = 1;
     const int items = groups*pp.jSplits;
     const bool fast = !c.smallBox;
-    if (fast) {
-        pp.onlyMinImage = 0;
-        pp.workCounter = reinterpret_cast<unsigned int*>(st.pairCounters + 5);
-        const int grid = std::min((items + P_WARPS - 1)/P_WARPS, P_FAST_MINBLOCKS*numSM);
-        if (emitPairs) dispatchPair<true, true>(pp, forces, emode, grid, s);
-        else           dispatchPair<true, false>(pp, forces, emode, grid, s);
+    // An energy+forces call runs two passes: the FP32 force pass (no energy: lean, 5 CTAs per SM) and an energy-only FP64
+    // pass over the half shell. One fused pass was slower (0.295 ms against 0.15 + 0.07 at 32k atoms): the FP64 staging
+    // costs the force loop its occupancy, and an energy needs each pair only once.
+    struct Pass { bool forces; int emode; };
+    Pass passes[2] = {{forces, emode}, {false, 2}};
+    int nPass = 1;
+    if (forces && emode == 2 && !emitPairs) { passes[0].emode = 0; nPass = 2; }
+    for (int k = 0; k < nPass; k++) {
+        unsigned long long* ctr = st.pairCounters + 5 + 3*k;      // [0] fast work items, [1] generic work items, [2] listed clusters
+        pp.wrapList = st.wrapList + (size_t) k*(st.Npad/P_ITILE + 1);
+        pp.wrapCount = ctr + 2;
+        pp.countStats = k == 0 ? 1 : 0;
+        const bool f = passes[k].forces; const int em = passes[k].emode;
+        if (fast) {
+            pp.onlyMinImage = 0;
+            pp.workCounter = reinterpret_cast<unsigned int*>(ctr);
+            const int grid = std::min((items + P_WARPS - 1)/P_WARPS, (em == 2 ? 4 : P_FAST_MINBLOCKS)*numSM);
+            if (emitPairs) dispatchPair<true, true>(pp, f, em, grid, s);
+            else           dispatchPair<true, false>(pp, f, em, grid, s);
+            CFX_LAUNCH_CHECK(); st.launches++;
+        }
+        // every cluster (small boxes), or the few whose stencil wraps onto itself in a large box -- a cluster stretched
+        // over a sparse region -- which the fast kernel listed (it exits at once when there are none)
+        pp.onlyMinImage = fast ? 1 : 0;
+        pp.workCounter = reinterpret_cast<unsigned int*>(ctr + 1);
+        const int grid = std::min((items + P_WARPS - 1)/P_WARPS, 4*numSM);
+        if (emitPairs) dispatchPair<false, true>(pp, f, em, grid, s);
+        else           dispatchPair<false, false>(pp, f, em, grid, s);
         CFX_LAUNCH_CHECK(); st.launches++;
     }
-    // every cluster (small boxes), or the few whose stencil wraps onto itself in a large box -- a cluster stretched over
-    // a sparse region -- which the fast kernel listed (it exits at once when there are none)
-    pp.onlyMinImage = fast ? 1 : 0;
-    pp.workCounter = reinterpret_cast<unsigned int*>(st.pairCounters + 6);
-    const int grid = std::min((items + P_WARPS - 1)/P_WARPS, 4*numSM);
-    if (emitPairs) dispatchPair<false, true>(pp, forces, emode, grid, s);
-    else           dispatchPair<false, false>(pp, forces, emode, grid, s);
-    CFX_LAUNCH_CHECK(); st.launches++;
     mark(st, "direct_pairs", s);
 }
 
