@@ -104,7 +104,7 @@ typedef struct cfx_stats {
     int64_t pair_candidates;    /* distance tests the pair kernel executed                          */
     int64_t kernel_launches;    /* kernels of this library launched by the last evaluation          */
     int32_t cells[3];
-    int32_t reserved;
+    int32_t longest_pair_list;  /* longest per-cluster candidate list built so far (capacity diagnostics) */
 } cfx_stats;
 
 const char* cfx_last_error(void);

@@ -41,7 +41,7 @@ class EwaldParams(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("pairs_in_cutoff", C.c_int64), ("pair_candidates", C.c_int64), ("kernel_launches", C.c_int64),
-                ("cells", C.c_int32 * 3), ("reserved", C.c_int32)]
+                ("cells", C.c_int32 * 3), ("longest_pair_list", C.c_int32)]
 
 
 # every symbol include/cfx_b200.h declares (tests check the built library exports all of them)

@@ -71,6 +71,7 @@ void freeCells(State& st) {
     cudaFree(st.pairCounters); cudaFree(st.filledUser); st.filledUser = nullptr;
     cudaFree(st.wrapList); st.wrapList = nullptr;
     cudaFree(st.userLocalD); cudaFree(st.sortedLocalD); cudaFree(st.sortedLjD);
+    cudaFree(st.pairList); cudaFree(st.listCount); st.pairList = nullptr; st.listCount = nullptr; st.pairListEntries = 0;
     st.userLocalD = st.sortedLocalD = nullptr; st.sortedLjD = nullptr;
     st.cellOfAtom = st.cellCount = st.cellStart = st.cellFill = nullptr;
     st.userLocal = st.sortedLocal = st.sortedMeta = nullptr; st.pairCounters = nullptr;
@@ -350,6 +351,8 @@ int cfx_create(const cfx_system_desc* d, const cfx_options* opts, cfx_handle** o
     CFX_CUDA(cudaMallocHost(&st.hPos, sizeof(double)*3*std::max(N, 1)));
     CFX_CUDA(cudaMallocHost(&st.hForce, sizeof(double)*3*std::max(N, 1)));
     CFX_CUDA(cudaMallocHost(&st.hEnergy, sizeof(double)*CFX_E_COUNT));
+    CFX_CUDA(cudaMallocHost(&st.hListOverflow, sizeof(unsigned long long)));
+    *st.hListOverflow = 0;
 
     if (st.pbc) {
         checkBox(d->default_box);
@@ -397,6 +400,7 @@ void cfx_destroy(cfx_handle* h) {
     if (st.hPos) cudaFreeHost(st.hPos);
     if (st.hForce) cudaFreeHost(st.hForce);
     if (st.hEnergy) cudaFreeHost(st.hEnergy);
+    if (st.hListOverflow) cudaFreeHost(st.hListOverflow);
     for (cudaEvent_t e : st.timeEvents) cudaEventDestroy(e);
     if (st.evFork) cudaEventDestroy(st.evFork);
     if (st.evJoin) cudaEventDestroy(st.evJoin);
@@ -458,6 +462,8 @@ int cfx_execute(cfx_handle* h, const double* positions, const double* box, int i
         else
             CFX_CUDA(cudaMemcpyAsync(st.hForce, st.forceOut, vecBytes, cudaMemcpyDeviceToHost, s));
         CFX_CUDA(cudaMemcpyAsync(st.hEnergy, st.energyOut, sizeof(double)*CFX_E_COUNT, cudaMemcpyDeviceToHost, s));
+        if (st.pbc && st.pairCounters)
+            CFX_CUDA(cudaMemcpyAsync(st.hListOverflow, st.pairCounters + 11, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     };
     if (st.useGraph) {
         const void* gp = regP ? positions : nullptr;
@@ -484,6 +490,14 @@ int cfx_execute(cfx_handle* h, const double* positions, const double* box, int i
     CFX_CUDA(cudaStreamSynchronize(s));
     st.evaluated = true;
     st.stagedPosCurrent = true;
+    if (st.pbc && *st.hListOverflow > st.listOverflowSeen) {
+        // some candidate lists outgrew listCap (those clusters went through the generic pair kernel: the result is exact,
+        // only slower): enlarge the lists for the next evaluation
+        st.listOverflowSeen = *st.hListOverflow;
+        st.listCap *= 2;
+        allocPairLists(st);
+        dropGraphs(st);
+    }
     if (energy) memcpy(energy, st.hEnergy, sizeof(double)*CFX_E_COUNT);
     if (forces && !regF)
         for (size_t k = 0; k < 3*(size_t) st.N; k++) forces[k] += st.hForce[k];
@@ -591,12 +605,13 @@ int cfx_get_stats(const cfx_handle* hc, cfx_stats* out) {
     out->kernel_launches = st.launches;
     for (int d = 0; d < 3; d++) out->cells[d] = st.cells.nc[d];
     if (st.pbc && st.evaluated && st.pairCounters) {
-        unsigned long long c[4];
+        unsigned long long c[13];
         CFX_CUDA(cudaSetDevice(st.device));
         CFX_CUDA(cudaDeviceSynchronize());
         CFX_CUDA(cudaMemcpy(c, st.pairCounters, sizeof(c), cudaMemcpyDeviceToHost));
         out->pairs_in_cutoff = (int64_t) (c[0]/2);          // the kernel counts every pair from both sides
         out->pair_candidates = (int64_t) c[1];
+        out->longest_pair_list = (int32_t) c[12];
     }
     return CFX_OK;
     CFX_CATCH

@@ -176,6 +176,10 @@ struct State {
     double4* userLocalD = nullptr; double4* sortedLocalD = nullptr;   // the same in double (+ charge): FP64 pair energies
     double2* sortedLjD = nullptr;       // [N] (sigma/2, 2 sqrt(eps)) in double, sorted order
     double ePoly[25] = {0}; double eTScale = 0; int ePolyOK = 0;   // polynomial of the FP64 pair energies (direct.cu)
+    unsigned int* pairList = nullptr; int* listCount = nullptr;     // candidate lists of the fast pair kernel (direct.cu)
+    size_t pairListEntries = 0; int listCap = 0;
+    unsigned long long listOverflowSeen = 0;
+    unsigned long long* hListOverflow = nullptr;        // pinned copy of pairCounters[11], read after the host call's sync
     int* wrapList = nullptr;            // clusters the fast pair kernel left to the generic one
     int* filledUser = nullptr;          // cell fill in arrival order (input of the rank pass)
     unsigned int* exclMaxR2 = nullptr;  // [Npad] float bits: per atom, largest r2 to an excluded partner (this evaluation)
@@ -232,6 +236,7 @@ double measureTf32Peak(int device, int iters);
 void planKSpaceTensor(State& st);                                                       // kspace_tc.cu
 void launchGatherTensor(State& st, long long* dForce, long long* dDedq, cudaStream_t s);
 void planCells(State& st);
+void allocPairLists(State& st);                                                          // direct.cu: (re)allocate the candidate lists for st.listCap
 void launchDirect(State& st, const double* dPos, bool forces, int energyMode /*0 none, 1 FP32 terms, 2 FP64 terms*/, bool emitPairs, long long* dForce, long long* dDedq, cudaStream_t s); // piece (2)
 void mark(State& st, const char* name, cudaStream_t s);   // per-kernel timing marker (no-op unless st.timing)
 // the kernel sequence of one evaluation (api.cu); skipDiscardedEnergy: do not produce the partial energy the

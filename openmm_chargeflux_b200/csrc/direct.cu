@@ -201,6 +201,9 @@ struct PairParams {
     unsigned int* workCounter;               // dynamic work distribution: next (cluster, column share) item
     int* wrapList;                           // clusters the fast kernel left to the generic one (*wrapCount of them)
     unsigned long long* wrapCount;
+    // candidate lists of the fast path (buildListKernel): for i-cluster g, listCount[g - groupLo] entries (negative: the
+    // cluster is left to the generic kernel) at pairList + (g - groupLo)*listCap, each = sorted index | image code << 27
+    unsigned int* pairList; int* listCount; int listCap;
     int countStats;                          // this pass adds to counters[0..1] (the second pass of an energy+forces call does not)
 };
 
@@ -350,9 +353,10 @@ __global__ void __launch_bounds__(P_WARPS*32, (FAST && EMODE != 2) ? P_FAST_MINB
         const int loY = ominy - 2, nY = min(omaxy - ominy + 5, p.ncy);
         const int loZ = ominz - 2, nZ = min(omaxz - ominz + 5, p.ncz);
         const bool wraps = (omaxx - ominx + 5 > p.ncx) || (omaxy - ominy + 5 > p.ncy) || (omaxz - ominz + 5 > p.ncz);
-        if (FAST && wraps) {                            // left to the generic kernel launched behind this one
-            if (lane == 0 && share == 0) p.wrapList[atomicAdd(p.wrapCount, 1ull)] = g;
-            continue;
+        int listN = 0;
+        if (FAST) {                                     // negative: buildListKernel left the cluster to the generic kernel
+            listN = p.listCount[g - p.groupLo];
+            if (listN < 0) continue;
         }
         const bool minImage = FAST ? false : wraps;
 
@@ -554,91 +558,151 @@ __global__ void __launch_bounds__(P_WARPS*32, (FAST && EMODE != 2) ? P_FAST_MINB
             }
         };
 
-        // walk the stencil columns (x outer, y inner); column `col` belongs to share col % jSplits
-        int cxw = FAST ? wrapOnce(c0x + loX, p.ncx) : modPos(c0x + loX, p.ncx);
-        const int cyw0 = FAST ? wrapOnce(c0y + loY, p.ncy) : modPos(c0y + loY, p.ncy);
-        int shareCtr = 0;
-        for (int ax = 0; ax < nX; ax++) {
-            const float shx = (loX + ax)*p.csx;
-            const float ex0 = fmaxf(0.f, fmaxf(shx - bmaxx, bminx - (shx + p.csx)));
-            int cyw = cyw0;
-            for (int ay = 0; ay < nY; ay++) {
-                const int cyCur = cyw;
-                const bool mine = shareCtr == share;
-                if (++cyw == p.ncy) cyw = 0;
-                if (++shareCtr == nShares) shareCtr = 0;
-                if (!mine) continue;
-                const float shy = (loY + ay)*p.csy;
-                // z range of this column: the cells cut by the sphere of radius rc around the bounding box
-                int zRel0 = loZ, zCount = nZ;
-                if (!minImage) {
-                    const float ey0 = fmaxf(0.f, fmaxf(shy - bmaxy, bminy - (shy + p.csy)));
-                    const float d2 = fmaf(ey0, ey0, ex0*ex0);
-                    if (d2 > rcut2) continue;
-                    const float dzMax = sqrtf(rcut2 - d2) + 1e-4f;
-                    const int za = max(loZ, (int) floorf((bminz - dzMax)*p.invCsz));
-                    const int zb = min(loZ + nZ - 1, (int) floorf((bmaxz + dzMax)*p.invCsz));
-                    zRel0 = za; zCount = zb - za + 1;
-                    if (zCount <= 0) continue;
-                }
-                const int rowCell = (cxw*p.ncy + cyCur)*p.ncz;
-                // unwrapped cell units [zlo, zlo + zCount - 1] -> at most two contiguous wrapped segments
-                const int zlo = c0z + zRel0;
-                const int zloW = FAST ? wrapOnce(zlo, p.ncz) : modPos(zlo, p.ncz);
-                const int nSeg = (zloW + zCount - 1 < p.ncz) ? 1 : 2;
-                for (int sg = 0; sg < nSeg; sg++) {
-                    const int segLo = sg == 0 ? zloW : 0;
-                    const int segHi = sg == 0 ? min(zloW + zCount - 1, p.ncz - 1) : zloW + zCount - 1 - p.ncz;
-                    const int zShift = (sg == 0 ? zlo - zloW : zlo - zloW + p.ncz) - c0z;
-                    const int s1 = p.cellStart[rowCell + segHi + 1];
-                    for (int sb = HALF ? max(p.cellStart[rowCell + segLo], i0 + 1) : p.cellStart[rowCell + segLo]; sb < s1; sb += 32) {
-                        const int s = sb + lane;
-                        bool pass = false, cls = false;
-                        float4 pj = farAway, mj = farAway;
-                        double4 pjD = make_double4(0.0, 0.0, 0.0, 0.0);
-                        if (s < s1) {
-                            const float4 l4 = p.sortedLocal[s];
-                            mj = p.sortedMeta[s];
-                            const int cz = __float_as_int(mj.w) >> (2*CELL_BITS);
-                            pj = make_float4(l4.x + shx, l4.y + shy, fmaf((float) (cz + zShift), p.csz, l4.z), l4.w);
-                            if (EMODE == 2) {
-                                const double4 ld = p.sortedLocalD[s];
-                                pjD = make_double4(ld.x + (loX + ax)*p.dcsx, ld.y + (loY + ay)*p.dcsy, ld.z + (cz + zShift)*p.dcsz, ld.w);
-                            }
-                            if (minImage) pass = true;
-                            else {
-                                const float ex = fmaxf(0.f, fmaxf(bminx - pj.x, pj.x - bmaxx));
-                                const float ey = fmaxf(0.f, fmaxf(bminy - pj.y, pj.y - bmaxy));
-                                const float ez = fmaxf(0.f, fmaxf(bminz - pj.z, pj.z - bmaxz));
-                                pass = fmaf(ez, ez, fmaf(ey, ey, ex*ex)) <= rcut2;
-                            }
-                            cls = anyLJi && mj.y != 0.f;
-                        }
-                        const unsigned int m1 = __ballot_sync(0xffffffffu, pass && cls);
-                        const unsigned int m0 = __ballot_sync(0xffffffffu, pass && !cls);
-                        if (pass) {
-                            const int slot = cls ? ((base1 + count1 + __popc(m1 & lt)) & (P_JCAP - 1)) : ((base0 + count0 + __popc(m0 & lt)) & (P_JCAP - 1));
-                            float* e = &sRing[warp][cls][0][slot];
-                            e[0] = pj.x; e[P_JCAP] = pj.y; e[2*P_JCAP] = pj.z; e[3*P_JCAP] = pj.w; e[4*P_JCAP] = mj.z;
-                            if (cls) { e[5*P_JCAP] = mj.x; e[6*P_JCAP] = mj.y; }
-                            if (EMODE == 2) {
-                                e[7*P_JCAP] = __int_as_float(s);
-                                double* ed = &sRingD[warp][cls][0][slot];
-                                ed[0] = pjD.x; ed[P_JCAP] = pjD.y; ed[2*P_JCAP] = pjD.z; ed[3*P_JCAP] = pjD.w;
-                                if (cls) { const double2 ljj = p.sortedLjD[s]; ed[4*P_JCAP] = ljj.x; ed[5*P_JCAP] = ljj.y; }
-                            }
-                        }
-                        count0 += __popc(m0); count1 += __popc(m1);
+        if (FAST) {
+            // fast path: the candidates of this cluster were listed by buildListKernel (the j atoms within the cutoff of
+            // the cluster's bounding box, in stencil order); a share takes a contiguous range of 32-entry chunks
+            const unsigned int* lst = p.pairList + (size_t) (g - p.groupLo)*p.listCap;
+            const int nChunks = (listN + 31) >> 5;
+            const int chunkLo = (int) ((long long) nChunks*share/nShares), chunkHi = (int) ((long long) nChunks*(share + 1)/nShares);
+            for (int eb = chunkLo*32; eb < chunkHi*32; eb += 32) {
+                const int e = eb + lane;
+                bool pass = false, cls = false;
+                float4 pj = farAway, mj = farAway;
+                double4 pjD = make_double4(0.0, 0.0, 0.0, 0.0);
+                int s = 0;
+                if (e < listN) {
+                    const unsigned int ent = lst[e];
+                    s = (int) (ent & 0x7ffffffu);
+                    pass = !HALF || s > i0;
+                    if (pass) {
+                        const int code = (int) (ent >> 27);
+                        const float4 l4 = p.sortedLocal[s];
+                        mj = p.sortedMeta[s];
+                        const int cj = __float_as_int(mj.w);
+                        const int cz3 = code/9, cy3 = (code - 9*cz3)/3, cx3 = code - 9*cz3 - 3*cy3;
+                        const int offx = (cj & CELL_MASK) - c0x + (cx3 - 1)*p.ncx;
+                        const int offy = ((cj >> CELL_BITS) & CELL_MASK) - c0y + (cy3 - 1)*p.ncy;
+                        const int offz = (cj >> (2*CELL_BITS)) - c0z + (cz3 - 1)*p.ncz;
+                        pj = make_float4(l4.x + offx*p.csx, l4.y + offy*p.csy, fmaf((float) offz, p.csz, l4.z), l4.w);
                         if (EMODE == 2) {
-                            if (m0) { lastHi0 = sb + 31 - __clz(m0); hi0 = max(hi0, lastHi0); }
-                            if (m1) { lastHi1 = sb + 31 - __clz(m1); hi1 = max(hi1, lastHi1); }
+                            const double4 ld = p.sortedLocalD[s];
+                            pjD = make_double4(ld.x + offx*p.dcsx, ld.y + offy*p.dcsy, ld.z + offz*p.dcsz, ld.w);
                         }
-                        nCand += (unsigned int) __popc(m0 | m1);
-                        flush(false);
+                        cls = anyLJi && mj.y != 0.f;
                     }
                 }
+                const unsigned int m1 = __ballot_sync(0xffffffffu, pass && cls);
+                const unsigned int m0 = __ballot_sync(0xffffffffu, pass && !cls);
+                if (pass) {
+                    const int slot = cls ? ((base1 + count1 + __popc(m1 & lt)) & (P_JCAP - 1)) : ((base0 + count0 + __popc(m0 & lt)) & (P_JCAP - 1));
+                    float* er = &sRing[warp][cls][0][slot];
+                    er[0] = pj.x; er[P_JCAP] = pj.y; er[2*P_JCAP] = pj.z; er[3*P_JCAP] = pj.w; er[4*P_JCAP] = mj.z;
+                    if (cls) { er[5*P_JCAP] = mj.x; er[6*P_JCAP] = mj.y; }
+                    if (EMODE == 2) {
+                        er[7*P_JCAP] = __int_as_float(s);
+                        double* ed = &sRingD[warp][cls][0][slot];
+                        ed[0] = pjD.x; ed[P_JCAP] = pjD.y; ed[2*P_JCAP] = pjD.z; ed[3*P_JCAP] = pjD.w;
+                        if (cls) { const double2 ljj = p.sortedLjD[s]; ed[4*P_JCAP] = ljj.x; ed[5*P_JCAP] = ljj.y; }
+                    }
+                }
+                count0 += __popc(m0); count1 += __popc(m1);
+                if (EMODE == 2) {
+                    // (list order is stencil order, not sorted order: the largest index of the chunk, by warp reduction)
+                    const int sm0 = __reduce_max_sync(0xffffffffu, (pass && !cls) ? s : -1);
+                    const int sm1 = __reduce_max_sync(0xffffffffu, (pass && cls) ? s : -1);
+                    if (m0) { lastHi0 = sm0; hi0 = max(hi0, sm0); }
+                    if (m1) { lastHi1 = sm1; hi1 = max(hi1, sm1); }
+                }
+                flush(false);
             }
-            if (++cxw == p.ncx) cxw = 0;
+        }
+        else {
+            // walk the stencil columns (x outer, y inner); column `col` belongs to share col % jSplits
+            int cxw = FAST ? wrapOnce(c0x + loX, p.ncx) : modPos(c0x + loX, p.ncx);
+            const int cyw0 = FAST ? wrapOnce(c0y + loY, p.ncy) : modPos(c0y + loY, p.ncy);
+            int shareCtr = 0;
+            for (int ax = 0; ax < nX; ax++) {
+                const float shx = (loX + ax)*p.csx;
+                const float ex0 = fmaxf(0.f, fmaxf(shx - bmaxx, bminx - (shx + p.csx)));
+                int cyw = cyw0;
+                for (int ay = 0; ay < nY; ay++) {
+                    const int cyCur = cyw;
+                    const bool mine = shareCtr == share;
+                    if (++cyw == p.ncy) cyw = 0;
+                    if (++shareCtr == nShares) shareCtr = 0;
+                    if (!mine) continue;
+                    const float shy = (loY + ay)*p.csy;
+                    // z range of this column: the cells cut by the sphere of radius rc around the bounding box
+                    int zRel0 = loZ, zCount = nZ;
+                    if (!minImage) {
+                        const float ey0 = fmaxf(0.f, fmaxf(shy - bmaxy, bminy - (shy + p.csy)));
+                        const float d2 = fmaf(ey0, ey0, ex0*ex0);
+                        if (d2 > rcut2) continue;
+                        const float dzMax = sqrtf(rcut2 - d2) + 1e-4f;
+                        const int za = max(loZ, (int) floorf((bminz - dzMax)*p.invCsz));
+                        const int zb = min(loZ + nZ - 1, (int) floorf((bmaxz + dzMax)*p.invCsz));
+                        zRel0 = za; zCount = zb - za + 1;
+                        if (zCount <= 0) continue;
+                    }
+                    const int rowCell = (cxw*p.ncy + cyCur)*p.ncz;
+                    // unwrapped cell units [zlo, zlo + zCount - 1] -> at most two contiguous wrapped segments
+                    const int zlo = c0z + zRel0;
+                    const int zloW = FAST ? wrapOnce(zlo, p.ncz) : modPos(zlo, p.ncz);
+                    const int nSeg = (zloW + zCount - 1 < p.ncz) ? 1 : 2;
+                    for (int sg = 0; sg < nSeg; sg++) {
+                        const int segLo = sg == 0 ? zloW : 0;
+                        const int segHi = sg == 0 ? min(zloW + zCount - 1, p.ncz - 1) : zloW + zCount - 1 - p.ncz;
+                        const int zShift = (sg == 0 ? zlo - zloW : zlo - zloW + p.ncz) - c0z;
+                        const int s1 = p.cellStart[rowCell + segHi + 1];
+                        for (int sb = HALF ? max(p.cellStart[rowCell + segLo], i0 + 1) : p.cellStart[rowCell + segLo]; sb < s1; sb += 32) {
+                            const int s = sb + lane;
+                            bool pass = false, cls = false;
+                            float4 pj = farAway, mj = farAway;
+                            double4 pjD = make_double4(0.0, 0.0, 0.0, 0.0);
+                            if (s < s1) {
+                                const float4 l4 = p.sortedLocal[s];
+                                mj = p.sortedMeta[s];
+                                const int cz = __float_as_int(mj.w) >> (2*CELL_BITS);
+                                pj = make_float4(l4.x + shx, l4.y + shy, fmaf((float) (cz + zShift), p.csz, l4.z), l4.w);
+                                if (EMODE == 2) {
+                                    const double4 ld = p.sortedLocalD[s];
+                                    pjD = make_double4(ld.x + (loX + ax)*p.dcsx, ld.y + (loY + ay)*p.dcsy, ld.z + (cz + zShift)*p.dcsz, ld.w);
+                                }
+                                if (minImage) pass = true;
+                                else {
+                                    const float ex = fmaxf(0.f, fmaxf(bminx - pj.x, pj.x - bmaxx));
+                                    const float ey = fmaxf(0.f, fmaxf(bminy - pj.y, pj.y - bmaxy));
+                                    const float ez = fmaxf(0.f, fmaxf(bminz - pj.z, pj.z - bmaxz));
+                                    pass = fmaf(ez, ez, fmaf(ey, ey, ex*ex)) <= rcut2;
+                                }
+                                cls = anyLJi && mj.y != 0.f;
+                            }
+                            const unsigned int m1 = __ballot_sync(0xffffffffu, pass && cls);
+                            const unsigned int m0 = __ballot_sync(0xffffffffu, pass && !cls);
+                            if (pass) {
+                                const int slot = cls ? ((base1 + count1 + __popc(m1 & lt)) & (P_JCAP - 1)) : ((base0 + count0 + __popc(m0 & lt)) & (P_JCAP - 1));
+                                float* e = &sRing[warp][cls][0][slot];
+                                e[0] = pj.x; e[P_JCAP] = pj.y; e[2*P_JCAP] = pj.z; e[3*P_JCAP] = pj.w; e[4*P_JCAP] = mj.z;
+                                if (cls) { e[5*P_JCAP] = mj.x; e[6*P_JCAP] = mj.y; }
+                                if (EMODE == 2) {
+                                    e[7*P_JCAP] = __int_as_float(s);
+                                    double* ed = &sRingD[warp][cls][0][slot];
+                                    ed[0] = pjD.x; ed[P_JCAP] = pjD.y; ed[2*P_JCAP] = pjD.z; ed[3*P_JCAP] = pjD.w;
+                                    if (cls) { const double2 ljj = p.sortedLjD[s]; ed[4*P_JCAP] = ljj.x; ed[5*P_JCAP] = ljj.y; }
+                                }
+                            }
+                            count0 += __popc(m0); count1 += __popc(m1);
+                            if (EMODE == 2) {
+                                if (m0) { lastHi0 = sb + 31 - __clz(m0); hi0 = max(hi0, lastHi0); }
+                                if (m1) { lastHi1 = sb + 31 - __clz(m1); hi1 = max(hi1, lastHi1); }
+                            }
+                            nCand += (unsigned int) __popc(m0 | m1);
+                            flush(false);
+                        }
+                    }
+                }
+                if (++cxw == p.ncx) cxw = 0;
+            }
         }
         flush(true);
 
@@ -667,6 +731,124 @@ __global__ void __launch_bounds__(P_WARPS*32, (FAST && EMODE != 2) ? P_FAST_MINB
         for (int o = 16; o > 0; o >>= 1) nIn += __shfl_xor_sync(0xffffffffu, nIn, o);
         if (lane == 0 && p.countStats) {
             atomicAdd(p.counters + 0, (unsigned long long) nIn);        // ordered pairs: the host halves it
+            if (!FAST) atomicAdd(p.counters + 1, (unsigned long long) nCand*P_ITILE);
+        }
+        __syncwarp();
+    }
+}
+
+// Candidate lists of the fast path. One warp per i-cluster walks the (x, y) columns of the cluster's 5x5 stencil, clips
+// each column's z range to the sphere of radius rc around the cluster's bounding box, tests the column's atoms against
+// the bounding box 32 at a time and appends the ones within the cutoff of the box, ballot-compacted, to the cluster's list:
+// entry = sorted index | image code << 27, code = (sx+1) + 3 (sy+1) + 9 (sz+1) with s the periodic image (in boxes) of the
+// atom's cell as seen from the cluster. The pair passes of the evaluation (force pass, energy pass, pair emission) read
+// the list instead of repeating the search. Clusters whose stencil would wrap onto itself, or whose list outgrows
+// listCap (overflow is counted in counters[11]; the host enlarges the lists for the next evaluation), are put on wrapList
+// and evaluated by the generic pair kernel.
+__global__ void __launch_bounds__(P_WARPS*32) buildListKernel(const __grid_constant__ PairParams p) {
+    const int lane = threadIdx.x & 31;
+    const unsigned int lt = (1u << lane) - 1u;
+    const float rcut2 = p.rc2*1.0001f;
+    const unsigned int totalItems = (unsigned int) (p.groupHi - p.groupLo);
+    for (;;) {
+        unsigned int item = 0;
+        if (lane == 0) item = atomicAdd(p.workCounter, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= totalItems) break;
+        const int g = p.groupLo + (int) item;
+        const int i0 = g*P_ITILE;
+        const int ni = min(P_ITILE, p.N - i0);
+        const int ii = lane & 7;
+        const int iIdx = i0 + (ii < ni ? ii : 0);
+        const int c0 = __float_as_int(p.sortedMeta[i0].w);
+        const int c0x = c0 & CELL_MASK, c0y = (c0 >> CELL_BITS) & CELL_MASK, c0z = c0 >> (2*CELL_BITS);
+        const float4 li = p.sortedLocal[iIdx];
+        const int ci = __float_as_int(p.sortedMeta[iIdx].w);
+        const int ox = wrapNearest((ci & CELL_MASK) - c0x, p.ncx);
+        const int oy = wrapNearest(((ci >> CELL_BITS) & CELL_MASK) - c0y, p.ncy);
+        const int oz = wrapNearest((ci >> (2*CELL_BITS)) - c0z, p.ncz);
+        const float pix = li.x + ox*p.csx, piy = li.y + oy*p.csy, piz = li.z + oz*p.csz;
+        float bminx = pix, bminy = piy, bminz = piz, bmaxx = pix, bmaxy = piy, bmaxz = piz;
+        int ominx = ox, ominy = oy, ominz = oz, omaxx = ox, omaxy = oy, omaxz = oz;
+        #pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {               // lanes l and l + 8 hold the same atom
+            bminx = fminf(bminx, __shfl_xor_sync(0xffffffffu, bminx, o)); bmaxx = fmaxf(bmaxx, __shfl_xor_sync(0xffffffffu, bmaxx, o));
+            bminy = fminf(bminy, __shfl_xor_sync(0xffffffffu, bminy, o)); bmaxy = fmaxf(bmaxy, __shfl_xor_sync(0xffffffffu, bmaxy, o));
+            bminz = fminf(bminz, __shfl_xor_sync(0xffffffffu, bminz, o)); bmaxz = fmaxf(bmaxz, __shfl_xor_sync(0xffffffffu, bmaxz, o));
+            ominx = min(ominx, __shfl_xor_sync(0xffffffffu, ominx, o)); omaxx = max(omaxx, __shfl_xor_sync(0xffffffffu, omaxx, o));
+            ominy = min(ominy, __shfl_xor_sync(0xffffffffu, ominy, o)); omaxy = max(omaxy, __shfl_xor_sync(0xffffffffu, omaxy, o));
+            ominz = min(ominz, __shfl_xor_sync(0xffffffffu, ominz, o)); omaxz = max(omaxz, __shfl_xor_sync(0xffffffffu, omaxz, o));
+        }
+        const int loX = ominx - 2, nX = omaxx - ominx + 5;
+        const int loY = ominy - 2, nY = omaxy - ominy + 5;
+        const int loZ = ominz - 2, nZ = omaxz - ominz + 5;
+        unsigned int* lst = p.pairList + (size_t) item*p.listCap;
+        int count = 0;
+        bool giveUp = nX > p.ncx || nY > p.ncy || nZ > p.ncz;      // the stencil would wrap onto itself
+        unsigned int nCand = 0;
+        int cxw = wrapOnce(c0x + loX, p.ncx);
+        const int cyw0 = wrapOnce(c0y + loY, p.ncy);
+        for (int ax = 0; ax < nX && !giveUp; ax++) {
+            const float shx = (loX + ax)*p.csx;
+            const float ex0 = fmaxf(0.f, fmaxf(shx - bmaxx, bminx - (shx + p.csx)));
+            const int ux = c0x + loX + ax;
+            const int codeX = ux < 0 ? 0 : (ux >= p.ncx ? 2 : 1);
+            int cyw = cyw0;
+            for (int ay = 0; ay < nY && !giveUp; ay++) {
+                const int cyCur = cyw;
+                if (++cyw == p.ncy) cyw = 0;
+                const float shy = (loY + ay)*p.csy;
+                const float ey0 = fmaxf(0.f, fmaxf(shy - bmaxy, bminy - (shy + p.csy)));
+                const float d2 = fmaf(ey0, ey0, ex0*ex0);
+                if (d2 > rcut2) continue;
+                const float dzMax = sqrtf(rcut2 - d2) + 1e-4f;
+                const int za = max(loZ, (int) floorf((bminz - dzMax)*p.invCsz));
+                const int zb = min(loZ + nZ - 1, (int) floorf((bmaxz + dzMax)*p.invCsz));
+                const int zCount = zb - za + 1;
+                if (zCount <= 0) continue;
+                const int uy = c0y + loY + ay;
+                const int codeXY = codeX + 3*(uy < 0 ? 0 : (uy >= p.ncy ? 2 : 1));
+                const int rowCell = (cxw*p.ncy + cyCur)*p.ncz;
+                const int zlo = c0z + za;
+                const int zloW = wrapOnce(zlo, p.ncz);
+                const int nSeg = (zloW + zCount - 1 < p.ncz) ? 1 : 2;
+                for (int sg = 0; sg < nSeg && !giveUp; sg++) {
+                    const int segLo = sg == 0 ? zloW : 0;
+                    const int segHi = sg == 0 ? min(zloW + zCount - 1, p.ncz - 1) : zloW + zCount - 1 - p.ncz;
+                    const int zImage = (sg == 0 ? zlo - zloW : zlo - zloW + p.ncz);        // multiple of ncz: -ncz, 0 or ncz
+                    const int zShift = zImage - c0z;
+                    const unsigned int code = (unsigned int) (codeXY + 9*(zImage < 0 ? 0 : (zImage > 0 ? 2 : 1))) << 27;
+                    const int s1 = p.cellStart[rowCell + segHi + 1];
+                    for (int sb = p.cellStart[rowCell + segLo]; sb < s1; sb += 32) {
+                        const int s = sb + lane;
+                        bool pass = false;
+                        if (s < s1) {
+                            const float4 l4 = p.sortedLocal[s];
+                            const int cz = __float_as_int(p.sortedMeta[s].w) >> (2*CELL_BITS);
+                            const float x = l4.x + shx, y = l4.y + shy, z = fmaf((float) (cz + zShift), p.csz, l4.z);
+                            const float ex = fmaxf(0.f, fmaxf(bminx - x, x - bmaxx));
+                            const float ey = fmaxf(0.f, fmaxf(bminy - y, y - bmaxy));
+                            const float ez = fmaxf(0.f, fmaxf(bminz - z, z - bmaxz));
+                            pass = fmaf(ez, ez, fmaf(ey, ey, ex*ex)) <= rcut2;
+                        }
+                        const unsigned int m = __ballot_sync(0xffffffffu, pass);
+                        const int k = __popc(m);
+                        if (count + k > p.listCap) { giveUp = true; break; }
+                        if (pass) lst[count + __popc(m & lt)] = (unsigned int) s | code;
+                        count += k;
+                    }
+                }
+            }
+            if (++cxw == p.ncx) cxw = 0;
+        }
+        nCand = (unsigned int) count;
+        if (lane == 0) {
+            if (giveUp) {
+                p.wrapList[atomicAdd(p.wrapCount, 1ull)] = g;
+                if (!(nX > p.ncx || nY > p.ncy || nZ > p.ncz)) atomicAdd(p.counters + 11, 1ull);     // list overflow
+            }
+            p.listCount[item] = giveUp ? -1 : count;
+            atomicMax(p.counters + 12, (unsigned long long) count);                                   // longest list so far
             atomicAdd(p.counters + 1, (unsigned long long) nCand*P_ITILE);
         }
         __syncwarp();
@@ -732,6 +914,19 @@ static void fitEnergyPolynomial(const State& st, double* coef, double* tScale, i
     *ok = worst < 1e-10L ? 1 : 0;
 }
 
+// candidate lists of this rank's i-clusters (fast path only), listCap entries each
+void allocPairLists(State& st) {
+    cudaFree(st.pairList); cudaFree(st.listCount);
+    st.pairList = nullptr; st.listCount = nullptr; st.pairListEntries = 0;
+    if (st.cells.smallBox) return;
+    const int numGroups = (st.N + P_ITILE - 1)/P_ITILE;
+    const int lo = (int) ((int64_t) numGroups*st.shardRank/st.shardCount), hi = (int) ((int64_t) numGroups*(st.shardRank + 1)/st.shardCount);
+    const size_t groups = (size_t) std::max(hi - lo, 1);
+    CFX_CUDA(cudaMalloc(&st.pairList, sizeof(unsigned int)*groups*st.listCap));
+    CFX_CUDA(cudaMalloc(&st.listCount, sizeof(int)*groups));
+    st.pairListEntries = groups*st.listCap;
+}
+
 void planCells(State& st) {
     CellPlan& c = st.cells;
     c.smallBox = false;
@@ -758,13 +953,20 @@ void planCells(State& st) {
     CFX_CUDA(cudaMalloc(&st.sortedLjD, sizeof(double2)*st.Npad));
     static_assert(E_POLY_DEG + 1 <= sizeof(st.ePoly)/sizeof(double), "State::ePoly too small");
     fitEnergyPolynomial(st, st.ePoly, &st.eTScale, &st.ePolyOK);
-    CFX_CUDA(cudaMalloc(&st.wrapList, sizeof(int)*2*(st.Npad/P_ITILE + 1)));
+    CFX_CUDA(cudaMalloc(&st.wrapList, sizeof(int)*(st.Npad/P_ITILE + 1)));
+    if (st.listCap <= 0) {
+        st.listCap = 4096;                               // ~4x the candidates of a cluster in liquid water at rc = 1 nm
+        if (const char* e = getenv("CFX_LIST_CAP")) st.listCap = std::max(32, atoi(e));
+    }
+    allocPairLists(st);
     CFX_CUDA(cudaMalloc(&st.pairCounters, sizeof(unsigned long long)*16));
     CFX_CUDA(cudaMemset(st.pairCounters, 0, sizeof(unsigned long long)*16));
 }
 
-// pairCounters (16 x u64): [0] in-cutoff ordered pairs, [1] distance tests, [2] emitted pairs; per pass k of an evaluation
-// [5+3k] / [6+3k] work-item counters of the fast / generic pair kernel, [7+3k] clusters the fast kernel left to the generic one.
+// pairCounters (16 x u64): [0] in-cutoff ordered pairs, [1] distance tests, [2] emitted pairs; work-item counters of the
+// fast / generic pair kernel: [5] / [6] (first pass), [8] / [9] (energy pass of an energy+forces call), [10] list builder;
+// [7] clusters left to the generic kernel; [11] list overflows so far (not reset: the host enlarges listCap when it grows);
+// [12] longest candidate list so far.
 void launchDirect(State& st, const double* dPos, bool forces, int emode, bool emitPairs, long long* dForce, long long* dDedq, cudaStream_t s) {
     if (!forces && emode == 0 && !emitPairs) return;
     CellPlan& c = st.cells;
@@ -822,14 +1024,25 @@ void launchDirect(State& st, const double* dPos, bool forces, int emode, bool em
     // An energy+forces call runs two passes: the FP32 force pass (no energy: lean, 5 CTAs per SM) and an energy-only FP64
     // pass over the half shell. One fused pass was slower (0.295 ms against 0.15 + 0.07 at 32k atoms): the FP64 staging
     // costs the force loop its occupancy, and an energy needs each pair only once.
+    if (fast) {
+        // candidate lists, shared by every pair pass of this evaluation
+        pp.pairList = st.pairList; pp.listCount = st.listCount; pp.listCap = st.listCap;
+        pp.wrapList = st.wrapList; pp.wrapCount = st.pairCounters + 7;
+        pp.workCounter = reinterpret_cast<unsigned int*>(st.pairCounters + 10);
+        buildListKernel<<<std::min((groups + P_WARPS - 1)/P_WARPS, 8*numSM), P_WARPS*32, 0, s>>>(pp);
+        CFX_LAUNCH_CHECK(); st.launches++;
+        mark(st, "pair_list", s);
+    }
+    // An energy+forces call runs two passes: the FP32 force pass (no energy: lean, 5 CTAs per SM) and an energy-only FP64
+    // pass over the half shell. One fused pass was slower: the FP64 staging costs the force loop its occupancy, and an
+    // energy needs each pair only once.
     struct Pass { bool forces; int emode; };
     Pass passes[2] = {{forces, emode}, {false, 2}};
     int nPass = 1;
     if (forces && emode == 2 && !emitPairs) { passes[0].emode = 0; nPass = 2; }
+    pp.wrapList = st.wrapList; pp.wrapCount = st.pairCounters + 7;
     for (int k = 0; k < nPass; k++) {
-        unsigned long long* ctr = st.pairCounters + 5 + 3*k;      // [0] fast work items, [1] generic work items, [2] listed clusters
-        pp.wrapList = st.wrapList + (size_t) k*(st.Npad/P_ITILE + 1);
-        pp.wrapCount = ctr + 2;
+        unsigned long long* ctr = st.pairCounters + (k == 0 ? 5 : 8);      // [0] fast work items, [1] generic work items
         pp.countStats = k == 0 ? 1 : 0;
         const bool f = passes[k].forces; const int em = passes[k].emode;
         if (fast) {
@@ -840,8 +1053,8 @@ void launchDirect(State& st, const double* dPos, bool forces, int emode, bool em
             else           dispatchPair<true, false>(pp, f, em, grid, s);
             CFX_LAUNCH_CHECK(); st.launches++;
         }
-        // every cluster (small boxes), or the few whose stencil wraps onto itself in a large box -- a cluster stretched
-        // over a sparse region -- which the fast kernel listed (it exits at once when there are none)
+        // every cluster (small boxes), or the few the list builder left out in a large box -- a cluster stretched over a
+        // sparse region, whose stencil wraps onto itself, or a list overflow -- (it exits at once when there are none)
         pp.onlyMinImage = fast ? 1 : 0;
         pp.workCounter = reinterpret_cast<unsigned int*>(ctr + 1);
         const int grid = std::min((items + P_WARPS - 1)/P_WARPS, 4*numSM);
