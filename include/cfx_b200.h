@@ -86,7 +86,10 @@ typedef struct cfx_options {
     int32_t shard_count;   /* number of ranks sharing one evaluation (1 = whole evaluation here)     */
     int32_t use_graph;     /* 1 = replay the step as one CUDA graph (default), 0 = plain launches    */
     int32_t flags;         /* CFX_OPT_* bits                                                         */
-    int32_t reserved[3];
+    int32_t list_skin_pm;  /* skin of the direct-space candidate lists in picometres: the lists are built for
+                              cutoff + skin and reused until an atom has moved skin/2 (the in-cutoff test itself is
+                              exact every call). 0 = default (100 pm), negative = rebuild at every evaluation        */
+    int32_t reserved[2];
 } cfx_options;
 
 typedef struct cfx_handle cfx_handle;
@@ -102,9 +105,11 @@ typedef struct cfx_ewald_params {
 typedef struct cfx_stats {
     int64_t pairs_in_cutoff;    /* in-cutoff, non-excluded i<j pairs of the last evaluation         */
     int64_t pair_candidates;    /* distance tests the pair kernel executed                          */
-    int64_t kernel_launches;    /* kernels of this library launched by the last evaluation          */
+    int64_t kernel_launches;    /* kernels of this library launched by the last evaluation (some return at once when the
+                                   candidate lists are reused)                                       */
     int32_t cells[3];
     int32_t longest_pair_list;  /* longest per-cluster candidate list built so far (capacity diagnostics) */
+    int64_t pair_list_builds;   /* how many evaluations of this handle re-sorted the atoms and rebuilt the lists */
 } cfx_stats;
 
 const char* cfx_last_error(void);

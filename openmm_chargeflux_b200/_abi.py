@@ -32,7 +32,7 @@ class SystemDesc(C.Structure):
 
 class Options(C.Structure):
     _fields_ = [("device", C.c_int32), ("shard_rank", C.c_int32), ("shard_count", C.c_int32),
-                ("use_graph", C.c_int32), ("flags", C.c_int32), ("reserved", C.c_int32 * 3)]
+                ("use_graph", C.c_int32), ("flags", C.c_int32), ("list_skin_pm", C.c_int32), ("reserved", C.c_int32 * 2)]
 
 
 class EwaldParams(C.Structure):
@@ -41,7 +41,7 @@ class EwaldParams(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("pairs_in_cutoff", C.c_int64), ("pair_candidates", C.c_int64), ("kernel_launches", C.c_int64),
-                ("cells", C.c_int32 * 3), ("longest_pair_list", C.c_int32)]
+                ("cells", C.c_int32 * 3), ("longest_pair_list", C.c_int32), ("pair_list_builds", C.c_int64)]
 
 
 # every symbol include/cfx_b200.h declares (tests check the built library exports all of them)

@@ -72,6 +72,7 @@ void freeCells(State& st) {
     cudaFree(st.wrapList); st.wrapList = nullptr;
     cudaFree(st.userLocalD); cudaFree(st.sortedLocalD); cudaFree(st.sortedLjD);
     cudaFree(st.pairList); cudaFree(st.listCount); st.pairList = nullptr; st.listCount = nullptr; st.pairListEntries = 0;
+    cudaFree(st.rebuildFlag); cudaFree(st.posAtBuild); st.rebuildFlag = nullptr; st.posAtBuild = nullptr;
     st.userLocalD = st.sortedLocalD = nullptr; st.sortedLjD = nullptr;
     st.cellOfAtom = st.cellCount = st.cellStart = st.cellFill = nullptr;
     st.userLocal = st.sortedLocal = st.sortedMeta = nullptr; st.pairCounters = nullptr;
@@ -176,7 +177,7 @@ void ensureCells(State& st) {
     // the cell grid depends on the current box
     int nc[3];
     for (int d = 0; d < 3; d++)
-        nc[d] = std::max(1, std::min((int) floor(st.box.L[d]/(0.5*st.cutoff)), 1023));
+        nc[d] = cellsPerAxis(st, d);
     if (st.cellCount && nc[0] == st.cells.nc[0] && nc[1] == st.cells.nc[1] && nc[2] == st.cells.nc[2]) {
         for (int d = 0; d < 3; d++) { st.cells.csd[d] = st.box.L[d]/nc[d]; st.cells.cs[d] = (float) st.cells.csd[d]; }
         return;
@@ -189,8 +190,10 @@ void ensureBox(State& st, const double* box) {
     checkBox(box);
     if (box[0] < 2*st.cutoff || box[4] < 2*st.cutoff || box[8] < 2*st.cutoff)
         throw ArgError("the periodic box must be at least twice the cutoff in every direction");
-    if (st.box.L[0] != box[0] || st.box.L[1] != box[4] || st.box.L[2] != box[8]) { setBox(st, box); dropGraphs(st); }
+    const bool changed = st.box.L[0] != box[0] || st.box.L[1] != box[4] || st.box.L[2] != box[8];
+    if (changed) { setBox(st, box); dropGraphs(st); }
     ensureCells(st);
+    if (changed) invalidatePairLists(st);
 }
 
 } // namespace cfx
@@ -248,6 +251,11 @@ int cfx_create(const cfx_system_desc* d, const cfx_options* opts, cfx_handle** o
     st.useGraph = opts ? (opts->use_graph != 0) : true;
     st.pinCallerBuffers = opts && (opts->flags & CFX_OPT_PIN_CALLER_BUFFERS);
     st.skipDiscardedEnergy = opts && (opts->flags & CFX_OPT_SKIP_DISCARDED_ENERGY);
+    {
+        const int pm = opts ? opts->list_skin_pm : 0;
+        st.skin = pm < 0 ? 0.0 : (pm == 0 ? 0.1 : 1e-3*pm);
+        if (const char* e = getenv("CFX_LIST_SKIN")) st.skin = std::max(0.0, atof(e));
+    }
     if (d->use_pbc == 0 && st.shardCount != 1)
         throw ArgError("sharded handles need a periodic system: the non-periodic all-pairs branch is not partitioned");
     st.N = N;
@@ -496,6 +504,7 @@ int cfx_execute(cfx_handle* h, const double* positions, const double* box, int i
         st.listOverflowSeen = *st.hListOverflow;
         st.listCap *= 2;
         allocPairLists(st);
+        invalidatePairLists(st);
         dropGraphs(st);
     }
     if (energy) memcpy(energy, st.hEnergy, sizeof(double)*CFX_E_COUNT);
@@ -605,13 +614,14 @@ int cfx_get_stats(const cfx_handle* hc, cfx_stats* out) {
     out->kernel_launches = st.launches;
     for (int d = 0; d < 3; d++) out->cells[d] = st.cells.nc[d];
     if (st.pbc && st.evaluated && st.pairCounters) {
-        unsigned long long c[13];
+        unsigned long long c[14];
         CFX_CUDA(cudaSetDevice(st.device));
         CFX_CUDA(cudaDeviceSynchronize());
         CFX_CUDA(cudaMemcpy(c, st.pairCounters, sizeof(c), cudaMemcpyDeviceToHost));
         out->pairs_in_cutoff = (int64_t) (c[0]/2);          // the kernel counts every pair from both sides
         out->pair_candidates = (int64_t) c[1];
         out->longest_pair_list = (int32_t) c[12];
+        out->pair_list_builds = (int64_t) c[13];
     }
     return CFX_OK;
     CFX_CATCH
@@ -879,6 +889,7 @@ int cfx_update_parameters(cfx_handle* h, const cfx_system_desc* d) {
     CFX_CUDA(cudaMemcpy(st.lj, lj.data(), sizeof(float2)*N, cudaMemcpyHostToDevice));
     CFX_CUDA(cudaMemcpy(st.ljd, ljd.data(), sizeof(double2)*N, cudaMemcpyHostToDevice));
     if (st.numTerms) CFX_CUDA(cudaMemcpy(st.termPar, termPar.data(), sizeof(double)*termPar.size(), cudaMemcpyHostToDevice));
+    if (st.pbc) invalidatePairLists(st);                 // the sorted records carry the LJ parameters
     st.evaluated = false;
     return CFX_OK;
     CFX_CATCH

@@ -178,6 +178,9 @@ struct State {
     double ePoly[25] = {0}; double eTScale = 0; int ePolyOK = 0;   // polynomial of the FP64 pair energies (direct.cu)
     unsigned int* pairList = nullptr; int* listCount = nullptr;     // candidate lists of the fast pair kernel (direct.cu)
     size_t pairListEntries = 0; int listCap = 0;
+    double skin = 0.0;                  // lists are built for cutoff + skin and reused until an atom has moved skin/2 (0: rebuilt every evaluation)
+    int* rebuildFlag = nullptr;         // device: non-zero = this evaluation re-sorts the atoms and rebuilds the lists
+    double* posAtBuild = nullptr;       // [3N] positions the lists were built from
     unsigned long long listOverflowSeen = 0;
     unsigned long long* hListOverflow = nullptr;        // pinned copy of pairCounters[11], read after the host call's sync
     int* wrapList = nullptr;            // clusters the fast pair kernel left to the generic one
@@ -236,7 +239,9 @@ double measureTf32Peak(int device, int iters);
 void planKSpaceTensor(State& st);                                                       // kspace_tc.cu
 void launchGatherTensor(State& st, long long* dForce, long long* dDedq, cudaStream_t s);
 void planCells(State& st);
-void allocPairLists(State& st);                                                          // direct.cu: (re)allocate the candidate lists for st.listCap
+void allocPairLists(State& st);
+int cellsPerAxis(const State& st, int d);                                                // direct.cu: cell grid for the current box
+void invalidatePairLists(State& st);                                                     // direct.cu: the next evaluation rebuilds                                                          // direct.cu: (re)allocate the candidate lists for st.listCap
 void launchDirect(State& st, const double* dPos, bool forces, int energyMode /*0 none, 1 FP32 terms, 2 FP64 terms*/, bool emitPairs, long long* dForce, long long* dDedq, cudaStream_t s); // piece (2)
 void mark(State& st, const char* name, cudaStream_t s);   // per-kernel timing marker (no-op unless st.timing)
 // the kernel sequence of one evaluation (api.cu); skipDiscardedEnergy: do not produce the partial energy the

@@ -52,11 +52,15 @@ struct CellParams {
 };
 
 // wrap, bin, cell-local coordinates; counts per cell
-__global__ void __launch_bounds__(256) cellAssignKernel(CellParams p, const double* __restrict__ pos, const float* __restrict__ qf,
-        const double* __restrict__ qd, int* __restrict__ cellOfAtom, float4* __restrict__ userLocal, double4* __restrict__ userLocalD,
-        int* __restrict__ cellCount) {
+// The cell-build kernels and the list builder run only in evaluations whose rebuild flag is set (displacementKernel):
+// the launches stay in the step's CUDA graph and return at once otherwise.
+__global__ void __launch_bounds__(256) cellAssignKernel(CellParams p, const int* __restrict__ rebuildFlag, const double* __restrict__ pos,
+        const float* __restrict__ qf, const double* __restrict__ qd, int* __restrict__ cellOfAtom, float4* __restrict__ userLocal,
+        double4* __restrict__ userLocalD, int* __restrict__ cellCount, double* __restrict__ posAtBuild) {
+    if (!*rebuildFlag) return;
     const int i = blockIdx.x*blockDim.x + threadIdx.x;
     if (i >= p.N) return;
+    posAtBuild[3*(size_t) i] = pos[3*(size_t) i]; posAtBuild[3*(size_t) i + 1] = pos[3*(size_t) i + 1]; posAtBuild[3*(size_t) i + 2] = pos[3*(size_t) i + 2];
     double u[3] = {pos[3*(size_t) i]*p.invLx, pos[3*(size_t) i + 1]*p.invLy, pos[3*(size_t) i + 2]*p.invLz};
     const int nc[3] = {p.ncx, p.ncy, p.ncz};
     const double cs[3] = {p.csx, p.csy, p.csz};
@@ -79,8 +83,10 @@ __global__ void __launch_bounds__(256) cellAssignKernel(CellParams p, const doub
 }
 
 // exclusive scan of cellCount -> cellStart (single CTA; ncells is at most a few 10^4)
-__global__ void __launch_bounds__(1024) cellScanKernel(int ncells, const int* __restrict__ cellCount, int* __restrict__ cellStart,
-        int* __restrict__ cellFill) {
+__global__ void __launch_bounds__(1024) cellScanKernel(int ncells, const int* __restrict__ rebuildFlag, const int* __restrict__ cellCount,
+        int* __restrict__ cellStart, int* __restrict__ cellFill, unsigned long long* __restrict__ wrapCount) {
+    if (!*rebuildFlag) return;
+    if (threadIdx.x == 0) *wrapCount = 0ull;               // the list builder behind this kernel refills the generic kernel's list
     __shared__ int warpTotals[32];
     __shared__ int carry;
     if (threadIdx.x == 0) carry = 0;
@@ -116,8 +122,9 @@ __global__ void __launch_bounds__(1024) cellScanKernel(int ncells, const int* __
     if (threadIdx.x == 0) cellStart[ncells] = carry;
 }
 
-__global__ void __launch_bounds__(256) cellFillKernel(int N, const int* __restrict__ cellOfAtom, int* __restrict__ cellFill,
-        int* __restrict__ sortedUser) {
+__global__ void __launch_bounds__(256) cellFillKernel(int N, const int* __restrict__ rebuildFlag, const int* __restrict__ cellOfAtom,
+        int* __restrict__ cellFill, int* __restrict__ sortedUser) {
+    if (!*rebuildFlag) return;
     const int i = blockIdx.x*blockDim.x + threadIdx.x;
     if (i >= N) return;
     const int slot = atomicAdd(cellFill + cellOfAtom[i], 1);
@@ -129,11 +136,12 @@ __global__ void __launch_bounds__(256) cellFillKernel(int N, const int* __restri
 // accumulation order downstream -- is deterministic, and a column of cells is one z-ordered run. Writes both sorted
 // records in one pass: sortedLocal = (x, y, z inside the cell, q), sortedMeta = (sigma/2, 2 sqrt(eps), user index,
 // packed cell coordinates).
-__global__ void __launch_bounds__(256) cellRankGatherKernel(int N, int ncy, int ncz, const int* __restrict__ filledUser,
+__global__ void __launch_bounds__(256) cellRankGatherKernel(int N, int ncy, int ncz, const int* __restrict__ rebuildFlag, const int* __restrict__ filledUser,
         const int* __restrict__ cellOfAtom, const int* __restrict__ cellStart, const float4* __restrict__ userLocal,
         const float2* __restrict__ lj, float4* __restrict__ sortedLocal, float4* __restrict__ sortedMeta,
         const double4* __restrict__ userLocalD, const double2* __restrict__ ljd, double4* __restrict__ sortedLocalD,
         double2* __restrict__ sortedLjD) {
+    if (!*rebuildFlag) return;
     const int s = blockIdx.x*blockDim.x + threadIdx.x;
     if (s >= N) return;
     const int u = filledUser[s];
@@ -153,6 +161,48 @@ __global__ void __launch_bounds__(256) cellRankGatherKernel(int N, int ncy, int 
     sortedLocalD[dst] = userLocalD[u];
     sortedLjD[dst] = ljd[u];
     sortedMeta[dst] = make_float4(l.x, l.y, __int_as_float(u), __int_as_float(cx | (cy << CELL_BITS) | (cz << (2*CELL_BITS))));
+}
+
+// Has any atom moved more than skin/2 (minimum image) since the lists were built? Then this evaluation rebuilds.
+__global__ void __launch_bounds__(256) displacementKernel(int N, const double* __restrict__ pos, const double* __restrict__ posAtBuild,
+        double Lx, double Ly, double Lz, double limit2, int* __restrict__ rebuildFlag) {
+    const int i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= N || *rebuildFlag) return;
+    double dx = pos[3*(size_t) i] - posAtBuild[3*(size_t) i];
+    double dy = pos[3*(size_t) i + 1] - posAtBuild[3*(size_t) i + 1];
+    double dz = pos[3*(size_t) i + 2] - posAtBuild[3*(size_t) i + 2];
+    dx -= Lx*rint(dx/Lx); dy -= Ly*rint(dy/Ly); dz -= Lz*rint(dz/Lz);
+    if (!(dx*dx + dy*dy + dz*dz <= limit2)) *rebuildFlag = 1;          // (NaN positions rebuild too)
+}
+
+// Evaluations that reuse the lists keep the atoms in the order of the last build: the sorted records get this
+// evaluation's coordinates -- relative to the cell the atom was in at the build, so slightly outside [0, cell size) --
+// and charges. Runs in every evaluation (the charges change with the geometry).
+__global__ void __launch_bounds__(256) refreshSortedKernel(CellParams p, const double* __restrict__ pos, const float* __restrict__ qf,
+        const double* __restrict__ qd, float4* __restrict__ sortedLocal, const float4* __restrict__ sortedMeta, double4* __restrict__ sortedLocalD) {
+    const int s = blockIdx.x*blockDim.x + threadIdx.x;
+    if (s >= p.N) return;
+    const float4 m = sortedMeta[s];
+    const int u = __float_as_int(m.z), cj = __float_as_int(m.w);
+    const int c[3] = {cj & CELL_MASK, (cj >> CELL_BITS) & CELL_MASK, cj >> (2*CELL_BITS)};
+    const double uu[3] = {pos[3*(size_t) u]*p.invLx, pos[3*(size_t) u + 1]*p.invLy, pos[3*(size_t) u + 2]*p.invLz};
+    const int nc[3] = {p.ncx, p.ncy, p.ncz};
+    const double cs[3] = {p.csx, p.csy, p.csz};
+    double loc[3];
+    #pragma unroll
+    for (int d = 0; d < 3; d++) {
+        const double f = uu[d] - floor(uu[d]);
+        double g = f*nc[d] - c[d];                                     // in cells, relative to the build-time cell
+        if (g > 0.5*nc[d]) g -= nc[d];
+        if (g < -0.5*nc[d]) g += nc[d];
+        loc[d] = g*cs[d];
+    }
+    sortedLocal[s] = make_float4((float) loc[0], (float) loc[1], (float) loc[2], qf[u]);
+    sortedLocalD[s] = make_double4(loc[0], loc[1], loc[2], qd[u]);
+}
+
+__global__ void finishListKernel(int* __restrict__ rebuildFlag, unsigned long long* __restrict__ counters) {
+    if (threadIdx.x == 0 && blockIdx.x == 0 && *rebuildFlag) { *rebuildFlag = 0; counters[13] += 1ull; }     // [13]: list builds so far
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -204,6 +254,9 @@ struct PairParams {
     // candidate lists of the fast path (buildListKernel): for i-cluster g, listCount[g - groupLo] entries (negative: the
     // cluster is left to the generic kernel) at pairList + (g - groupLo)*listCap, each = sorted index | image code << 27
     unsigned int* pairList; int* listCount; int listCap;
+    const int* rebuildFlag;                  // list builder: return at once unless set
+    float rlist2;                            // (cutoff + skin)^2: what the lists are built for
+    float drift;                             // skin/2: how far an atom may be outside the cell it was sorted into
     int countStats;                          // this pass adds to counters[0..1] (the second pass of an energy+forces call does not)
 };
 
@@ -584,7 +637,13 @@ __global__ void __launch_bounds__(P_WARPS*32, (FAST && EMODE != 2) ? P_FAST_MINB
                         const int offy = ((cj >> CELL_BITS) & CELL_MASK) - c0y + (cy3 - 1)*p.ncy;
                         const int offz = (cj >> (2*CELL_BITS)) - c0z + (cz3 - 1)*p.ncz;
                         pj = make_float4(l4.x + offx*p.csx, l4.y + offy*p.csy, fmaf((float) offz, p.csz, l4.z), l4.w);
-                        if (EMODE == 2) {
+                        // the list was built for cutoff + skin around the bounding box of that time: keep what is within
+                        // the cutoff of the box now
+                        const float ex = fmaxf(0.f, fmaxf(bminx - pj.x, pj.x - bmaxx));
+                        const float ey = fmaxf(0.f, fmaxf(bminy - pj.y, pj.y - bmaxy));
+                        const float ez = fmaxf(0.f, fmaxf(bminz - pj.z, pj.z - bmaxz));
+                        pass = fmaf(ez, ez, fmaf(ey, ey, ex*ex)) <= rcut2;
+                        if (EMODE == 2 && pass) {
                             const double4 ld = p.sortedLocalD[s];
                             pjD = make_double4(ld.x + offx*p.dcsx, ld.y + offy*p.dcsy, ld.z + offz*p.dcsz, ld.w);
                         }
@@ -623,7 +682,8 @@ __global__ void __launch_bounds__(P_WARPS*32, (FAST && EMODE != 2) ? P_FAST_MINB
             int shareCtr = 0;
             for (int ax = 0; ax < nX; ax++) {
                 const float shx = (loX + ax)*p.csx;
-                const float ex0 = fmaxf(0.f, fmaxf(shx - bmaxx, bminx - (shx + p.csx)));
+                // (atoms sorted at the last list build may be up to p.drift outside their cell)
+                const float ex0 = fmaxf(0.f, fmaxf(shx - bmaxx, bminx - (shx + p.csx)) - p.drift);
                 int cyw = cyw0;
                 for (int ay = 0; ay < nY; ay++) {
                     const int cyCur = cyw;
@@ -635,10 +695,10 @@ __global__ void __launch_bounds__(P_WARPS*32, (FAST && EMODE != 2) ? P_FAST_MINB
                     // z range of this column: the cells cut by the sphere of radius rc around the bounding box
                     int zRel0 = loZ, zCount = nZ;
                     if (!minImage) {
-                        const float ey0 = fmaxf(0.f, fmaxf(shy - bmaxy, bminy - (shy + p.csy)));
+                        const float ey0 = fmaxf(0.f, fmaxf(shy - bmaxy, bminy - (shy + p.csy)) - p.drift);
                         const float d2 = fmaf(ey0, ey0, ex0*ex0);
                         if (d2 > rcut2) continue;
-                        const float dzMax = sqrtf(rcut2 - d2) + 1e-4f;
+                        const float dzMax = sqrtf(rcut2 - d2) + 1e-4f + p.drift;
                         const int za = max(loZ, (int) floorf((bminz - dzMax)*p.invCsz));
                         const int zb = min(loZ + nZ - 1, (int) floorf((bmaxz + dzMax)*p.invCsz));
                         zRel0 = za; zCount = zb - za + 1;
@@ -746,9 +806,10 @@ __global__ void __launch_bounds__(P_WARPS*32, (FAST && EMODE != 2) ? P_FAST_MINB
 // listCap (overflow is counted in counters[11]; the host enlarges the lists for the next evaluation), are put on wrapList
 // and evaluated by the generic pair kernel.
 __global__ void __launch_bounds__(P_WARPS*32) buildListKernel(const __grid_constant__ PairParams p) {
+    if (!*p.rebuildFlag) return;
     const int lane = threadIdx.x & 31;
     const unsigned int lt = (1u << lane) - 1u;
-    const float rcut2 = p.rc2*1.0001f;
+    const float rcut2 = p.rlist2*1.0001f;
     const unsigned int totalItems = (unsigned int) (p.groupHi - p.groupLo);
     for (;;) {
         unsigned int item = 0;
@@ -927,13 +988,31 @@ void allocPairLists(State& st) {
     st.pairListEntries = groups*st.listCap;
 }
 
+// The skin only applies where the fast (list) path runs: at least 7 cells of edge >= (cutoff + skin)/2 per axis, so
+// that the 5-cell stencil covers cutoff + skin around a cluster and does not wrap onto itself.
+static double effectiveSkin(const State& st) {
+    for (int d = 0; d < 3; d++)
+        if ((int) floor(st.box.L[d]/(0.5*(st.cutoff + st.skin))) < 7) return 0.0;
+    return st.skin;
+}
+
+int cellsPerAxis(const State& st, int d) {
+    const int n = (int) floor(st.box.L[d]/(0.5*(st.cutoff + effectiveSkin(st))));
+    return std::max(1, std::min(n, CELL_MASK));
+}
+
+void invalidatePairLists(State& st) {
+    if (!st.rebuildFlag) return;
+    CFX_CUDA(cudaDeviceSynchronize());
+    CFX_CUDA(cudaMemset(st.rebuildFlag, 1, sizeof(int)));
+}
+
 void planCells(State& st) {
     CellPlan& c = st.cells;
     c.smallBox = false;
     c.ncells = 1;
     for (int d = 0; d < 3; d++) {
-        int n = (int) floor(st.box.L[d]/(0.5*st.cutoff));
-        n = std::max(1, std::min(n, CELL_MASK));
+        int n = cellsPerAxis(st, d);
         c.nc[d] = n;
         c.csd[d] = st.box.L[d]/n;
         c.cs[d] = (float) c.csd[d];
@@ -959,6 +1038,9 @@ void planCells(State& st) {
         if (const char* e = getenv("CFX_LIST_CAP")) st.listCap = std::max(32, atoi(e));
     }
     allocPairLists(st);
+    CFX_CUDA(cudaMalloc(&st.rebuildFlag, sizeof(int)));
+    CFX_CUDA(cudaMemset(st.rebuildFlag, 1, sizeof(int)));
+    CFX_CUDA(cudaMalloc(&st.posAtBuild, sizeof(double)*3*st.Npad));
     CFX_CUDA(cudaMalloc(&st.pairCounters, sizeof(unsigned long long)*16));
     CFX_CUDA(cudaMemset(st.pairCounters, 0, sizeof(unsigned long long)*16));
 }
@@ -966,21 +1048,35 @@ void planCells(State& st) {
 // pairCounters (16 x u64): [0] in-cutoff ordered pairs, [1] distance tests, [2] emitted pairs; work-item counters of the
 // fast / generic pair kernel: [5] / [6] (first pass), [8] / [9] (energy pass of an energy+forces call), [10] list builder;
 // [7] clusters left to the generic kernel; [11] list overflows so far (not reset: the host enlarges listCap when it grows);
-// [12] longest candidate list so far.
+// [12] longest candidate list so far; [13] list builds so far.
 void launchDirect(State& st, const double* dPos, bool forces, int emode, bool emitPairs, long long* dForce, long long* dDedq, cudaStream_t s) {
     if (!forces && emode == 0 && !emitPairs) return;
     CellPlan& c = st.cells;
     CellParams cp{st.N, c.nc[0], c.nc[1], c.nc[2], c.ncells, 1.0/st.box.L[0], 1.0/st.box.L[1], 1.0/st.box.L[2], c.csd[0], c.csd[1], c.csd[2]};
+    const double skin = c.smallBox ? 0.0 : effectiveSkin(st);
     CFX_CUDA(cudaMemsetAsync(st.cellCount, 0, sizeof(int)*(c.ncells + 1), s));
-    CFX_CUDA(cudaMemsetAsync(st.pairCounters + 5, 0, sizeof(unsigned long long)*6, s));
-    cellAssignKernel<<<(st.N + 255)/256, 256, 0, s>>>(cp, dPos, st.qf, st.q, st.cellOfAtom, st.userLocal, st.userLocalD, st.cellCount);
+    CFX_CUDA(cudaMemsetAsync(st.pairCounters + 5, 0, sizeof(unsigned long long)*2, s));
+    CFX_CUDA(cudaMemsetAsync(st.pairCounters + 8, 0, sizeof(unsigned long long)*3, s));
+    // Re-sort and rebuild the candidate lists only when an atom has moved skin/2 since the last build (always without a
+    // skin / in small boxes). The flag lives on the device: the guarded kernels stay in the step's graph.
+    if (skin > 0.0) {
+        displacementKernel<<<(st.N + 255)/256, 256, 0, s>>>(st.N, dPos, st.posAtBuild, st.box.L[0], st.box.L[1], st.box.L[2],
+                0.25*skin*skin, st.rebuildFlag);
+        CFX_LAUNCH_CHECK(); st.launches++;
+    }
+    else
+        CFX_CUDA(cudaMemsetAsync(st.rebuildFlag, 1, sizeof(int), s));
+    cellAssignKernel<<<(st.N + 255)/256, 256, 0, s>>>(cp, st.rebuildFlag, dPos, st.qf, st.q, st.cellOfAtom, st.userLocal, st.userLocalD,
+            st.cellCount, st.posAtBuild);
     CFX_LAUNCH_CHECK(); st.launches++;
-    cellScanKernel<<<1, 1024, 0, s>>>(c.ncells, st.cellCount, st.cellStart, st.cellFill);
+    cellScanKernel<<<1, 1024, 0, s>>>(c.ncells, st.rebuildFlag, st.cellCount, st.cellStart, st.cellFill, st.pairCounters + 7);
     CFX_LAUNCH_CHECK(); st.launches++;
-    cellFillKernel<<<(st.N + 255)/256, 256, 0, s>>>(st.N, st.cellOfAtom, st.cellFill, st.filledUser);
+    cellFillKernel<<<(st.N + 255)/256, 256, 0, s>>>(st.N, st.rebuildFlag, st.cellOfAtom, st.cellFill, st.filledUser);
     CFX_LAUNCH_CHECK(); st.launches++;
-    cellRankGatherKernel<<<(st.N + 255)/256, 256, 0, s>>>(st.N, c.nc[1], c.nc[2], st.filledUser, st.cellOfAtom, st.cellStart,
+    cellRankGatherKernel<<<(st.N + 255)/256, 256, 0, s>>>(st.N, c.nc[1], c.nc[2], st.rebuildFlag, st.filledUser, st.cellOfAtom, st.cellStart,
             st.userLocal, st.lj, st.sortedLocal, st.sortedMeta, st.userLocalD, st.ljd, st.sortedLocalD, st.sortedLjD);
+    CFX_LAUNCH_CHECK(); st.launches++;
+    refreshSortedKernel<<<(st.N + 255)/256, 256, 0, s>>>(cp, dPos, st.qf, st.q, st.sortedLocal, st.sortedMeta, st.sortedLocalD);
     CFX_LAUNCH_CHECK(); st.launches++;
     mark(st, "cell_build", s);
 
@@ -1008,6 +1104,9 @@ void launchDirect(State& st, const double* dPos, bool forces, int emode, bool em
     for (int k = 0; k <= E_POLY_DEG; k++) pp.ePoly[k] = st.ePoly[k];
     pp.eTScale = st.eTScale; pp.ePolyOK = st.ePolyOK;
     pp.dcsx = c.csd[0]; pp.dcsy = c.csd[1]; pp.dcsz = c.csd[2];
+    pp.rebuildFlag = st.rebuildFlag;
+    pp.rlist2 = (float) ((st.cutoff + skin)*(st.cutoff + skin));
+    pp.drift = (float) (0.5*skin);
     pp.counters = st.pairCounters; pp.pairBuffer = st.pairBuffer; pp.pairCapacity = (unsigned long long) st.pairCapacity;
     const int groups = pp.groupHi - pp.groupLo;
     if (groups <= 0) return;
@@ -1030,6 +1129,8 @@ void launchDirect(State& st, const double* dPos, bool forces, int emode, bool em
         pp.wrapList = st.wrapList; pp.wrapCount = st.pairCounters + 7;
         pp.workCounter = reinterpret_cast<unsigned int*>(st.pairCounters + 10);
         buildListKernel<<<std::min((groups + P_WARPS - 1)/P_WARPS, 8*numSM), P_WARPS*32, 0, s>>>(pp);
+        CFX_LAUNCH_CHECK(); st.launches++;
+        finishListKernel<<<1, 32, 0, s>>>(st.rebuildFlag, st.pairCounters);
         CFX_LAUNCH_CHECK(); st.launches++;
         mark(st, "pair_list", s);
     }

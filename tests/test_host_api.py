@@ -55,7 +55,7 @@ def test_struct_layout_matches_header():
     assert ctypes.sizeof(_abi.SystemDesc) == 216
     assert ctypes.sizeof(_abi.Options) == 32
     assert ctypes.sizeof(_abi.EwaldParams) == 32
-    assert ctypes.sizeof(_abi.Stats) == 40
+    assert ctypes.sizeof(_abi.Stats) == 48
 
 
 def test_no_cpu_fallback():
