@@ -617,20 +617,29 @@ __global__ void __launch_bounds__(P_WARPS*32, (FAST && EMODE != 2) ? P_FAST_MINB
             const unsigned int* lst = p.pairList + (size_t) (g - p.groupLo)*p.listCap;
             const int nChunks = (listN + 31) >> 5;
             const int chunkLo = (int) ((long long) nChunks*share/nShares), chunkHi = (int) ((long long) nChunks*(share + 1)/nShares);
+            // software pipeline over the 32-entry chunks: the entries of chunk k+2 and the sorted records of chunk k+1 are
+            // in flight while chunk k is staged and its tiles are evaluated (the records are a dependent gather)
+            const int eEnd = min(listN, chunkHi*32);
+            auto loadEntry = [&](int e) -> unsigned int { return e < eEnd ? lst[e] : 0xffffffffu; };
+            auto wanted = [&](unsigned int ent) -> bool { return ent != 0xffffffffu && (!HALF || (int) (ent & 0x7ffffffu) > i0); };
+            unsigned int entCur = loadEntry(chunkLo*32 + lane), entNext = loadEntry(chunkLo*32 + 32 + lane);
+            float4 l4Cur = farAway, mjCur = farAway;
+            if (wanted(entCur)) { l4Cur = p.sortedLocal[entCur & 0x7ffffffu]; mjCur = p.sortedMeta[entCur & 0x7ffffffu]; }
             for (int eb = chunkLo*32; eb < chunkHi*32; eb += 32) {
-                const int e = eb + lane;
+                float4 l4Next = farAway, mjNext = farAway;
+                if (wanted(entNext)) { l4Next = p.sortedLocal[entNext & 0x7ffffffu]; mjNext = p.sortedMeta[entNext & 0x7ffffffu]; }
+                const unsigned int entAfter = loadEntry(eb + 64 + lane);
                 bool pass = false, cls = false;
                 float4 pj = farAway, mj = farAway;
                 double4 pjD = make_double4(0.0, 0.0, 0.0, 0.0);
                 int s = 0;
-                if (e < listN) {
-                    const unsigned int ent = lst[e];
+                if (wanted(entCur)) {
+                    const unsigned int ent = entCur;
                     s = (int) (ent & 0x7ffffffu);
-                    pass = !HALF || s > i0;
-                    if (pass) {
+                    {
                         const int code = (int) (ent >> 27);
-                        const float4 l4 = p.sortedLocal[s];
-                        mj = p.sortedMeta[s];
+                        const float4 l4 = l4Cur;
+                        mj = mjCur;
                         const int cj = __float_as_int(mj.w);
                         const int cz3 = code/9, cy3 = (code - 9*cz3)/3, cx3 = code - 9*cz3 - 3*cy3;
                         const int offx = (cj & CELL_MASK) - c0x + (cx3 - 1)*p.ncx;
@@ -650,6 +659,7 @@ __global__ void __launch_bounds__(P_WARPS*32, (FAST && EMODE != 2) ? P_FAST_MINB
                         cls = anyLJi && mj.y != 0.f;
                     }
                 }
+                entCur = entNext; entNext = entAfter; l4Cur = l4Next; mjCur = mjNext;
                 const unsigned int m1 = __ballot_sync(0xffffffffu, pass && cls);
                 const unsigned int m0 = __ballot_sync(0xffffffffu, pass && !cls);
                 if (pass) {

@@ -2,9 +2,10 @@
 same execution count) with instruction and stall-sample shares.   python tools/ncu_blocks.py file.ncu-rep [min_pct]"""
 import collections, csv, io, subprocess, sys
 rep = sys.argv[1]; minpct = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
+kidx = int(sys.argv[3]) if len(sys.argv) > 3 else 0      # which launch of the report
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
-hdr, r = rows[0], rows[2]
+hdr, r = rows[0], rows[2 + kidx]
 want = ["Kernel Name", "gpu__time_duration.sum", "smsp__inst_executed.sum", "smsp__issue_active.avg.per_cycle_active", "sm__warps_active.avg.per_cycle_active",
         "launch__registers_per_thread", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
         "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
@@ -15,6 +16,8 @@ for h, v in zip(hdr, r):
         print("%-90s %s" % (h, v))
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+rows = rows[starts[min(2*kidx, len(starts) - 1)]:]        # every launch is exported twice
 hdr = rows[1]
 iS, iE, iSm = hdr.index("Source"), hdr.index("Instructions Executed"), hdr.index("# Samples")
 blocks, cur, k = [], None, 0
