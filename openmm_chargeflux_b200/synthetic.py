@@ -187,3 +187,25 @@ def config(name):
     if name == "c5":
         return methanol_water()
     return water_box(**CONFIGS[name])
+
+
+def ballistic_frames(pos, n_frames, dt_ps=0.0005, temperature=300.0, seed=17):
+    """Positions for a benchmark whose atoms move every step: frame k = pos + k dt v with per-atom Maxwell-Boltzmann
+    velocities (O: 15.999, H: 1.008 g/mol; kT in kJ/mol), i.e. straight-line motion at thermal speed. Harder on a
+    neighbour list than real MD (bonded atoms vibrate instead of flying apart): the fastest hydrogens cover 0.05 nm in
+    about ten 0.5 fs steps. Callers walk the frames forwards and backwards so that the geometry stays bounded.
+    Returns float64 [n_frames, N, 3]."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    n = len(pos)
+    mass = np.tile([15.999, 1.008, 1.008], (n + 2) // 3)[:n]
+    sigma = np.sqrt(0.0083144626 * temperature / mass)          # nm/ps
+    vel = rng.normal(size=(n, 3)) * sigma[:, None]
+    k = np.arange(n_frames, dtype=np.float64)[:, None, None]
+    return pos[None, :, :] + k * dt_ps * vel[None, :, :]
+
+
+def ping_pong(step, n_frames):
+    """Frame index of step `step` when walking 0, 1, ..., n-1, n-2, ..., 1, 0, 1, ..."""
+    period = 2 * (n_frames - 1)
+    r = step % period
+    return r if r < n_frames else period - r
