@@ -334,13 +334,11 @@ def run_ours(args, pos, box, force, workload):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: there is no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
-    nccl_log = None
     if world > 1:
-        # NCCL's INFO log (rank count, transports, NVLS) stays available to whoever runs this: it goes to a per-process
-        # file and rank 0 copies every rank's file to stderr after the JSON line, so that stdout holds the one JSON line
+        # NCCL's INFO log (rank count, transports, NVLS) stays visible to whoever runs this: it is sent to stderr, so that
+        # stdout holds the one JSON line
         os.environ.setdefault("NCCL_DEBUG", "INFO")
-        nccl_log = "/tmp/cfx_nccl_%d" % os.getppid()
-        os.environ["NCCL_DEBUG_FILE"] = nccl_log + ".%h.%p.log"
+        os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n = len(pos)
     comm_id = broadcast_comm_id(dist, rank) if world > 1 else None
@@ -575,12 +573,6 @@ def run_ours(args, pos, box, force, workload):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-        if rank == 0 and nccl_log:
-            import glob
-            for path in sorted(glob.glob(nccl_log + ".*.log")):
-                with open(path) as fh:
-                    sys.stderr.write(fh.read())
-                os.unlink(path)
 
 
 def main():

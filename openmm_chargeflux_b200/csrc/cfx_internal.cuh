@@ -176,7 +176,7 @@ struct State {
     double4* userLocalD = nullptr; double4* sortedLocalD = nullptr;   // the same in double (+ charge): FP64 pair energies
     double2* sortedLjD = nullptr;       // [N] (sigma/2, 2 sqrt(eps)) in double, sorted order
     double ePoly[25] = {0}; double eTScale = 0; int ePolyOK = 0;   // polynomial of the FP64 pair energies (direct.cu)
-    unsigned int* pairList = nullptr; int* listCount = nullptr;     // candidate lists of the fast pair kernel (direct.cu)
+    unsigned int* pairList = nullptr; int2* listCount = nullptr;     // candidate lists of the fast pair kernel (direct.cu)
     size_t pairListEntries = 0; int listCap = 0;
     double skin = 0.0;                  // lists are built for cutoff + skin and reused until an atom has moved skin/2 (0: rebuilt every evaluation)
     int* rebuildFlag = nullptr;         // device: non-zero = this evaluation re-sorts the atoms and rebuilds the lists

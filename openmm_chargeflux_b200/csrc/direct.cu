@@ -251,9 +251,10 @@ struct PairParams {
     unsigned int* workCounter;               // dynamic work distribution: next (cluster, column share) item
     int* wrapList;                           // clusters the fast kernel left to the generic one (*wrapCount of them)
     unsigned long long* wrapCount;
-    // candidate lists of the fast path (buildListKernel): for i-cluster g, listCount[g - groupLo] entries (negative: the
-    // cluster is left to the generic kernel) at pairList + (g - groupLo)*listCap, each = sorted index | image code << 27
-    unsigned int* pairList; int* listCount; int listCap;
+    // candidate lists of the fast path (buildListKernel): for i-cluster g, listCount[g - groupLo] = (entries at the front,
+    // entries at the back) of pairList + (g - groupLo)*listCap (x negative: the cluster is left to the generic kernel),
+    // each entry = sorted index | image code << 27
+    unsigned int* pairList; int2* listCount; int listCap;
     const int* rebuildFlag;                  // list builder: return at once unless set
     float rlist2;                            // (cutoff + skin)^2: what the lists are built for
     float drift;                             // skin/2: how far an atom may be outside the cell it was sorted into
@@ -406,10 +407,12 @@ __global__ void __launch_bounds__(P_WARPS*32, (FAST && EMODE != 2) ? P_FAST_MINB
         const int loY = ominy - 2, nY = min(omaxy - ominy + 5, p.ncy);
         const int loZ = ominz - 2, nZ = min(omaxz - ominz + 5, p.ncz);
         const bool wraps = (omaxx - ominx + 5 > p.ncx) || (omaxy - ominy + 5 > p.ncy) || (omaxz - ominz + 5 > p.ncz);
-        int listN = 0;
+        int listN = 0, listFront = 0;
         if (FAST) {                                     // negative: buildListKernel left the cluster to the generic kernel
-            listN = p.listCount[g - p.groupLo];
-            if (listN < 0) continue;
+            const int2 lc = p.listCount[g - p.groupLo];
+            if (lc.x < 0) continue;
+            listFront = lc.x;
+            listN = HALF ? lc.x : lc.x + lc.y;          // energy passes: only the atoms behind the cluster in sorted order
         }
         const bool minImage = FAST ? false : wraps;
 
@@ -620,7 +623,9 @@ __global__ void __launch_bounds__(P_WARPS*32, (FAST && EMODE != 2) ? P_FAST_MINB
             // software pipeline over the 32-entry chunks: the entries of chunk k+2 and the sorted records of chunk k+1 are
             // in flight while chunk k is staged and its tiles are evaluated (the records are a dependent gather)
             const int eEnd = min(listN, chunkHi*32);
-            auto loadEntry = [&](int e) -> unsigned int { return e < eEnd ? lst[e] : 0xffffffffu; };
+            auto loadEntry = [&](int e) -> unsigned int {          // front part, then the back part (stored downwards from the end)
+                return e < eEnd ? lst[e < listFront ? e : p.listCap - 1 - (e - listFront)] : 0xffffffffu;
+            };
             auto wanted = [&](unsigned int ent) -> bool { return ent != 0xffffffffu && (!HALF || (int) (ent & 0x7ffffffu) > i0); };
             unsigned int entCur = loadEntry(chunkLo*32 + lane), entNext = loadEntry(chunkLo*32 + 32 + lane);
             float4 l4Cur = farAway, mjCur = farAway;
@@ -854,7 +859,7 @@ __global__ void __launch_bounds__(P_WARPS*32) buildListKernel(const __grid_const
         const int loY = ominy - 2, nY = omaxy - ominy + 5;
         const int loZ = ominz - 2, nZ = omaxz - ominz + 5;
         unsigned int* lst = p.pairList + (size_t) item*p.listCap;
-        int count = 0;
+        int count = 0, countB = 0;
         bool giveUp = nX > p.ncx || nY > p.ncy || nZ > p.ncz;      // the stencil would wrap onto itself
         unsigned int nCand = 0;
         int cxw = wrapOnce(c0x + loX, p.ncx);
@@ -902,24 +907,31 @@ __global__ void __launch_bounds__(P_WARPS*32) buildListKernel(const __grid_const
                             const float ez = fmaxf(0.f, fmaxf(bminz - z, z - bmaxz));
                             pass = fmaf(ez, ez, fmaf(ey, ey, ex*ex)) <= rcut2;
                         }
-                        const unsigned int m = __ballot_sync(0xffffffffu, pass);
-                        const int k = __popc(m);
-                        if (count + k > p.listCap) { giveUp = true; break; }
-                        if (pass) lst[count + __popc(m & lt)] = (unsigned int) s | code;
-                        count += k;
+                        // atoms behind the cluster in sorted order fill the list from the front, the others from the back:
+                        // energy passes (each pair once, from the atom that comes first) read only the front part
+                        const bool behind = s > i0;
+                        const unsigned int mA = __ballot_sync(0xffffffffu, pass && behind);
+                        const unsigned int mB = __ballot_sync(0xffffffffu, pass && !behind);
+                        const int kA = __popc(mA), kB = __popc(mB);
+                        if (count + countB + kA + kB > p.listCap) { giveUp = true; break; }
+                        if (pass) {
+                            if (behind) lst[count + __popc(mA & lt)] = (unsigned int) s | code;
+                            else        lst[p.listCap - 1 - (countB + __popc(mB & lt))] = (unsigned int) s | code;
+                        }
+                        count += kA; countB += kB;
                     }
                 }
             }
             if (++cxw == p.ncx) cxw = 0;
         }
-        nCand = (unsigned int) count;
+        nCand = (unsigned int) (count + countB);
         if (lane == 0) {
             if (giveUp) {
                 p.wrapList[atomicAdd(p.wrapCount, 1ull)] = g;
                 if (!(nX > p.ncx || nY > p.ncy || nZ > p.ncz)) atomicAdd(p.counters + 11, 1ull);     // list overflow
             }
-            p.listCount[item] = giveUp ? -1 : count;
-            atomicMax(p.counters + 12, (unsigned long long) count);                                   // longest list so far
+            p.listCount[item] = giveUp ? make_int2(-1, 0) : make_int2(count, countB);
+            atomicMax(p.counters + 12, (unsigned long long) (count + countB));                                   // longest list so far
             atomicAdd(p.counters + 1, (unsigned long long) nCand*P_ITILE);
         }
         __syncwarp();
@@ -994,7 +1006,7 @@ void allocPairLists(State& st) {
     const int lo = (int) ((int64_t) numGroups*st.shardRank/st.shardCount), hi = (int) ((int64_t) numGroups*(st.shardRank + 1)/st.shardCount);
     const size_t groups = (size_t) std::max(hi - lo, 1);
     CFX_CUDA(cudaMalloc(&st.pairList, sizeof(unsigned int)*groups*st.listCap));
-    CFX_CUDA(cudaMalloc(&st.listCount, sizeof(int)*groups));
+    CFX_CUDA(cudaMalloc(&st.listCount, sizeof(int2)*groups));
     st.pairListEntries = groups*st.listCap;
 }
 

@@ -31,11 +31,13 @@ def test_lists_are_reused_and_rebuilt_on_the_displacement_trigger():
     p = pos.copy()
     for it in range(12):
         e, f, _ = ctx.evaluate(p)
-        e2, f2, _ = fresh.evaluate(p)
+        e2, f2, comps = fresh.evaluate(p)
         builds.append(ctx.kernel.stats().pair_list_builds)
         # same neighbour set (bit-exact, against the oracle at a few steps), same physics as a handle without history
         assert ctx.kernel.stats().pairs_in_cutoff == fresh.kernel.stats().pairs_in_cutoff
-        assert abs(e - e2) <= 1e-8 * abs(e2), (it, e, e2)
+        # (the total of this box is ~80 kJ/mol out of components of 1e5: compare at the scale of the components; the
+        # energies are summed as 2^-24 fixed point per warp, so two summation orders differ by ~1e-6 kJ/mol)
+        assert abs(e - e2) <= 1e-10 * np.abs(comps[:4]).max(), (it, e, e2)
         assert _relrms(f, f2) < 4e-6, (it, _relrms(f, f2))      # two FP32 summation orders, each ~1e-6 from the oracle
         if it in (0, 5, 11):
             eo, fo = oracle.execute(p, box)
