@@ -115,7 +115,8 @@ struct SParams {
 // columns, padded to TNP float2 so the group is 16-byte aligned) for all 64 rows; lane owns rows
 // lane and lane+32. Per atom a warp reads the row phases q*Ex(nx), Ey(|ny|) of its two rows (4 LDS.64)
 // and forms the row operand a = (xr*yc, xr*ys, xi*yc, xi*ys) in registers (8 FMUL), reads its TN column
-// phases with warp-UNIFORM LDS.128 (1 wavefront each) and issues 16*TN FFMA. The atom rows arrive by
+// phases with warp-UNIFORM LDS.128 (1 wavefront each) and issues 8*TN packed FFMA2 (one per (component, column): the
+// (cos, sin) pair of products; 0.244 -> 0.218 ms at 32k atoms against scalar FFMA: the kernel is issue-bound). The atom rows arrive by
 // bulk TMA into a ring of stages; there is one CTA barrier per 32 atoms and no staging of the operand.
 template <int TN, int G>
 __global__ void __launch_bounds__(32*G, (G <= 4) ? 3 : 1) structureFactorKernel(SParams p) {
@@ -145,13 +146,13 @@ __global__ void __launch_bounds__(32*G, (G <= 4) ? 3 : 1) structureFactorKernel(
         offY[it] = p.Kx + (row - nx*p.Ky);
     }
 
-    float acc[2][TN][8];
+    float2 acc2[2][TN][4];                                 // (zc, zs) products of row operand component m
     #pragma unroll
     for (int i = 0; i < 2; i++)
         #pragma unroll
         for (int c = 0; c < TN; c++)
             #pragma unroll
-            for (int k = 0; k < 8; k++) acc[i][c][k] = 0.f;
+            for (int k = 0; k < 4; k++) acc2[i][c][k] = make_float2(0.f, 0.f);
 
     if (tid == 0) {
         for (int s = 0; s < p.stages; s++) { mbarInit(mbar + s, 1); done[s] = 0; }
@@ -183,30 +184,25 @@ __global__ void __launch_bounds__(32*G, (G <= 4) ? 3 : 1) structureFactorKernel(
             for (int c = 0; c < TNP/2; c++) b[c] = bPtr[j*bPitch4 + c];
             const float4 a0 = make_float4(x0.x*y0.x, x0.x*y0.y, x0.y*y0.x, x0.y*y0.y);
             const float4 a1 = make_float4(x1.x*y1.x, x1.x*y1.y, x1.y*y1.x, x1.y*y1.y);
-            // Register-bank layout: the accumulators live in aligned quads (they are stored as float4), the
-            // column phases in aligned quads (LDS.128): zc in even, zs in odd registers. Storing the zs product
-            // FIRST in each accumulator pair makes the two non-reused operands of every FFMA (phase, accumulator)
-            // opposite-parity, i.e. free of register-bank conflicts: acc[2m] += a_m*zs, acc[2m+1] += a_m*zc.
             const float av0[4] = {a0.x, a0.y, a0.z, a0.w};
             const float av1[4] = {a1.x, a1.y, a1.z, a1.w};
+            // packed FP32: one FFMA2 per (row operand component, column) = the (zc, zs) pair of products
             #pragma unroll
             for (int m = 0; m < 4; m++) {
+                const float2 am = make_float2(av0[m], av0[m]);
                 #pragma unroll
                 for (int c = 0; c < TN; c++) {
-                    const float zc = (c & 1) ? b[c/2].z : b[c/2].x;
-                    const float zs = (c & 1) ? b[c/2].w : b[c/2].y;
-                    acc[0][c][2*m]     = fmaf(av0[m], zs, acc[0][c][2*m]);
-                    acc[0][c][2*m + 1] = fmaf(av0[m], zc, acc[0][c][2*m + 1]);
+                    const float2 z = (c & 1) ? make_float2(b[c/2].z, b[c/2].w) : make_float2(b[c/2].x, b[c/2].y);
+                    acc2[0][c][m] = __ffma2_rn(am, z, acc2[0][c][m]);
                 }
             }
             #pragma unroll
             for (int m = 0; m < 4; m++) {
+                const float2 am = make_float2(av1[m], av1[m]);
                 #pragma unroll
                 for (int c = 0; c < TN; c++) {
-                    const float zc = (c & 1) ? b[c/2].z : b[c/2].x;
-                    const float zs = (c & 1) ? b[c/2].w : b[c/2].y;
-                    acc[1][c][2*m]     = fmaf(av1[m], zs, acc[1][c][2*m]);
-                    acc[1][c][2*m + 1] = fmaf(av1[m], zc, acc[1][c][2*m + 1]);
+                    const float2 z = (c & 1) ? make_float2(b[c/2].z, b[c/2].w) : make_float2(b[c/2].x, b[c/2].y);
+                    acc2[1][c][m] = __ffma2_rn(am, z, acc2[1][c][m]);
                 }
             }
         }
@@ -230,8 +226,8 @@ __global__ void __launch_bounds__(32*G, (G <= 4) ? 3 : 1) structureFactorKernel(
         for (int c = 0; c < TN; c++) {
             const int col = warp*TNP + c;
             float4* out = reinterpret_cast<float4*>(p.part + (((size_t) blockIdx.y*p.numRows + row)*p.kzPad + col)*8);
-            out[0] = make_float4(acc[i][c][0], acc[i][c][1], acc[i][c][2], acc[i][c][3]);
-            out[1] = make_float4(acc[i][c][4], acc[i][c][5], acc[i][c][6], acc[i][c][7]);
+            out[0] = make_float4(acc2[i][c][0].y, acc2[i][c][0].x, acc2[i][c][1].y, acc2[i][c][1].x);      // (zs, zc) order of the partials
+            out[1] = make_float4(acc2[i][c][2].y, acc2[i][c][2].x, acc2[i][c][3].y, acc2[i][c][3].x);
         }
     }
 }
