@@ -1,6 +1,7 @@
 // api.cu -- the C ABI of include/cfx_b200.h: parameter preprocessing (what
 // ReferenceCalcCoulForceKernel::initialize does, ReferenceCoulKernels.cpp:230-422), the per-evaluation
 // kernel sequence (execute, :424-636) replayed as one CUDA graph, parity getters and timing helpers.
+#include <nvtx3/nvToolsExt.h>
 #include "cfx_internal.cuh"
 
 #include <algorithm>
@@ -23,7 +24,15 @@ void throwCuda(cudaError_t code, const char* what, const char* file, int line) {
 
 void setLastError(const std::string& msg) { g_lastError = msg; }
 
+// NVTX (header-only nvtx3: no-ops unless a profiler is attached): one range per entry-point call, one mark per phase
+// of the kernel sequence as it is enqueued or captured (inside a replayed graph the kernels carry their own names).
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
 void mark(State& st, const char* name, cudaStream_t s) {
+    nvtxMarkA(name);
     if (!st.timing) return;
     cudaEvent_t ev;
     CFX_CUDA(cudaEventCreate(&ev));
@@ -220,6 +229,7 @@ int cfx_device_count(void) {
 int cfx_create(const cfx_system_desc* d, const cfx_options* opts, cfx_handle** out) {
     // a failed create must not leak the handle, its streams, pinned buffers or device allocations
     struct Guard { cfx_handle* h = nullptr; ~Guard() { if (h) cfx_destroy(h); } } guard;
+    NvtxRange nvtxRange("cfx_create");
     CFX_TRY
     if (!d || !out) throw ArgError("null argument");
     *out = nullptr;
@@ -419,6 +429,7 @@ void cfx_destroy(cfx_handle* h) {
 
 int cfx_execute(cfx_handle* h, const double* positions, const double* box, int include_forces, int include_energy,
                 double* energy, double* forces) {
+    NvtxRange nvtxRange("cfx_execute");
     CFX_TRY
     if (!h) throw ArgError("null handle");
     State& st = h->st;
@@ -519,6 +530,7 @@ int cfx_execute(cfx_handle* h, const double* positions, const double* box, int i
 static int executeDeviceImpl(cfx_handle* h, const double* d_positions, const double* box, int include_forces, int include_energy,
                              long long* d_force_fixed, long long* d_dedq_fixed, double* d_energy, void* stream, bool shard,
                              bool reduce = false) {
+    NvtxRange nvtxRange("cfx_execute_device");
     CFX_TRY
     if (!h) throw ArgError("null handle");
     State& st = h->st;
