@@ -79,3 +79,38 @@ def test_list_overflow_falls_back_to_the_generic_kernel_and_grows(monkeypatch):
         assert ctx.kernel.stats().pairs_in_cutoff == ref.kernel.stats().pairs_in_cutoff
     assert np.array_equal(f, f0) and e == e0                        # lists large enough again: identical to the reference handle
     ctx.kernel.close(); ref.kernel.close()
+
+
+@pytest.mark.parametrize("world", [3])
+def test_sharded_handles_on_the_list_path_sum_to_the_unsharded_result(world):
+    """Every rank lists only its own slab of i-clusters; the slabs' fixed-point sums reproduce the unsharded evaluation,
+    before and after the atoms have moved (ranks emulated as consecutive launches on one GPU)."""
+    import torch
+    pos, box, force = _box(seed=6)
+    n = len(pos)
+    whole = runtime.CoulContext(force, box)
+    kernels = [runtime.CalcCoulForceKernel(shard_rank=r, shard_count=world) for r in range(world)]
+    for k in kernels:
+        k.initialize(box, force)
+    npad = kernels[0].padded_num_particles()
+    stream = torch.cuda.Stream()
+    rng = np.random.default_rng(9)
+    p = pos.copy()
+    for it in range(3):
+        e, f, comps = whole.evaluate(p)
+        d_pos = torch.tensor(p.reshape(-1), device="cuda")
+        d_force = torch.zeros(3 * npad, dtype=torch.int64, device="cuda")
+        d_energy = torch.zeros(8, dtype=torch.float64, device="cuda")
+        with torch.cuda.stream(stream):
+            for k in kernels:
+                k.execute_device(d_pos.data_ptr(), box, d_force.data_ptr(), 0, d_energy.data_ptr(), stream.cuda_stream)
+        stream.synchronize()
+        fs = d_force.cpu().numpy().reshape(3, npad)[:, :n].T / 4294967296.0
+        es = d_energy.cpu().numpy()
+        assert np.abs(es[:4] - comps[:4]).max() <= 1e-9 * np.abs(comps[:4]).max()
+        assert _relrms(fs, f) <= 2e-6
+        p = p + rng.normal(scale=0.01, size=p.shape)                # it = 1, 2: past skin/2 for some atoms -> rebuild
+    assert all(k.stats().pair_list_builds >= 2 for k in kernels)
+    for k in kernels:
+        k.close()
+    whole.kernel.close()
