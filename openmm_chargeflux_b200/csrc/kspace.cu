@@ -102,6 +102,13 @@ __global__ void __launch_bounds__(128) phaseTableKernel(TableParams p, const dou
 #define S_ATOMS_PER_STAGE 32
 #define S_BM 64                    // rows per CTA: lane + 32*i, i < 2
 #define S_MAX_WARPS 8
+#ifndef S_UNROLL
+#define S_UNROLL 2
+#endif
+#ifndef S_MINBLOCKS
+#define S_MINBLOCKS 3
+#endif
+constexpr int kSUnroll = S_UNROLL;
 
 struct SParams {
     const float2* rowS; float* part;
@@ -119,7 +126,7 @@ struct SParams {
 // (cos, sin) pair of products; 0.244 -> 0.218 ms at 32k atoms against scalar FFMA: the kernel is issue-bound). The atom rows arrive by
 // bulk TMA into a ring of stages; there is one CTA barrier per 32 atoms and no staging of the operand.
 template <int TN, int G>
-__global__ void __launch_bounds__(32*G, (G <= 4) ? 3 : 1) structureFactorKernel(SParams p) {
+__global__ void __launch_bounds__(32*G, (G <= 4) ? S_MINBLOCKS : 1) structureFactorKernel(SParams p) {
     constexpr int TNP = (TN + 1) & ~1;
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem);
@@ -175,7 +182,7 @@ __global__ void __launch_bounds__(32*G, (G <= 4) ? 3 : 1) structureFactorKernel(
         const float2* x1p = rw + offX[1]; const float2* y1p = rw + offY[1];
         const float4* bPtr = reinterpret_cast<const float4*>(rw + p.zOff + warp*TNP);
         const int bPitch4 = p.rowPitch/2;
-        #pragma unroll 2
+        #pragma unroll (kSUnroll)
         for (int j = 0; j < S_ATOMS_PER_STAGE; j++) {
             const float2 x0 = x0p[j*p.rowPitch], y0 = y0p[j*p.rowPitch];
             const float2 x1 = x1p[j*p.rowPitch], y1 = y1p[j*p.rowPitch];

@@ -30,7 +30,8 @@ void B200CalcCoulForceKernel::initialize(const System& system, const CoulForce& 
     cfx_options opts;
     opts.device = -1; opts.shard_rank = 0; opts.shard_count = 1; opts.use_graph = 1;
     opts.flags = CFX_OPT_PIN_CALLER_BUFFERS;
-    for (int k = 0; k < 3; k++) opts.reserved[k] = 0;
+    opts.list_skin_pm = 0;                       // library default (100 pm)
+    for (int k = 0; k < 2; k++) opts.reserved[k] = 0;
     check(cfx_create(&d, &opts, &handle), "B200CalcCoulForceKernel::initialize");
 }
 

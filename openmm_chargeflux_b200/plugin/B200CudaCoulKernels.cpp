@@ -116,7 +116,8 @@ void B200CudaCalcCoulForceKernel::initialize(const System& system, const CoulFor
     opts.device = cu.getDeviceIndex(); opts.shard_rank = 0; opts.shard_count = 1; opts.use_graph = 1;
     // the value execute() would return for includeEnergy == false is discarded by OpenMM: do not compute it
     opts.flags = CFX_OPT_SKIP_DISCARDED_ENERGY;
-    for (int k = 0; k < 3; k++) opts.reserved[k] = 0;
+    opts.list_skin_pm = 0;                       // library default (100 pm)
+    for (int k = 0; k < 2; k++) opts.reserved[k] = 0;
     check(cfx_create(&d.desc, &opts, &handle), "B200CudaCalcCoulForceKernel::initialize");
     cu.addForce(new B200CoulForceInfo(force));                      // CudaCoulKernels.cpp:519
 }
