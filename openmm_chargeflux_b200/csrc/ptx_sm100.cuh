@@ -19,11 +19,16 @@ __device__ __forceinline__ void mbarExpectTx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbarArrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smemU32(bar)) : "memory");
 }
+#ifndef MBAR_SUSPEND_HINT_NS
+#define MBAR_SUSPEND_HINT_NS 0x989680u
+#endif
 __device__ __forceinline__ void mbarWait(uint64_t* bar, uint32_t parity) {
     uint32_t done;
     do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(smemU32(bar)), "r"(parity) : "memory");
+        // (suspend-time hint: the warp sleeps in the barrier unit until the phase completes or the hint expires, instead
+        // of spinning through issue slots the other warps of its scheduler need)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smemU32(bar)), "r"(parity), "r"(MBAR_SUSPEND_HINT_NS) : "memory");
     } while (!done);
 }
 
