@@ -337,8 +337,10 @@ def run_ours(args, pos, box, force, workload):
     if world > 1:
         # NCCL's INFO log (rank count, transports, NVLS) stays visible to whoever runs this: it is sent to stderr, so that
         # stdout holds the one JSON line
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
+        # (the GPU boxes preset NCCL_DEBUG=VERSION: raise it to INFO unless the caller asked for more)
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "INFO"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n = len(pos)
     comm_id = broadcast_comm_id(dist, rank) if world > 1 else None

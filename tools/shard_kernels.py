@@ -8,6 +8,7 @@ dpos = torch.tensor(pos, device='cuda')
 for rank in (0, world - 1):
     k = runtime.CalcCoulForceKernel(shard_rank=rank, shard_count=world)
     k.initialize(box, f)
-    kt = k.time_kernels(dpos.data_ptr(), box, 10, True, False)
-    print("rank", rank, "of", world, "sum %.4f ms" % sum(kt.values()), {a: round(b, 4) for a, b in kt.items()})
-    print("   device time per eval (graph): %.4f ms" % k.time_device(dpos.data_ptr(), box, 20, True, False))
+    for inc_e in (False, True):
+        kt = k.time_kernels(dpos.data_ptr(), box, 10, True, inc_e)
+        print("rank", rank, "of", world, "energy", inc_e, "sum %.4f ms" % sum(kt.values()), {a: round(b, 4) for a, b in kt.items()})
+        print("   device time per eval (graph): %.4f ms" % k.time_device(dpos.data_ptr(), box, 20, True, inc_e))
