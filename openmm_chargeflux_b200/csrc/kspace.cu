@@ -552,7 +552,11 @@ void planKSpace(State& st) {
     const int ctasPerSM = std::max(1, std::min(4, (int) ((size_t) 220*1024/(f.smem + 1024))));
     const int slots = ctasPerSM*numSM;
     int splits = std::max(1, slots/std::max(1, f.rowTiles));
-    const int maxSplits = std::max(1, st.Npad/(4*S_ATOMS_PER_STAGE));       // >= 4 stages per CTA
+    // stages (of 32 atoms) per CTA at least: small row shards (multi-GPU) would otherwise be cut into hundreds of short
+    // CTAs whose partial sums the coefficient kernel then has to add (8 ranks at 32k atoms: 0.176 -> 0.160 ms per rank)
+    int minStages = 16;
+    if (const char* e = getenv("CFX_S_MIN_STAGES")) minStages = std::max(1, atoi(e));     // experiments
+    const int maxSplits = std::max(1, st.Npad/(minStages*S_ATOMS_PER_STAGE));
     splits = std::min(splits, maxSplits);
     int aps = (st.Npad + splits - 1)/splits;
     aps = (aps + S_ATOMS_PER_STAGE - 1)/S_ATOMS_PER_STAGE*S_ATOMS_PER_STAGE;
