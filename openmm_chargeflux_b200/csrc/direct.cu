@@ -225,6 +225,7 @@ constexpr int kPairUnroll = P_UNROLL;
 #define P_EUNROLL 1       // FP64 energy passes
 #endif
 constexpr int kEnergyUnroll = P_EUNROLL;
+#define P_MAX_JSPLITS 8        // shares of one cluster's candidate list (small systems, shards)
 #define P_JCAP 64            // ring capacity: < 32 waiting entries + one 32-candidate chunk
 
 struct PairParams {
@@ -1137,8 +1138,8 @@ void launchDirect(State& st, const double* dPos, bool forces, int emode, bool em
     // shares meet in the fixed-point atomics).
     int numSM = 148;
     cudaDeviceGetAttribute(&numSM, cudaDevAttrMultiProcessorCount, st.device);
-    pp.jSplits = std::max(1, std::min(8, (28*numSM + groups - 1)/groups));
-    if (const char* e = getenv("CFX_PAIR_JSPLITS")) pp.jSplits = std::max(1, std::min(8, atoi(e)));     // experiments
+    pp.jSplits = std::max(1, std::min(P_MAX_JSPLITS, (28*numSM + groups - 1)/groups));
+    if (const char* e = getenv("CFX_PAIR_JSPLITS")) pp.jSplits = std::max(1, std::min(32, atoi(e)));     // experiments
     if (emitPairs) pp.jSplits = 1;
     const int items = groups*pp.jSplits;
     const bool fast = !c.smallBox;
