@@ -153,9 +153,19 @@ __global__ void appendEnergyFixedKernel(const long long* __restrict__ energyFixe
 void enqueueEvaluation(State& st, const double* dPos, bool includeForces, bool includeEnergy, long long* dForce, cudaStream_t s, bool skipDiscardedEnergy) {
     CFX_CUDA(cudaMemsetAsync(st.dedqFixed, 0, sizeof(long long)*st.Npad, s));
     CFX_CUDA(cudaMemsetAsync(st.energyFixed, 0, sizeof(long long)*8, s));
+    const bool overlap = st.pbc && st.overlapBranches && !st.timing;
+    const int emodeAll = includeEnergy ? 2 : ((skipDiscardedEnergy || st.skipDiscardedEnergy) ? 0 : 1);
+    if (overlap) {
+        // the search half of the direct-space branch needs only the positions: it starts on the side stream while the
+        // charge-flux assembly runs
+        CFX_CUDA(cudaMemsetAsync(st.pairCounters, 0, sizeof(unsigned long long)*4, s));
+        CFX_CUDA(cudaEventRecord(st.evStart, s));
+        CFX_CUDA(cudaStreamWaitEvent(st.sideStream, st.evStart, 0));
+        launchDirect(st, dPos, includeForces, emodeAll, false, dForce, st.dedqFixed, st.sideStream, 1);
+    }
     launchFluxAssembly(st, dPos, s);
     if (st.pbc) {
-        CFX_CUDA(cudaMemsetAsync(st.pairCounters, 0, sizeof(unsigned long long)*4, s));
+        if (!overlap) CFX_CUDA(cudaMemsetAsync(st.pairCounters, 0, sizeof(unsigned long long)*4, s));
         // reference quirks mirrored: reciprocal energy only with includeEnergy; direct,
         // self and exclusion energies always; pair/recip forces and dE/dq only with includeForces
         const int emode = includeEnergy ? 2 : ((skipDiscardedEnergy || st.skipDiscardedEnergy) ? 0 : 1);
@@ -166,7 +176,7 @@ void enqueueEvaluation(State& st, const double* dPos, bool includeForces, bool i
             CFX_CUDA(cudaEventRecord(st.evFork, s));
             CFX_CUDA(cudaStreamWaitEvent(st.sideStream, st.evFork, 0));
             launchExclusionCorrection(st, dPos, includeForces, dForce, st.dedqFixed, st.sideStream);   // first: see flux.cu
-            launchDirect(st, dPos, includeForces, emode, false, dForce, st.dedqFixed, st.sideStream);
+            launchDirect(st, dPos, includeForces, emode, false, dForce, st.dedqFixed, st.sideStream, 2);
             CFX_CUDA(cudaEventRecord(st.evJoin, st.sideStream));
             launchKSpace(st, dPos, includeForces, includeEnergy, dForce, st.dedqFixed, s);
             CFX_CUDA(cudaStreamWaitEvent(s, st.evJoin, 0));
@@ -348,6 +358,7 @@ int cfx_create(const cfx_system_desc* d, const cfx_options* opts, cfx_handle** o
     CFX_CUDA(cudaStreamCreateWithFlags(&st.sideStream, cudaStreamNonBlocking));
     CFX_CUDA(cudaEventCreateWithFlags(&st.evFork, cudaEventDisableTiming));
     CFX_CUDA(cudaEventCreateWithFlags(&st.evJoin, cudaEventDisableTiming));
+    CFX_CUDA(cudaEventCreateWithFlags(&st.evStart, cudaEventDisableTiming));
     st.q0 = upload(q0); st.lj = upload(lj); st.ljd = upload(ljd);
     st.termIdx = upload(termIdx); st.termPar = upload(termPar);
     st.qcsrPtr = upload(csrPtr, 2); st.qcsrSlot = upload(csrSlot); st.qcsrCoef = upload(csrCoef);
@@ -422,6 +433,7 @@ void cfx_destroy(cfx_handle* h) {
     for (cudaEvent_t e : st.timeEvents) cudaEventDestroy(e);
     if (st.evFork) cudaEventDestroy(st.evFork);
     if (st.evJoin) cudaEventDestroy(st.evJoin);
+    if (st.evStart) cudaEventDestroy(st.evStart);
     if (st.sideStream) cudaStreamDestroy(st.sideStream);
     if (st.stream) cudaStreamDestroy(st.stream);
     delete h;

@@ -133,7 +133,7 @@ struct State {
 
     cudaStream_t stream = nullptr;      // owned stream for the host-buffer path
     cudaStream_t sideStream = nullptr;  // direct-space branch runs here, forked/joined inside the step (and its graph)
-    cudaEvent_t evFork = nullptr, evJoin = nullptr;
+    cudaEvent_t evFork = nullptr, evJoin = nullptr, evStart = nullptr;
     bool overlapBranches = true;
     // parameters (device)
     double* q0 = nullptr;
@@ -242,7 +242,8 @@ void planCells(State& st);
 void allocPairLists(State& st);
 int cellsPerAxis(const State& st, int d);                                                // direct.cu: cell grid for the current box
 void invalidatePairLists(State& st);                                                     // direct.cu: the next evaluation rebuilds                                                          // direct.cu: (re)allocate the candidate lists for st.listCap
-void launchDirect(State& st, const double* dPos, bool forces, int energyMode /*0 none, 1 FP32 terms, 2 FP64 terms*/, bool emitPairs, long long* dForce, long long* dDedq, cudaStream_t s); // piece (2)
+void launchDirect(State& st, const double* dPos, bool forces, int energyMode /*0 none, 1 FP32 terms, 2 FP64 terms*/, bool emitPairs, long long* dForce, long long* dDedq, cudaStream_t s,
+                  int phase = 0 /*0 all, 1 position-only part (search), 2 the rest*/); // piece (2)
 void mark(State& st, const char* name, cudaStream_t s);   // per-kernel timing marker (no-op unless st.timing)
 // the kernel sequence of one evaluation (api.cu); skipDiscardedEnergy: do not produce the partial energy the
 // reference returns (and OpenMM discards) when includeEnergy is false -- used by the MD harness

@@ -201,6 +201,17 @@ __global__ void __launch_bounds__(256) refreshSortedKernel(CellParams p, const d
     sortedLocalD[s] = make_double4(loc[0], loc[1], loc[2], qd[u]);
 }
 
+// The search half of the direct-space branch (displacement check, re-sort, lists) depends on the positions only and is
+// enqueued before the charge-flux assembly has finished; the sorted records get this evaluation's charges here.
+__global__ void __launch_bounds__(256) refreshChargesKernel(int N, const float* __restrict__ qf, const double* __restrict__ qd,
+        const float4* __restrict__ sortedMeta, float4* __restrict__ sortedLocal, double4* __restrict__ sortedLocalD) {
+    const int s = blockIdx.x*blockDim.x + threadIdx.x;
+    if (s >= N) return;
+    const int u = __float_as_int(sortedMeta[s].z);
+    sortedLocal[s].w = qf[u];
+    sortedLocalD[s].w = qd[u];
+}
+
 __global__ void finishListKernel(int* __restrict__ rebuildFlag, unsigned long long* __restrict__ counters) {
     if (threadIdx.x == 0 && blockIdx.x == 0 && *rebuildFlag) { *rebuildFlag = 0; counters[13] += 1ull; }     // [13]: list builds so far
 }
@@ -1072,11 +1083,15 @@ void planCells(State& st) {
 // fast / generic pair kernel: [5] / [6] (first pass), [8] / [9] (energy pass of an energy+forces call), [10] list builder;
 // [7] clusters left to the generic kernel; [11] list overflows so far (not reset: the host enlarges listCap when it grows);
 // [12] longest candidate list so far; [13] list builds so far.
-void launchDirect(State& st, const double* dPos, bool forces, int emode, bool emitPairs, long long* dForce, long long* dDedq, cudaStream_t s) {
+// phase 0: the whole branch; 1: the part that needs only the positions (displacement check, re-sort, candidate lists);
+// 2: the rest (charges into the sorted records, pair passes), after a phase-1 call of the same evaluation
+void launchDirect(State& st, const double* dPos, bool forces, int emode, bool emitPairs, long long* dForce, long long* dDedq, cudaStream_t s,
+                  int phase) {
     if (!forces && emode == 0 && !emitPairs) return;
     CellPlan& c = st.cells;
     CellParams cp{st.N, c.nc[0], c.nc[1], c.nc[2], c.ncells, 1.0/st.box.L[0], 1.0/st.box.L[1], 1.0/st.box.L[2], c.csd[0], c.csd[1], c.csd[2]};
     const double skin = c.smallBox ? 0.0 : effectiveSkin(st);
+    if (phase != 2) {
     CFX_CUDA(cudaMemsetAsync(st.cellCount, 0, sizeof(int)*(c.ncells + 1), s));
     CFX_CUDA(cudaMemsetAsync(st.pairCounters + 5, 0, sizeof(unsigned long long)*2, s));
     CFX_CUDA(cudaMemsetAsync(st.pairCounters + 8, 0, sizeof(unsigned long long)*3, s));
@@ -1102,6 +1117,11 @@ void launchDirect(State& st, const double* dPos, bool forces, int emode, bool em
     refreshSortedKernel<<<(st.N + 255)/256, 256, 0, s>>>(cp, dPos, st.qf, st.q, st.sortedLocal, st.sortedMeta, st.sortedLocalD);
     CFX_LAUNCH_CHECK(); st.launches++;
     mark(st, "cell_build", s);
+    }
+    else {
+        refreshChargesKernel<<<(st.N + 255)/256, 256, 0, s>>>(st.N, st.qf, st.q, st.sortedMeta, st.sortedLocal, st.sortedLocalD);
+        CFX_LAUNCH_CHECK(); st.launches++;
+    }
 
     PairParams pp;
     pp.N = st.N; pp.Npad = st.Npad;
@@ -1146,9 +1166,9 @@ void launchDirect(State& st, const double* dPos, bool forces, int emode, bool em
     // An energy+forces call runs two passes: the FP32 force pass (no energy: lean, 5 CTAs per SM) and an energy-only FP64
     // pass over the half shell. One fused pass was slower (0.295 ms against 0.15 + 0.07 at 32k atoms): the FP64 staging
     // costs the force loop its occupancy, and an energy needs each pair only once.
-    if (fast) {
+    pp.pairList = st.pairList; pp.listCount = st.listCount; pp.listCap = st.listCap;
+    if (fast && phase != 2) {
         // candidate lists, shared by every pair pass of this evaluation
-        pp.pairList = st.pairList; pp.listCount = st.listCount; pp.listCap = st.listCap;
         pp.wrapList = st.wrapList; pp.wrapCount = st.pairCounters + 7;
         pp.workCounter = reinterpret_cast<unsigned int*>(st.pairCounters + 10);
         buildListKernel<<<std::min((groups + P_WARPS - 1)/P_WARPS, 8*numSM), P_WARPS*32, 0, s>>>(pp);
@@ -1157,6 +1177,7 @@ void launchDirect(State& st, const double* dPos, bool forces, int emode, bool em
         CFX_LAUNCH_CHECK(); st.launches++;
         mark(st, "pair_list", s);
     }
+    if (phase == 1) return;
     // An energy+forces call runs two passes: the FP32 force pass (no energy: lean, 5 CTAs per SM) and an energy-only FP64
     // pass over the half shell. One fused pass was slower: the FP64 staging costs the force loop its occupancy, and an
     // energy needs each pair only once.

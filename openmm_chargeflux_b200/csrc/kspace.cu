@@ -552,9 +552,12 @@ void planKSpace(State& st) {
     const int ctasPerSM = std::max(1, std::min(4, (int) ((size_t) 220*1024/(f.smem + 1024))));
     const int slots = ctasPerSM*numSM;
     int splits = std::max(1, slots/std::max(1, f.rowTiles));
-    // stages (of 32 atoms) per CTA at least: small row shards (multi-GPU) would otherwise be cut into hundreds of short
-    // CTAs whose partial sums the coefficient kernel then has to add (8 ranks at 32k atoms: 0.176 -> 0.160 ms per rank)
-    int minStages = 16;
+    // stages (of 32 atoms) per CTA at least. Row shards (multi-GPU) would otherwise be cut into hundreds of short CTAs
+    // whose partial sums the coefficient kernel then has to add (8 ranks at 32k atoms: 0.176 -> 0.160 ms per rank); an
+    // unsharded small box keeps short FP32 accumulation chains (the split sums are added in FP64: with one 648-atom
+    // chain per thread the reciprocal energy of the 216-water boxes moves by 2e-7, too much for their 1e-6 of a
+    // 25 kJ/mol total)
+    int minStages = st.shardCount > 1 ? 16 : 4;
     if (const char* e = getenv("CFX_S_MIN_STAGES")) minStages = std::max(1, atoi(e));     // experiments
     const int maxSplits = std::max(1, st.Npad/(minStages*S_ATOMS_PER_STAGE));
     splits = std::min(splits, maxSplits);

@@ -139,7 +139,9 @@ def test_sharded_handles_sum_to_the_unsharded_result(world, build_native):
     stream.synchronize()
     fs = d_force.cpu().numpy().reshape(3, npad)[:, :n].T / FIXED_SCALE
     es = d_energy.cpu().numpy()
-    assert abs(es[4] - e) <= 1e-8 * abs(e)
+    # (a rank's FP32 structure-factor partial sums run over other atom splits than the unsharded handle's: the
+    # reciprocal energy of the two agrees to FP32 summation noise, ~2e-8 of the total here, not to the last bit)
+    assert abs(es[4] - e) <= 1e-7 * abs(e)
     assert np.abs(es[:4] - comps[:4]).max() <= 1e-8 * np.abs(comps[:4]).max()
     assert rel_rms(fs, f) <= 2e-6
 
@@ -175,7 +177,7 @@ def test_execute_shard_fills_the_reduction_buffer_like_execute_device(flags, bui
     es = buf[3 * npad:3 * npad + 5] / ENERGY_SCALE
     # includeEnergy=False: the partial energy OpenMM discards is summed from FP32 pair terms, and a shard deals its
     # clusters' stencil columns over more CTAs than the whole evaluation does (different FP32 partial sums)
-    assert abs(es[4] - e) <= (1e-8 if flags[1] else 1e-6) * max(abs(e), 1e-3 * np.abs(comps[:4]).max())
+    assert abs(es[4] - e) <= (1e-7 if flags[1] else 1e-6) * max(abs(e), 1e-3 * np.abs(comps[:4]).max())
     assert abs(es[:4].sum() - es[4]) <= 1e-6
     assert rel_rms(fs, f) <= 2e-6
 
@@ -200,7 +202,7 @@ def test_multi_device_handle_matches_the_single_gpu_evaluation(ndev, build_nativ
         fm = np.full_like(pos, 0.5)
         cm = np.zeros(_abi.E_COUNT)
         em = multi.execute(pos, box, fm, *flags, components=cm)
-        assert abs(em - e) <= (1e-8 if flags[1] else 1e-6) * max(abs(e), 1e-3 * np.abs(comps[:4]).max())
+        assert abs(em - e) <= (1e-7 if flags[1] else 1e-6) * max(abs(e), 1e-3 * np.abs(comps[:4]).max())
         assert rel_rms(fm - 0.5, f) <= 2e-6
     multi.close()
 
