@@ -40,7 +40,13 @@ namespace {
 
 inline float __int_as_float_host(int v) { float f; memcpy(&f, &v, 4); return f; }
 __device__ __forceinline__ unsigned long long globalTimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+// role timeline of the tensor gather (tools/gt_trace.py): compiled in only with -DCFX_GT_TRACE_BUILD (the stamps and
+// their predicates cost the epilogue loop ~6 % of its instructions even when the trace buffer is absent)
+#ifdef CFX_GT_TRACE_BUILD
 #define GT_STAMP(slot) do { if (p.trace && lane == 0) p.trace[blockIdx.x*32 + (slot)] = globalTimer(); } while (0)
+#else
+#define GT_STAMP(slot) do { } while (0)
+#endif
 __device__ __forceinline__ void namedBarrier(int id, int threads) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(threads) : "memory"); }
 
 constexpr int GT_MMA_WARP = 2;               // warps 2-3: MMA issuers, one per accumulator slot
@@ -105,11 +111,13 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gatherTensorKernel(GTParams p, 
             const uint32_t planeFloats = p.planeBytes/4;
             unsigned char* raw = smem + p.offRaw;
             int rs = 0; uint32_t rph = 0;
+            int colTile = u0 % p.numColTiles;                        // (no division in the loops: units advance column tile by column tile)
             for (int unit = u0; unit < u1; unit++) {
                 if (unit - u0 >= p.rawStages) mbarWait(&rawEmpty[rs], rph ^ 1);
                 mbarExpectTx(&rawFull[rs], p.planeBytes);
-                bulkLoad(raw + (size_t) rs*p.planeBytes, p.coefT + (size_t) (unit % p.numColTiles)*planeFloats, p.planeBytes, &rawFull[rs]);
+                bulkLoad(raw + (size_t) rs*p.planeBytes, p.coefT + (size_t) colTile*planeFloats, p.planeBytes, &rawFull[rs]);
                 if (++rs == p.rawStages) { rs = 0; rph ^= 1; }
+                if (++colTile == p.numColTiles) colTile = 0;
             }
         }
         __syncwarp();
@@ -127,8 +135,9 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gatherTensorKernel(GTParams p, 
         int ob = 0; uint32_t oph = 0, aPh = 0;
         int curGroup = -1;
         uint32_t seq = 0;
-        for (int unit = u0; unit < u1; unit++) {
-            const int group = unit/p.numColTiles;
+        int group = u0/p.numColTiles, colTile = u0 - group*p.numColTiles;
+        for (int unit = u0; unit < u1; unit++, colTile++) {
+            if (colTile == p.numColTiles) { colTile = 0; group++; }
             if (group != curGroup) {
                 curGroup = group;
                 mbarWait(aFull, aPh); aPh ^= 1;
@@ -232,8 +241,9 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gatherTensorKernel(GTParams p, 
             cc = gi.z;
             __syncwarp();
         }
-        for (int unit = u0; unit < u1; unit++) {
-            const int group = unit/p.numColTiles;
+        int group = u0/p.numColTiles, colTile = u0 - group*p.numColTiles;
+        for (int unit = u0; unit < u1; unit++, colTile++) {
+            if (colTile == p.numColTiles) { colTile = 0; group++; }
             if (group != curGroup) {
                 const int gs = (curGroup < 0) ? 1 : 8;
                 if (warp == GT_EPI_WARP0) GT_STAMP(gs);
@@ -279,8 +289,10 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gatherTensorKernel(GTParams p, 
             }
             if (unit + 1 < u1) splitUnit(unit + 1);
             // row data / Ex of the NEXT unit are fetched while this one is processed (no exposed global latency)
-            const int unitN = (unit + 1 < u1) ? unit + 1 : unit;
-            const int groupN = unitN/p.numColTiles, g8N = (unitN - groupN*p.numColTiles)*SUBS + sub;
+            // (the next unit: next column tile of this atom group, or the first one of the next group; the last unit repeats itself)
+            int groupN = group, colN = colTile;
+            if (unit + 1 < u1 && ++colN == p.numColTiles) { colN = 0; groupN++; }
+            const int g8N = colN*SUBS + sub;
             const int4 giN = __ldg(p.groupInfo + g8N);
             float4 rdN = make_float4(0.f, 0.f, 0.f, 0.f);
             if (lane < 8) rdN = __ldg(p.rowData + p.signedLo + 8*g8N + lane);
