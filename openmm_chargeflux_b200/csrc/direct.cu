@@ -515,9 +515,16 @@ __global__ void __launch_bounds__(P_WARPS*32, (FAST && EMODE != 2) ? P_FAST_MINB
                         const double y = fma(0.5*y0, ey, y0);
                         // erfc(alpha r)/r = 1/r - alpha G(alpha^2 s), G(z) = erf(sqrt z)/sqrt z entire in z: one polynomial
                         const double t = fma(sD, p.eTScale, -1.0);
-                        double g = p.ePoly[E_POLY_DEG];
+                        // even and odd part as two independent Horner chains in t^2 (the single chain of 20 dependent DFMAs
+                        // left the FP64 pipe waiting on its own latency)
+                        const double t2 = t*t;
+                        double ge = p.ePoly[E_POLY_DEG], go = p.ePoly[E_POLY_DEG - 1];
                         #pragma unroll
-                        for (int k = E_POLY_DEG - 1; k >= 0; k--) g = fma(g, t, p.ePoly[k]);
+                        for (int k = E_POLY_DEG - 2; k >= 0; k -= 2) {
+                            ge = fma(ge, t2, p.ePoly[k]);
+                            if (k > 0) go = fma(go, t2, p.ePoly[k - 1]);
+                        }
+                        const double g = fma(go, t, ge);
                         const double fv = fma(-p.alphaD, g, y);
                         en = fma(on ? qq : 0.0, fv, en);
                         if (LJ) {
