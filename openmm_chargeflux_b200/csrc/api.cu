@@ -118,6 +118,13 @@ __global__ void addToMappedKernel(int n, const double* __restrict__ src, double*
     if (i < n) dst[i] += src[i];
 }
 
+// host entry point: positions read by the SMs from page-locked host memory (a copy node of this size costs ~50 us of
+// DMA set-up and transfer on the critical path of the step; the load-through kernel ~15 us)
+__global__ void fetchMappedKernel(int n, const double* __restrict__ src, double* __restrict__ dst) {
+    const int i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+}
+
 // Only for handles created with CFX_OPT_PIN_CALLER_BUFFERS (the caller promises that a buffer it passes stays allocated
 // until it passes a different one or destroys the handle): page-lock a caller buffer once it has been passed twice in a
 // row (buffers that change every call are staged: registering costs more than the copy). Returns true when `ptr` is
@@ -275,6 +282,7 @@ int cfx_create(const cfx_system_desc* d, const cfx_options* opts, cfx_handle** o
         const int pm = opts ? opts->list_skin_pm : 0;
         st.skin = pm < 0 ? 0.0 : (pm == 0 ? 0.1 : 1e-3*pm);
         if (const char* e = getenv("CFX_LIST_SKIN")) st.skin = std::max(0.0, atof(e));
+        if (const char* e = getenv("CFX_HOST_COPY_KERNELS")) st.hostCopyKernels = atoi(e) != 0;
     }
     if (d->use_pbc == 0 && st.shardCount != 1)
         throw ArgError("sharded handles need a periodic system: the non-periodic all-pairs branch is not partitioned");
@@ -467,25 +475,39 @@ int cfx_execute(cfx_handle* h, const double* positions, const double* box, int i
     if (!regP) memcpy(st.hPos, positions, vecBytes);
     const int key = (incF ? 1 : 0) | (incE ? 2 : 0);
     st.launches = 0;
+    const bool byKernels = st.hostCopyKernels;
     auto enqueueAll = [&]() {
-        CFX_CUDA(cudaMemcpyAsync(st.pos, regP ? positions : st.hPos, vecBytes, cudaMemcpyHostToDevice, s));
+        if (byKernels) {
+            const double* src = regP ? static_cast<const double*>(st.posReg.dev) : st.hPos;     // page-locked either way
+            fetchMappedKernel<<<(3*st.N + 255)/256, 256, 0, s>>>(3*st.N, src, st.pos);
+            CFX_LAUNCH_CHECK(); st.launches++;
+        }
+        else
+            CFX_CUDA(cudaMemcpyAsync(st.pos, regP ? positions : st.hPos, vecBytes, cudaMemcpyHostToDevice, s));
+        const long long* acc = st.forceFixed;
+        const long long* accEnergy = st.energyFixed;
         if (!sharded) {
             CFX_CUDA(cudaMemsetAsync(st.forceFixed, 0, sizeof(long long)*3*st.Npad, s));
             enqueueEvaluation(st, st.pos, incF, incE, st.forceFixed, s, false);
-            launchFinalize(st, st.forceFixed, st.energyFixed, s);
         }
         else {
             // this rank's shard into the reduction buffer (forces 2^32, energies 2^24 appended), one sum all-reduce over
             // the communicator, then every rank converts the whole result
-            long long* acc = st.reduceBuf;
             const size_t count = 3*(size_t) st.Npad + 8;
-            CFX_CUDA(cudaMemsetAsync(acc, 0, sizeof(long long)*count, s));
-            enqueueEvaluation(st, st.pos, incF, incE, acc, s, false);
-            appendEnergyFixedKernel<<<1, 32, 0, s>>>(st.energyFixed, acc + 3*(size_t) st.Npad);
+            CFX_CUDA(cudaMemsetAsync(st.reduceBuf, 0, sizeof(long long)*count, s));
+            enqueueEvaluation(st, st.pos, incF, incE, st.reduceBuf, s, false);
+            appendEnergyFixedKernel<<<1, 32, 0, s>>>(st.energyFixed, st.reduceBuf + 3*(size_t) st.Npad);
             CFX_LAUNCH_CHECK(); st.launches++;
-            commAllReduce(st, acc, count, s);
-            launchFinalize(st, acc, acc + 3*(size_t) st.Npad, s);
+            commAllReduce(st, st.reduceBuf, count, s);
+            acc = st.reduceBuf; accEnergy = st.reduceBuf + 3*(size_t) st.Npad;
         }
+        if (byKernels) {
+            // one kernel converts the fixed-point sums and stores them in page-locked host memory: added into the caller's
+            // registered array, or written to the staging array the host adds from after the sync
+            launchFinalizeToHost(st, acc, accEnergy, regF ? static_cast<double*>(st.forceReg.dev) : (forces ? st.hForce : nullptr), regF, s);
+            return;
+        }
+        launchFinalize(st, acc, accEnergy, s);
         if (regF) {
             addToMappedKernel<<<(3*st.N + 255)/256, 256, 0, s>>>(3*st.N, st.forceOut, static_cast<double*>(st.forceReg.dev));
             CFX_LAUNCH_CHECK(); st.launches++;
@@ -498,7 +520,7 @@ int cfx_execute(cfx_handle* h, const double* positions, const double* box, int i
     };
     if (st.useGraph) {
         const void* gp = regP ? positions : nullptr;
-        const void* gf = regF ? forces : static_cast<const void*>(st.hForce);      // staged: D2H always goes to hForce
+        const void* gf = regF ? forces : (forces || !byKernels ? static_cast<const void*>(st.hForce) : nullptr);   // staged: results go to hForce
         if (st.graphs[key] && (st.graphPos[key] != gp || st.graphForce[key] != gf)) {
             cudaGraphExecDestroy(st.graphs[key]); st.graphs[key] = nullptr;
         }

@@ -127,6 +127,7 @@ struct State {
     long long* reduceBuf = nullptr;     // [3*Npad + 8] reduction buffer of the host-buffer sharded path
     bool skipDiscardedEnergy = false;   // cfx_options.flags & CFX_OPT_SKIP_DISCARDED_ENERGY
     bool pinCallerBuffers = false;      // cfx_options.flags & CFX_OPT_PIN_CALLER_BUFFERS
+    bool hostCopyKernels = true;        // host path: positions fetched / results stored by kernels on page-locked memory, no copy nodes
     KSpacePlan ks;
     CellPlan cells;
     int64_t numKVectors = 0;
@@ -228,6 +229,8 @@ void launchChainRule(State& st, long long* dForce, const long long* dDedq, cudaS
 void launchExclusionCorrection(State& st, const double* dPos, bool forces, long long* dForce, long long* dDedq, cudaStream_t s);
 void launchNoCutoff(State& st, const double* dPos, bool forces, bool energy, long long* dForce, long long* dDedq, cudaStream_t s);
 void launchFinalize(State& st, const long long* dForce, const long long* dEnergyFixed, cudaStream_t s);
+void launchFinalizeToHost(State& st, const long long* dForce, const long long* dEnergyFixed, double* hostForce, bool accumulate,
+                          cudaStream_t s);
 void commAllReduce(State& st, long long* buf, size_t count, cudaStream_t s);           // comm.cu: in-place int64 sum over the ranks
 void commDestroy(State& st);
 void planKSpace(State& st);

@@ -283,6 +283,30 @@ __global__ void __launch_bounds__(256) finalizeKernel(int N, int Npad, const lon
     }
 }
 
+// Host-buffer entry point: the same conversion written straight into page-locked host memory (the caller's registered
+// array: read-modify-write, `accumulate`; the handle's staging array: write only), energies and the list-overflow
+// counter with it, so that the step's graph ends with one kernel instead of a kernel and three copy nodes.
+__global__ void __launch_bounds__(256) finalizeToHostKernel(int N, int Npad, const long long* __restrict__ forceFixed,
+        const long long* __restrict__ energyFixed, double* hostForce, bool accumulate, double* __restrict__ hostEnergy,
+        const unsigned long long* __restrict__ overflowSrc, unsigned long long* __restrict__ hostOverflow) {
+    const int k = blockIdx.x*blockDim.x + threadIdx.x;          // element of the [N][3] array: consecutive lanes, consecutive addresses
+    if (hostForce && k < 3*N) {
+        const int i = k/3, c = k - 3*i;
+        const double v = (double) forceFixed[(size_t) c*Npad + i]*(1.0/CFX_FIXED_SCALE);
+        hostForce[k] = accumulate ? hostForce[k] + v : v;
+    }
+    if (k == 0) {
+        double tot = 0.0;
+        for (int e = 0; e < 4; e++) {
+            const double v = (double) energyFixed[e]*(1.0/CFX_ENERGY_SCALE);
+            hostEnergy[e] = v;
+            tot += v;
+        }
+        hostEnergy[CFX_E_TOTAL] = tot;
+        if (overflowSrc) *hostOverflow = *overflowSrc;
+    }
+}
+
 inline BoxD boxOf(const State& st) { return BoxD{st.box.L[0], st.box.L[1], st.box.L[2]}; }
 
 } // namespace
@@ -336,6 +360,14 @@ void launchNoCutoff(State& st, const double* dPos, bool forces, bool energy, lon
 
 void launchFinalize(State& st, const long long* dForce, const long long* dEnergyFixed, cudaStream_t s) {
     finalizeKernel<<<(st.N + 255)/256, 256, 0, s>>>(st.N, st.Npad, dForce, dEnergyFixed, st.forceOut, st.energyOut);
+    CFX_LAUNCH_CHECK(); st.launches++;
+    mark(st, "finalize", s);
+}
+
+void launchFinalizeToHost(State& st, const long long* dForce, const long long* dEnergyFixed, double* hostForce, bool accumulate,
+                          cudaStream_t s) {
+    finalizeToHostKernel<<<(3*st.N + 255)/256, 256, 0, s>>>(st.N, st.Npad, dForce, dEnergyFixed, hostForce, accumulate, st.hEnergy,
+            (st.pbc && st.pairCounters) ? st.pairCounters + 11 : nullptr, st.hListOverflow);
     CFX_LAUNCH_CHECK(); st.launches++;
     mark(st, "finalize", s);
 }
