@@ -38,7 +38,8 @@ def load_library():
     lib.cfx_create.argtypes = [C.POINTER(_abi.SystemDesc), C.POINTER(_abi.Options), C.POINTER(C.c_void_p)]
     lib.cfx_destroy.argtypes = [C.c_void_p]
     lib.cfx_destroy.restype = None
-    lib.cfx_execute.argtypes = [C.c_void_p, _abi.c_double_p, _abi.c_double_p, C.c_int, C.c_int, _abi.c_double_p, _abi.c_double_p]
+    # plain addresses: building a typed ctypes pointer from a numpy array costs ~5 us each, the per-step call passes four
+    lib.cfx_execute.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     lib.cfx_execute_device.argtypes = [C.c_void_p, C.c_void_p, _abi.c_double_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p]
     lib.cfx_execute_shard.argtypes = [C.c_void_p, C.c_void_p, _abi.c_double_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
@@ -74,6 +75,14 @@ def _dp(a):
     return a.ctypes.data_as(_abi.c_double_p)
 
 
+def _addr(a):
+    """Address of a numpy array's buffer without going through ndarray.ctypes (the per-step call path)."""
+    try:
+        return C.addressof(C.c_char.from_buffer(a))
+    except (TypeError, ValueError):        # read-only or otherwise unexportable buffer
+        return a.ctypes.data
+
+
 def _box9(box):
     b = np.asarray(box, dtype=np.float64)
     if b.shape == (3,):
@@ -102,6 +111,9 @@ class CalcCoulForceKernel:
                                   list_skin_pm=0 if list_skin is None else (-1 if list_skin <= 0 else max(1, int(round(list_skin * 1e3)))))
         self._h = None
         self.num_particles = 0
+        self._e5 = np.zeros(_abi.E_COUNT)       # per-call scratch of execute(), addresses taken once
+        self._b9 = np.zeros(9)
+        self._e5_addr, self._b9_addr = self._e5.ctypes.data, self._b9.ctypes.data
 
     def _check(self, code):
         if code != _abi.CFX_OK:
@@ -129,17 +141,19 @@ class CalcCoulForceKernel:
     # CalcCoulForceKernel::execute(ContextImpl&, includeForces, includeEnergy): adds to `forces`
     # (a [N,3] float64 array, the platform's force vector) and returns the energy in kJ/mol.
     def execute(self, positions, box, forces=None, includeForces=True, includeEnergy=True, components=None):
-        pos = np.ascontiguousarray(positions, dtype=np.float64).reshape(-1)
+        pos = np.ascontiguousarray(positions, dtype=np.float64)
         if pos.size != 3 * self.num_particles:
             raise CfxError("positions has %d values, expected %d" % (pos.size, 3 * self.num_particles))
-        b = _box9(box)
-        e5 = np.zeros(_abi.E_COUNT)
+        self._b9[:] = _box9(box)
         fptr = None
         if forces is not None:
             if forces.dtype != np.float64 or not forces.flags.c_contiguous or forces.size != pos.size:
                 raise CfxError("forces must be a C-contiguous float64 array of shape [N,3]")
-            fptr = _dp(forces)
-        self._check(self._lib.cfx_execute(self._h, _dp(pos), _dp(b), int(includeForces), int(includeEnergy), _dp(e5), fptr))
+            fptr = _addr(forces)
+        e5 = self._e5
+        if self._lib.cfx_execute(self._h, _addr(pos), self._b9_addr, 1 if includeForces else 0, 1 if includeEnergy else 0,
+                                 self._e5_addr, fptr) != _abi.CFX_OK:
+            raise CfxError(self._lib.cfx_last_error().decode())
         if components is not None:
             components[:] = e5
         return float(e5[_abi.E_TOTAL])
