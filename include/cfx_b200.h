@@ -78,6 +78,11 @@ typedef struct cfx_system_desc {
  * OpenMM discards; by default it is reproduced (FP32 pair terms). With this flag such calls
  * return 0 for the direct component and skip its arithmetic. */
 #define CFX_OPT_SKIP_DISCARDED_ENERGY 2
+/* KMAX_FOLLOWS_BOX: the reference fixes kmax from the System's DEFAULT box at initialize and never revisits it
+ * (ReferenceCoulKernels.cpp:403-420), so under a barostat the reciprocal-space error drifts with the box (SURVEY.md
+ * section 8 f4). With this flag the same estimator is re-applied to the box of the call whenever the box has changed, and the
+ * reciprocal-space plan is rebuilt when kmax moves. Default off = the reference's behaviour. */
+#define CFX_OPT_KMAX_FOLLOWS_BOX 4
 
 /* Execution options (all optional; pass NULL for defaults). */
 typedef struct cfx_options {

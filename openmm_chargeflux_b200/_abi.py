@@ -9,6 +9,7 @@ import ctypes as C
 CFX_OK, CFX_ERR_ARGUMENT, CFX_ERR_CUDA, CFX_ERR_STATE = 0, 1, 2, 3
 OPT_PIN_CALLER_BUFFERS = 1
 OPT_SKIP_DISCARDED_ENERGY = 2
+OPT_KMAX_FOLLOWS_BOX = 4
 COMM_ID_BYTES = 128
 E_SELF, E_RECIP, E_DIRECT, E_EXCL, E_TOTAL, E_COUNT = 0, 1, 2, 3, 4, 5
 ONE_4PI_EPS0 = 138.935456

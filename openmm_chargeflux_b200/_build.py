@@ -67,9 +67,11 @@ def build_plugin(force=False, verbose=False):
     if not os.path.isdir(api_inc) or not os.path.exists(os.path.join(api_out, "libOpenMMCoul.so")):
         return PLUGIN_LIB if os.path.exists(PLUGIN_LIB) else None
     src_dir = os.path.join(PKG, "plugin")
-    sources = [os.path.join(src_dir, f) for f in ("B200CoulKernels.cpp", "B200CudaCoulKernels.cpp", "B200CoulKernelFactory.cpp")]
+    sources = [os.path.join(src_dir, f) for f in ("B200CoulKernels.cpp", "B200CudaCoulKernels.cpp", "B200CoulKernelFactory.cpp",
+                                                      "CoulForceProxy.cpp")]
     deps = sources + [os.path.join(src_dir, "B200CoulKernels.h"), os.path.join(src_dir, "B200CudaCoulKernels.h"),
-                      os.path.join(src_dir, "B200CoulKernelFactory.h"), os.path.join(ROOT, "include", "cfx_b200.h")]
+                      os.path.join(src_dir, "B200CoulKernelFactory.h"), os.path.join(src_dir, "CoulForceProxy.h"),
+                      os.path.join(ROOT, "include", "cfx_b200.h"), os.path.join(api_out, "libOpenMMShim.so")]
     if not force and not _newer(PLUGIN_LIB, deps):
         return PLUGIN_LIB
     cuda_home = os.environ.get("CUDA_HOME", "/usr/local/cuda")

@@ -212,12 +212,51 @@ void ensureCells(State& st) {
     planCells(st);
 }
 
+/* ReferenceCoulKernels.cpp:403-420: smallest kmax per axis whose error estimate is below the tolerance, forced odd */
+void deriveKmax(const State& st, const double* box, int K[3]) {
+    for (int a = 0; a < 3; a++) {
+        int k = 1;
+        while (ewaldErrorEstimate(k, box[4*a], st.alpha) > st.tol) k++;
+        if (k%2 == 0) k++;
+        K[a] = k;
+    }
+}
+
+void setKmax(State& st, const int K[3]) {
+    for (int a = 0; a < 3; a++) st.ks.K[a] = K[a];
+    const long long kx = K[0], ky = K[1], kz = K[2];
+    st.numKVectors = (kz - 1) + (ky - 1)*(2*kz - 1) + (kx - 1)*(2*ky - 1)*(2*kz - 1);
+}
+
+void freeKSpace(State& st) {
+    st.planGeneration++;
+    void* ptrs[] = {st.rowS, st.colX, st.colY, st.colZ4, st.sPart, st.gCoef, st.gRowInfo, st.ks_signedStart, st.zSplit, st.coefT,
+                    st.gRowData, st.gGroupInfo, st.gtTrace};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    st.rowS = nullptr; st.colX = st.colY = nullptr; st.colZ4 = nullptr; st.sPart = nullptr; st.gCoef = nullptr; st.gRowInfo = nullptr;
+    st.ks_signedStart = nullptr; st.zSplit = nullptr; st.coefT = nullptr; st.gRowData = nullptr; st.gGroupInfo = nullptr;
+    st.gtTrace = nullptr;
+}
+
 void ensureBox(State& st, const double* box) {
     checkBox(box);
     if (box[0] < 2*st.cutoff || box[4] < 2*st.cutoff || box[8] < 2*st.cutoff)
         throw ArgError("the periodic box must be at least twice the cutoff in every direction");
     const bool changed = st.box.L[0] != box[0] || st.box.L[1] != box[4] || st.box.L[2] != box[8];
     if (changed) { setBox(st, box); dropGraphs(st); }
+    if (changed && st.kmaxFollowsBox && st.N > 0) {
+        int K[3];
+        deriveKmax(st, box, K);
+        if (K[0] != st.ks.K[0] || K[1] != st.ks.K[1] || K[2] != st.ks.K[2]) {
+            CFX_CUDA(cudaDeviceSynchronize());                     // nothing may still read the old tables
+            freeKSpace(st);
+            const KSpacePlan old = st.ks;
+            st.ks = KSpacePlan();
+            setKmax(st, K);
+            try { planKSpace(st); }
+            catch (...) { freeKSpace(st); st.ks = KSpacePlan(); setKmax(st, old.K); planKSpace(st); throw; }
+        }
+    }
     ensureCells(st);
     if (changed) invalidatePairLists(st);
 }
@@ -277,6 +316,7 @@ int cfx_create(const cfx_system_desc* d, const cfx_options* opts, cfx_handle** o
     if (st.shardRank < 0 || st.shardRank >= st.shardCount) throw ArgError("shard_rank out of range");
     st.useGraph = opts ? (opts->use_graph != 0) : true;
     st.pinCallerBuffers = opts && (opts->flags & CFX_OPT_PIN_CALLER_BUFFERS);
+    st.kmaxFollowsBox = opts && (opts->flags & CFX_OPT_KMAX_FOLLOWS_BOX);
     st.skipDiscardedEnergy = opts && (opts->flags & CFX_OPT_SKIP_DISCARDED_ENERGY);
     {
         const int pm = opts ? opts->list_skin_pm : 0;
@@ -398,14 +438,9 @@ int cfx_create(const cfx_system_desc* d, const cfx_options* opts, cfx_handle** o
         st.cutoff = d->cutoff;
         st.tol = d->ewald_tol;
         st.alpha = (1.0/st.cutoff)*sqrt(-log(2.0*st.tol));            // :401
-        for (int a = 0; a < 3; a++) {                                  // :403-420, from the DEFAULT box
-            int k = 1;
-            while (ewaldErrorEstimate(k, d->default_box[4*a], st.alpha) > st.tol) k++;
-            if (k%2 == 0) k++;
-            st.ks.K[a] = k;
-        }
-        const long long kx = st.ks.K[0], ky = st.ks.K[1], kz = st.ks.K[2];
-        st.numKVectors = (kz - 1) + (ky - 1)*(2*kz - 1) + (kx - 1)*(2*ky - 1)*(2*kz - 1);
+        int K[3];
+        deriveKmax(st, d->default_box, K);                             // :403-420, from the DEFAULT box
+        setKmax(st, K);
         setBox(st, d->default_box);
         if (N > 0) {
             planKSpace(st);

@@ -127,6 +127,7 @@ struct State {
     long long* reduceBuf = nullptr;     // [3*Npad + 8] reduction buffer of the host-buffer sharded path
     bool skipDiscardedEnergy = false;   // cfx_options.flags & CFX_OPT_SKIP_DISCARDED_ENERGY
     bool pinCallerBuffers = false;      // cfx_options.flags & CFX_OPT_PIN_CALLER_BUFFERS
+    bool kmaxFollowsBox = false;        // cfx_options.flags & CFX_OPT_KMAX_FOLLOWS_BOX
     bool hostCopyKernels = true;        // host path: positions fetched / results stored by kernels on page-locked memory, no copy nodes
     KSpacePlan ks;
     CellPlan cells;

@@ -130,6 +130,62 @@ class CoulForce:
             self._fwater_params += np.asarray(par, dtype=np.float64).ravel().tolist()
         return self
 
+    # -- serialization (the reference registers no proxy) ------------------
+    # Same XML as plugin/CoulForceProxy.cpp writes through OpenMM's XmlSerializer, byte for byte: attributes in
+    # alphabetical order (the node's property map), doubles as %.17g, one tab per level.
+    def to_xml(self):
+        def el(depth, name, attrs, children=None):
+            head = "\t" * depth + "<" + name + "".join(' %s="%s"' % (k, attrs[k]) for k in sorted(attrs))
+            if not children:
+                return [head + "/>"]
+            return [head + ">"] + children + ["\t" * depth + "</" + name + ">"]
+
+        def d(v):
+            return "%.17g" % v
+
+        n = self.getNumParticles()
+        kids = []
+        kids += el(1, "Particles", {}, [x for i in range(n) for x in el(2, "Particle", {
+            "q": d(self._charges[i]), "sig": d(self._ljparams[2 * i]), "eps": d(self._ljparams[2 * i + 1])})])
+        kids += el(1, "Exceptions", {}, [x for p1, p2 in self._exclusions for x in el(2, "Exception", {"p1": p1, "p2": p2})])
+        kids += el(1, "FluxBonds", {}, [x for i in range(self.getNumFluxBonds()) for x in el(2, "Bond", dict(
+            zip(("p1", "p2"), self._fbond_idx[2 * i:2 * i + 2]), **dict(zip(("k", "b"), map(d, self._fbond_params[2 * i:2 * i + 2])))))])
+        kids += el(1, "FluxAngles", {}, [x for i in range(self.getNumFluxAngles()) for x in el(2, "Angle", dict(
+            zip(("p1", "p2", "p3"), self._fangle_idx[3 * i:3 * i + 3]),
+            **dict(zip(("k", "theta"), map(d, self._fangle_params[2 * i:2 * i + 2])))))])
+        kids += el(1, "FluxWaters", {}, [x for i in range(self.getNumFluxWaters()) for x in el(2, "Water", dict(
+            zip(("po", "ph1", "ph2"), self._fwater_idx[3 * i:3 * i + 3]),
+            **dict(zip(("k1", "k2", "kub", "b0", "ub0"), map(d, self._fwater_params[5 * i:5 * i + 5])))))])
+        root = el(0, "Force", {"type": "CoulForce", "version": 1, "forceGroup": self._force_group, "cutoff": d(self._cutoff),
+                               "ewaldTolerance": d(self._ewald_tol), "usesPeriodic": 1 if self._pbc else 0}, kids)
+        return '<?xml version="1.0" ?>\n' + "\n".join(root) + "\n"
+
+    @classmethod
+    def from_xml(cls, text):
+        import xml.etree.ElementTree as ET
+        root = ET.fromstring(text)
+        if root.get("type") != "CoulForce":
+            raise ValueError("the XML does not hold a CoulForce (type=%r)" % root.get("type"))
+        if int(root.get("version")) != 1:
+            raise ValueError("Unsupported version number")
+        f = cls()
+        f.setForceGroup(int(root.get("forceGroup", 0)))
+        f.setCutoffDistance(float(root.get("cutoff")))
+        f.setEwaldErrorTolerance(float(root.get("ewaldTolerance")))
+        f.setUsesPeriodicBoundaryConditions(int(root.get("usesPeriodic")) != 0)
+        for p in root.find("Particles"):
+            f.addParticle(float(p.get("q")), float(p.get("sig")), float(p.get("eps")))
+        for e in root.find("Exceptions"):
+            f.addException(int(e.get("p1")), int(e.get("p2")))
+        for b in root.find("FluxBonds"):
+            f.addFluxBond(int(b.get("p1")), int(b.get("p2")), float(b.get("k")), float(b.get("b")))
+        for a in root.find("FluxAngles"):
+            f.addFluxAngle(int(a.get("p1")), int(a.get("p2")), int(a.get("p3")), float(a.get("k")), float(a.get("theta")))
+        for w in root.find("FluxWaters"):
+            f.addFluxWater(int(w.get("po")), int(w.get("ph1")), int(w.get("ph2")), float(w.get("k1")), float(w.get("k2")),
+                           float(w.get("kub")), float(w.get("b0")), float(w.get("ub0")))
+        return f
+
     # -- C ABI parameter block --------------------------------------------------------------------
     def to_desc(self, default_box):
         """Build the ``cfx_system_desc`` block (include/cfx_b200.h). Returns (desc, keepalive)."""

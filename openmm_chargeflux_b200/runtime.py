@@ -98,16 +98,19 @@ class CalcCoulForceKernel:
         return "CalcCoulForce"      # CoulKernels.h:17-19
 
     def __init__(self, device=-1, shard_rank=0, shard_count=1, use_graph=True, pin_caller_buffers=False,
-                 skip_discarded_energy=False, list_skin=None):
+                 skip_discarded_energy=False, list_skin=None, kmax_follows_box=False):
         """list_skin: skin (nm) of the direct-space candidate lists (None = library default 0.1 nm, 0 = rebuild at every
         evaluation).
         pin_caller_buffers: the caller keeps the positions / forces arrays it passes to execute() alive until it passes
-        different ones or closes the kernel; they are then page-locked in place (CFX_OPT_PIN_CALLER_BUFFERS)."""
+        different ones or closes the kernel; they are then page-locked in place (CFX_OPT_PIN_CALLER_BUFFERS).
+        kmax_follows_box: re-derive kmax from the box of the call when it changes (CFX_OPT_KMAX_FOLLOWS_BOX); the default
+        keeps the kmax of the default box for the life of the kernel, as the reference does."""
         self._lib = load_library()
         self._opts = _abi.Options(device=device, shard_rank=shard_rank, shard_count=shard_count,
                                   use_graph=1 if use_graph else 0,
                                   flags=(_abi.OPT_PIN_CALLER_BUFFERS if pin_caller_buffers else 0)
-                                  | (_abi.OPT_SKIP_DISCARDED_ENERGY if skip_discarded_energy else 0),
+                                  | (_abi.OPT_SKIP_DISCARDED_ENERGY if skip_discarded_energy else 0)
+                                  | (_abi.OPT_KMAX_FOLLOWS_BOX if kmax_follows_box else 0),
                                   list_skin_pm=0 if list_skin is None else (-1 if list_skin <= 0 else max(1, int(round(list_skin * 1e3)))))
         self._h = None
         self.num_particles = 0

@@ -134,3 +134,27 @@ class ReferenceBuild(_Base):
         desc, self._keep = force.to_desc(default_box)
         self.h = C.c_void_p()
         self._check(self.lib.cfxref_create(C.byref(desc), platform.encode(), C.byref(self.h)))
+
+    def to_xml(self):
+        """XmlSerializer::serialize of the context's CoulForce (a loaded library must have registered a proxy for it)."""
+        need = C.c_int64(0)
+        self.lib.cfxref_serialize_xml.argtypes = [C.c_void_p, C.c_char_p, C.c_int64, C.POINTER(C.c_int64)]
+        self._check(self.lib.cfxref_serialize_xml(self.h, None, 0, C.byref(need)))
+        buf = C.create_string_buffer(need.value)
+        self._check(self.lib.cfxref_serialize_xml(self.h, buf, need.value, C.byref(need)))
+        return buf.value.decode()
+
+    @classmethod
+    def from_xml(cls, xml, default_box, platform="Reference", plugin=None):
+        """A context around XmlSerializer::deserialize(xml)."""
+        self = cls.__new__(cls)
+        if ReferenceBuild.lib is None:
+            ReferenceBuild.lib = C.CDLL(REF_LIB)
+            ReferenceBuild.lib.cfxref_destroy.argtypes = [C.c_void_p]
+        self._check(self.lib.cfxref_load_plugin((plugin or REF_PLUGIN).encode()))
+        box = np.ascontiguousarray(default_box, dtype=np.float64).reshape(9)
+        self.h = C.c_void_p()
+        self._check(self.lib.cfxref_create_from_xml(xml.encode(), _dp(box), platform.encode(), C.byref(self.h)))
+        self.lib.cfxref_num_particles.argtypes = [C.c_void_p]
+        self.n = self.lib.cfxref_num_particles(self.h)
+        return self

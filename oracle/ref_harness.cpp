@@ -27,6 +27,8 @@
 #include "openmm/internal/ContextImpl.h"
 #include "openmm/reference/ReferencePlatform.h"
 #include "openmm/reference/ReferenceNeighborList.h"
+#include "openmm/serialization/XmlSerializer.h"
+#include <sstream>
 
 // The parity getters read the reference kernel's private state (charges, Jacobian rows, neighbour
 // list, kmax). Access control does not change object layout; nothing in the reference is edited.
@@ -133,6 +135,46 @@ int cfxref_create(const cfx_system_desc* d, const char* platform, cfxref_handle*
 }
 
 void cfxref_destroy(cfxref_handle* h) { delete h; }
+int cfxref_num_particles(cfxref_handle* h) { return h->n; }
+
+/* XML text of the handle's CoulForce through XmlSerializer (needs a library that registered a proxy for CoulForce: the
+ * B200 plugin does at load; the reference registers none). Two-call protocol: out == NULL returns the size. */
+int cfxref_serialize_xml(cfxref_handle* h, char* out, int64_t capacity, int64_t* needed) {
+    try {
+        std::ostringstream text;
+        XmlSerializer::serialize<Force>(h->force, "Force", text);
+        const std::string s = text.str();
+        *needed = (int64_t) s.size() + 1;
+        if (!out) return CFX_OK;
+        if (capacity < *needed) { g_err = "xml buffer too small"; return CFX_ERR_ARGUMENT; }
+        memcpy(out, s.c_str(), s.size() + 1);
+        return CFX_OK;
+    } catch (std::exception& e) { g_err = e.what(); return CFX_ERR_ARGUMENT; }
+}
+
+/* A context whose CoulForce comes out of XmlSerializer::deserialize (the proxy's add* calls). */
+int cfxref_create_from_xml(const char* xml, const double* default_box, const char* platform, cfxref_handle** out) {
+    try {
+        ensurePlatforms();
+        std::istringstream text(xml);
+        Force* obj = XmlSerializer::deserialize<Force>(text);
+        CoulForce* f = dynamic_cast<CoulForce*>(obj);
+        if (!f) { delete obj; g_err = "the XML does not hold a CoulForce"; return CFX_ERR_ARGUMENT; }
+        cfxref_handle* h = new cfxref_handle();
+        h->n = f->getNumParticles();
+        for (int i = 0; i < h->n; i++) h->system.addParticle(1.0);
+        h->force = f;
+        h->system.addForce(f);
+        const double* b = default_box;
+        h->system.setDefaultPeriodicBoxVectors(Vec3(b[0],b[1],b[2]), Vec3(b[3],b[4],b[5]), Vec3(b[6],b[7],b[8]));
+        h->data = new ReferencePlatform::PlatformData(h->n);
+        Platform& p = Platform::getPlatformByName(platform);
+        h->isReferenceKernel = (std::string(platform) == "Reference");
+        h->context = new ContextImpl(h->system, p, h->data);
+        *out = h;
+        return CFX_OK;
+    } catch (std::exception& e) { g_err = e.what(); return CFX_ERR_ARGUMENT; }
+}
 
 /* energy: only the total is known to the caller of CalcCoulForceKernel::execute -> written to
  * energy[CFX_E_TOTAL]; the component slots are set to NaN. forces (may be NULL) is ADDED to. */

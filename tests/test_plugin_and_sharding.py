@@ -34,7 +34,7 @@ def test_shard_bounds_partition_everything_once():
 @pytest.mark.skipif(not os.path.exists(PLUGIN), reason="plugin adapter not built (needs the plugin's API headers)")
 def test_plugin_exports_the_loader_contract():
     lib = ctypes.CDLL(PLUGIN)
-    for sym in ("registerPlatforms", "registerKernelFactories", "registerCoulB200KernelFactories"):
+    for sym in ("registerPlatforms", "registerKernelFactories", "registerCoulB200KernelFactories", "registerCoulSerializationProxies"):
         assert hasattr(lib, sym)
 
 
