@@ -417,6 +417,12 @@ def run_ours(args, pos, box, force, workload):
     e2e_s = e2e(INCLUDE_ENERGY)
     clocks = sampler.stop(t_start, time.perf_counter()) if sampler else None     # timed loop + e2e loop, both under load
     e2e_f_s = e2e(False)
+    # the host-buffer call returns what the device-resident call does (same positions: frame 0)
+    pos_host[:] = me.frames_host[0]
+    forces_host[:] = 0.0
+    e_host = me.kernel.execute(pos_host, box, forces_host, True, INCLUDE_ENERGY)
+    e2e_check = {"forces_rel_rms_vs_device_call": float(np.sqrt(((forces_host - f_sharded) ** 2).sum() / (f_sharded ** 2).sum())),
+                 "energy_rel_vs_device_call": float(abs(e_host - e_sharded[4]) / abs(e_sharded[4]))}
 
     alpha, kmax, nk = me.kernel.ewald_params()
     line = None
@@ -440,7 +446,8 @@ def run_ours(args, pos, box, force, workload):
                                     "factors, FP32 pair terms); ns_per_day is derived from it",
                 "ns_per_day": ns_per_day(1e3 / ms_f),
                 "e2e": {"value": 1.0 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 24 * n, "d2h_bytes_per_step": 24 * n + 40,
-                        "forces_only": {"value": 1.0 / e2e_f_s, "ns_per_day": ns_per_day(1.0 / e2e_f_s)}},
+                        "forces_only": {"value": 1.0 / e2e_f_s, "ns_per_day": ns_per_day(1.0 / e2e_f_s)},
+                        "check": e2e_check},
                 "gpu_launches": int(launches_per_eval) * args.steps,
                 "clocks": clocks}
 

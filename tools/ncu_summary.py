@@ -1,5 +1,7 @@
 """Summarise an .ncu-rep (ncu --set full) launch by launch: duration, instructions, issue rate, pipes, stalls, DRAM / L2 bytes.
-   python tools/ncu_summary.py file.ncu-rep [traffic.json]   -- the optional JSON gets {kernel: dram bytes} of the LAST launch of each name"""
+   python tools/ncu_summary.py file.ncu-rep [traffic.json [bench]]   -- the optional JSON gets {kernel: dram bytes} of the LAST launch
+   of each name; with "bench" the keys are bench.py's kernel groups (capture of tools/probe_both.py: energy+forces calls first, then
+   forces only; "<group>_energy" = the energy+forces call, pair passes of one call added up)"""
 import csv, io, json, subprocess, sys
 rep = sys.argv[1]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -16,6 +18,7 @@ cols = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio"]
 scale = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "Tbyte": 1e12}
 traffic = {}
+launches = []
 for r in rows[2:]:
     d = dict(zip(hdr, r))
     u = dict(zip(hdr, units))
@@ -28,7 +31,31 @@ for r in rows[2:]:
         rd = float(d["dram__bytes_read.sum"]) * scale.get(u["dram__bytes_read.sum"], 1.0)
         wr = float(d["dram__bytes_write.sum"]) * scale.get(u["dram__bytes_write.sum"], 1.0)
         traffic[name] = {"dram_read_bytes": rd, "dram_write_bytes": wr, "duration_us": float(d["gpu__time_duration.sum"])}
+        launches.append((name, traffic[name]))
     except (KeyError, ValueError):
         pass
-if len(sys.argv) > 2:
+if len(sys.argv) > 3 and sys.argv[3] == "bench":
+    def group(name):
+        if "pairKernel" in name: return "direct_pairs"
+        if "gatherTensorKernel" in name or "gatherKernel" in name: return "kspace_gather"
+        if "structureFactor" in name: return "structure_factor"
+        return None
+    # split the launch sequence into evaluations at every flux-term kernel (the first kernel of a call that is captured)
+    evals, cur = [], None
+    for name, t in launches:
+        if "fluxTermKernel" in name or cur is None and group(name):
+            cur = {}
+            evals.append(cur)
+        g = group(name)
+        if g:
+            acc = cur.setdefault(g, {"dram_read_bytes": 0.0, "dram_write_bytes": 0.0, "duration_us": 0.0, "fp32_s": False})
+            for k in ("dram_read_bytes", "dram_write_bytes", "duration_us"): acc[k] += t[k]
+            if "structureFactorKernel" in name: acc["fp32_s"] = True
+    out = {}
+    for ev in evals:                                   # later evaluations overwrite earlier ones (warm lists)
+        energy = ev.get("structure_factor", {}).get("fp32_s", False)
+        for g, acc in ev.items():
+            out[g + ("_energy" if energy else "")] = {k: v for k, v in acc.items() if k != "fp32_s"}
+    json.dump(out, open(sys.argv[2], "w"), indent=1)
+elif len(sys.argv) > 2:
     json.dump(traffic, open(sys.argv[2], "w"), indent=1)
