@@ -151,6 +151,31 @@ def test_forces_accumulate_and_box_can_change(build_native):
     assert abs(e - eo[4]) <= E_RTOL * abs(eo[4]) and rel_rms(f, fo) <= F_RTOL
 
 
+def test_kmax_can_follow_the_box(build_native):
+    """CFX_OPT_KMAX_FOLLOWS_BOX: after a box change the handle behaves like one created for that box
+    (the reference's estimator, ReferenceCoulKernels.cpp:403-420, re-applied); both flag sets, there and back."""
+    pos, box, force = synthetic.water_box(216, seed=1, cutoff=0.9, ewald_tol=1e-4)
+    ctx = runtime.CoulContext(force, box, kmax_follows_box=True)
+    fixed = runtime.CoulContext(force, box)
+    k0 = ctx.kernel.ewald_params()[1]
+    for scale in (1.0, 1.4, 0.97, 1.0):
+        b = box * scale
+        o = Oracle(force, b)                                   # kmax from this box
+        ctx.box = b
+        for inc_e in (True, False, True):
+            e, f, _ = ctx.evaluate(pos * scale, True, inc_e)
+            eo, fo = o.execute(pos * scale, b, True, inc_e)
+            assert ctx.kernel.ewald_params() == o.ewald_params()
+            # (the stretched boxes have small totals next to their components: same scale as the other small-box tests)
+            assert abs(e - eo[4]) <= (E_RTOL if inc_e else E_RTOL_DISCARDED) * max(abs(eo[4]), 1e-3 * np.abs(eo[:4]).max()), (scale, inc_e)
+            assert rel_rms(f, fo) <= F_RTOL, (scale, inc_e)
+    assert Oracle(force, box * 1.4).ewald_params()[1] != k0     # the sweep did change kmax
+    # default: the reference's behaviour, kmax of the default box whatever the box of the call
+    fixed.box = box * 1.4
+    fixed.evaluate(pos * 1.4)
+    assert fixed.kernel.ewald_params()[1] == k0
+
+
 def test_results_are_bitwise_reproducible(build_native):
     pos, box, force = synthetic.config("c2")
     ctx = runtime.CoulContext(force, box)
