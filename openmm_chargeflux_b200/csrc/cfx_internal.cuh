@@ -73,6 +73,10 @@ __device__ __forceinline__ double blockSum(double v, double* scratch) {
 struct Box { double L[3]; double invL[3]; };
 
 // geometry of one structure-factor kernel: |nz| slot layout of the per-atom phase rows, grid, shared memory
+// st.energyFixed[8]: slots 0..3 are the energy components (2^24 fixed point); slot 7 holds the float bits of the largest
+// |q| of the evaluation (atomicMax by the charge assembly, read by the integer structure-factor kernel)
+constexpr int CFX_SLOT_QMAX = 7;
+
 struct SGeom {
     int TN = 7, NC = 0;          // TN columns per warp, NC column groups (FP32 kernel); |nz| = l lives in slot (l/TN)*TNP + l%TN
     int kzPad = 0, rowPitch = 0; // padded |nz| slots; float2 per atom row in rowS: Kx + Ky + kzPad
@@ -98,6 +102,11 @@ struct KSpacePlan {
     // tensor-core structure factors (kspace_tc.cu)
     bool tensorS = false;
     uint32_t tsRowStageBytes = 0, tsOffA = 0, tsOffB = 0, tsOffBar = 0;
+    // integer tensor-core structure factors (exact; energy and forces-only calls)
+    bool i8S = false;
+    int siRowStages = 0, siOpStages = 0;
+    uint32_t siRowStagePad = 0, siOpBytes = 0, siOffOp = 0, siOffBar = 0;
+    size_t siSmem = 0;
     // tensor-core gather (kspace_tc.cu): K padded to 8, atom tiles per work unit, columns per coefficient tile
     bool tensorGather = false;
     int tKp = 0, tKC = 0, tMT = 2, tNT = 128, tStages = 0, tColTiles = 0;
@@ -238,7 +247,7 @@ void planKSpace(State& st);
 void launchKSpace(State& st, const double* dPos, bool forces, bool energy, long long* dForce, long long* dDedq, cudaStream_t s);  // piece (3)
 bool structureTensorEligible(const State& st);                                          // kspace_tc.cu
 void planStructureTensor(State& st);
-void launchStructureTensor(State& st, cudaStream_t s);
+void launchStructureTensor(State& st, bool energy, cudaStream_t s);
 double measureTf32Peak(int device, int iters);
 void planKSpaceTensor(State& st);                                                       // kspace_tc.cu
 void launchGatherTensor(State& st, long long* dForce, long long* dDedq, cudaStream_t s);

@@ -132,6 +132,12 @@ __global__ void __launch_bounds__(256) chargeSumSelfKernel(int N, int Npad, cons
     }
     else if (i < Npad)
         qf[i] = 0.0f;
+    {   // largest |q| of this evaluation: fixes the fixed-point scale of the integer structure-factor kernel
+        unsigned int mb = (i < N) ? __float_as_uint(fabsf(qf[i])) : 0u;
+        mb = __reduce_max_sync(0xffffffffu, mb);
+        if ((threadIdx.x & 31) == 0 && mb != 0u)
+            atomicMax(reinterpret_cast<unsigned long long*>(energyFixed + CFX_SLOT_QMAX), (unsigned long long) mb);
+    }
     if (selfTerm) {
         e = blockSum(e, scratch);
         if (threadIdx.x == 0) atomicAddEnergy(energyFixed + CFX_E_SELF, e);

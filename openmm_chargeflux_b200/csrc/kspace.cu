@@ -634,7 +634,10 @@ void launchKSpace(State& st, const double* dPos, bool forces, bool energy, long 
     KSpacePlan& ks = st.ks;
     if (!forces && !energy) return;
     // the reciprocal energy needs round-to-nearest sums: FP32 kernel whenever it is requested
-    const bool useTensorS = ks.tensorS && (!energy || !ks.fp32S);
+    // The integer tensor-core kernel sums exactly (no truncation bias, order-independent), so it serves the energy call too
+    // (with a fourth digit plane: 31-bit operands). The TF32 kernel (used when the integer one is disabled) truncates on
+    // accumulation and never serves energies.
+    const bool useTensorS = ks.tensorS && (!energy || !ks.fp32S || ks.i8S);
     const SGeom& g = useTensorS ? ks.sT : ks.sF;
     const int Kx = ks.K[0], Ky = ks.K[1], Kz = ks.K[2];
     const int zOff = g.rowPitch - g.kzPad;
@@ -653,7 +656,7 @@ void launchKSpace(State& st, const double* dPos, bool forces, bool energy, long 
     sp.rowLo = ks.rowLo; sp.rowHi = ks.rowHi; sp.numRows = ks.numRows;
     sp.atomsPerSplit = g.atomsPerSplit; sp.Npad = st.Npad;
     const dim3 sGrid(g.rowTiles, g.splits);
-    if (useTensorS) launchStructureTensor(st, s);
+    if (useTensorS) launchStructureTensor(st, energy, s);
     else if (g.NC <= 4) {
         if (g.TN == 6)      structureFactorKernel<6, 4><<<sGrid, g.threads, g.smem, s>>>(sp);
         else if (g.TN == 7) structureFactorKernel<7, 4><<<sGrid, g.threads, g.smem, s>>>(sp);

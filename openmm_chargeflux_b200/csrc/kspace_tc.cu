@@ -564,6 +564,264 @@ __global__ void __launch_bounds__(ST_THREADS, 1) structureFactorTensorKernel(STP
     if (warp == 0) tmemFree<256>(tmem);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// structure factors on the INTEGER tensor cores (exact sums): the kernel of both the energy and the forces-only call
+// ------------------------------------------------------------------------------------------------
+// Same GEMM as above, P[(comp,row)][(l,c|s)] = sum_atoms A * Z, with both operands in fixed point: A' = A sA, Z' = Z sZ,
+// |A'|, |Z'| < 2^22 (sA from the largest |q| of this evaluation), written as SIGNED base-256 digits
+//     v = D2 2^16 + D1 2^8 + D0 (+ D-1 2^-8),   D1, D0, D-1 in [-128, 127], |D2| <= 64,
+// and the digit planes are multiplied by tcgen05.mma kind::i8 (s8 x s8 -> s32). Integer products and sums are exact: no
+// truncation bias, no need to take the accumulators out every stage, a result independent of the summation order.
+// Products of equal weight share an accumulator group (NN columns each, side by side in tensor memory):
+//     2^32: D2 D2     2^24: D2 D1, D1 D2     2^16: D2 D0, D1 D1, D0 D2     2^8: D2 D-1, D1 D0, D0 D1, D-1 D2
+// (weights below 2^8 are dropped: at most 3 x 2^14 per atom against products of ~2^40, zero-mean). With the Z digit planes
+// stacked along N ([D2 | D1 | D0 | D-1] rows), ONE MMA per A plane covers all its groups: A digit i times Z digits 0..3-i
+// lands in groups i..3, i.e. N = (4-i) NN columns from column i NN on: 3 (ND = 3) or 4 (ND = 4) MMAs of K = 32 atoms per row
+// tile and stage, where the TF32 kernel needs 12 of K = 8. ND = 3 (23-bit operands, ~4x the rounding noise of FP32 operands)
+// serves the forces-only call; the energy call adds the fourth digit (31-bit operands: quieter than FP32).
+// The digits come out of the float -> int conversion: t = fma(x, y, 2^23 + 0x408080) has the mantissa v + 0x408080, whose
+// bytes are D0 + 128, D1 + 128, D2 + 64; the residual fma(x, y, -(t - magic)) is exact and gives D-1 the same way; PRMT gathers
+// the bytes of four atoms into one word per plane.
+// Worst-case accumulator: 3 x 2^14 per atom in the 2^8 group -> at most 40,960 atoms per CTA (planStructureTensor).
+constexpr int SI_ATOMS = 32;                 // atoms per stage = one MMA k-step (32 int8)
+constexpr int SI_FORM_WARPS = 16, SI_FORM_WARP0 = 2;
+constexpr int SI_THREADS = (SI_FORM_WARP0 + SI_FORM_WARPS)*32;
+constexpr uint32_t SI_A_PLANE = 2*128*16;    // bytes of one digit plane of one row tile: two 16-atom chunks x 128 lanes x 16 B
+constexpr float SI_MAGIC = 12615808.0f;      // 2^23 + 0x408080
+constexpr float SI_MAGIC_LO = 8388736.0f;    // 2^23 + 128
+constexpr float SI_RANGE = 4160000.0f;       // |v| stays below 2^22 - 2^15 - 1407 (mantissa within [0, 2^23))
+constexpr int SI_MAX_ATOMS = 40960;
+
+struct SIParams {
+    const float2* rowS; float* part; const unsigned long long* qmaxSlot;
+    int rowPitch, Kx, Ky, Kz, zOff, kzPad;
+    int rowLo, rowHi, numRows;
+    int atomsPerSplit, Npad;
+    int rowStages, opStages;
+    uint32_t rowStageBytes, rowStagePad, offOp, opBytes, offBar;
+};
+
+// four biased mantissas -> the word of byte j (bytes of the word = atoms), as signed digits; mask = 0 for padding
+__device__ __forceinline__ uint32_t siPlane(uint32_t u0, uint32_t u1, uint32_t u2, uint32_t u3, int j, uint32_t mask) {
+    const uint32_t sel = (uint32_t) j | ((uint32_t) (4 + j) << 4);
+    const uint32_t w = __byte_perm(__byte_perm(u0, u1, sel), __byte_perm(u2, u3, sel), 0x5410);
+    return ((j == 2 ? w + 0x40404040u : w) ^ 0x80808080u) & mask;               // b - 64 (b in [0,127]) / b - 128
+}
+// t = rint(xy) + magic; returns the biased mantissa word of the residual digit
+__device__ __forceinline__ uint32_t siResidual(float x, float y, float t) {
+    const float r = fmaf(x, y, -(t - SI_MAGIC));                                 // exact, |r| <= 1/2
+    return __float_as_uint(fmaf(fminf(r, 0.4975f), 256.0f, SI_MAGIC_LO));
+}
+
+template <int NN, int TT, int ND>
+__global__ void __launch_bounds__(SI_THREADS, 1) structureFactorI8Kernel(SIParams p) {
+    static_assert(NN*TT == 128, "four weight groups of TT*NN columns fill the 512 tensor-memory columns");
+    constexpr uint32_t B_CHUNK = ND*NN*16;                // bytes of one 16-atom chunk column of the stacked Z operand
+    constexpr uint32_t A_BYTES = TT*ND*SI_A_PLANE;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.offBar);
+    uint64_t* rowsFull = bars;            // [4] TMA -> formers
+    uint64_t* rowsEmpty = bars + 4;       // [4] formers -> TMA
+    uint64_t* abFull = bars + 8;          // [4] formers -> MMA
+    uint64_t* abEmpty = bars + 12;        // [4] MMA -> formers
+    uint64_t* dFull = bars + 16;          // MMA -> epilogue (once)
+    uint64_t* tmemReady = bars + 17;      // accumulators zeroed -> MMA
+    uint32_t* tmemSlot = reinterpret_cast<uint32_t*>(bars + 18);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rowBase = p.rowLo + blockIdx.x*(32*TT);
+    const int atomBegin = blockIdx.y*p.atomsPerSplit;
+    const int atomEnd = min(atomBegin + p.atomsPerSplit, p.Npad);
+    const int numStages = (atomEnd - atomBegin)/SI_ATOMS;
+    const int RS = p.rowStages, OB = p.opStages;
+
+    if (tid == 0) {
+        for (int i = 0; i < 4; i++) {
+            mbarInit(&rowsFull[i], 1); mbarInit(&rowsEmpty[i], SI_FORM_WARPS);
+            mbarInit(&abFull[i], SI_FORM_WARPS); mbarInit(&abEmpty[i], 1);
+        }
+        mbarInit(dFull, 1); mbarInit(tmemReady, SI_FORM_WARPS);
+        mbarFenceInit();
+    }
+    if (warp == 0) tmemAlloc<512>(tmemSlot);
+    tcgen05FenceBefore();
+    __syncthreads();
+    tcgen05FenceAfter();
+    const uint32_t tmem = *tmemSlot;
+
+    if (warp == 0) {
+        // ---------------- producer: per-atom phase rows, 32 atoms per stage ----------------
+        if (lane == 0) {
+            int rs = 0; uint32_t ph = 0;
+            for (int st = 0; st < numStages; st++) {
+                if (st >= RS) mbarWait(&rowsEmpty[rs], ph ^ 1);
+                mbarExpectTx(&rowsFull[rs], p.rowStageBytes);
+                bulkLoad(smem + (size_t) rs*p.rowStagePad, p.rowS + (size_t) (atomBegin + st*SI_ATOMS)*p.rowPitch, p.rowStageBytes, &rowsFull[rs]);
+                if (++rs == RS) { rs = 0; ph ^= 1; }
+            }
+        }
+        __syncwarp();
+    }
+    else if (warp == 1) {
+        // ---------------- MMA issuer: every MMA accumulates (the accumulators start at zero) ----------------
+        mbarWait(tmemReady, 0);
+        tcgen05FenceAfter();
+        int b = 0; uint32_t ph = 0;
+        for (int st = 0; st < numStages; st++) {
+            mbarWait(&abFull[b], ph);
+            tcgen05FenceAfter();
+            const uint32_t opBase = smemU32(smem) + p.offOp + (uint32_t) b*p.opBytes;
+            const uint32_t zBase = opBase + A_BYTES;
+            if (electOne()) {
+                #pragma unroll
+                for (int t = 0; t < TT; t++) {
+                    #pragma unroll
+                    for (int i = 0; i < ND; i++) {                                 // A digit i (0 = D2) x Z digits 0 .. 3-i -> groups i ..
+                        const int nk = (4 - i < ND) ? 4 - i : ND;
+                        const uint64_t a = ummaSmemDesc(opBase + (uint32_t) (t*ND + i)*SI_A_PLANE, 128*16, 128);
+                        #pragma unroll
+                        for (int r0 = 0; r0 < nk*NN; r0 += 256) {
+                            const int n = (nk*NN - r0 < 256) ? nk*NN - r0 : 256;
+                            ummaI8SS(tmem + (uint32_t) (t*4*NN + i*NN + r0), a, ummaSmemDesc(zBase + (uint32_t) r0*16, B_CHUNK, 128),
+                                     ummaIdescS8(128, n), 1);
+                        }
+                    }
+                }
+                ummaCommit(&abEmpty[b]);
+                if (st == numStages - 1) ummaCommit(dFull);
+            }
+            __syncwarp();
+            if (++b == OB) { b = 0; ph ^= 1; }
+        }
+    }
+    else {
+        // ---------------- formers (16 warps), then the one-off epilogue ----------------
+        const int fw = warp - SI_FORM_WARP0, ft = tid - SI_FORM_WARP0*32;        // 0..15, 0..511
+        const int q4 = warp & 3;                                                 // the lane quarter this warp may access
+        {   // zero this warp's share of the accumulators: lane quarter q4, 128 of the 512 columns
+            const uint32_t base = tmem + ((uint32_t) (q4*32) << 16) + (uint32_t) (fw >> 2)*128;
+            #pragma unroll
+            for (int c = 0; c < 8; c++) tmemStoreZero16(base + 16*c);
+            tmemWaitStore();
+            tcgen05FenceBefore();
+            __syncwarp();
+            if (lane == 0) mbarArrive(tmemReady);
+        }
+        const unsigned int qbits = (unsigned int) __ldg(p.qmaxSlot);
+        const float sA = SI_RANGE/fmaxf(__uint_as_float(qbits), 1e-30f), sZ = SI_RANGE;
+        // A item of this thread: (row of the CTA, quad of 4 atoms); lanes = 4 quads of a chunk x 8 rows -> the 4-byte stores
+        // of a warp cover 8 x 16 contiguous bytes per plane
+        constexpr int A_ITEMS = 32*TT*8;
+        const bool hasA = ft < A_ITEMS;
+        const int aR = (ft >> 2) % (32*TT), aQ = ((ft >> 2)/(32*TT))*4 + (ft & 3);
+        const int aRow = rowBase + aR;
+        const bool aValid = hasA && aRow < p.rowHi;
+        const uint32_t aMask = aValid ? 0xFFFFFFFFu : 0u;
+        const int aNx = aValid ? aRow/p.Ky : 0, aM = aValid ? aRow - aNx*p.Ky : 0;
+        const uint32_t aDst = (uint32_t) (aR >> 5)*(ND*SI_A_PLANE) + (uint32_t) (aQ >> 2)*(128*16) + (uint32_t) (aR & 31)*16 + (uint32_t) (aQ & 3)*4;
+        const uint32_t aOffX = (uint32_t) ((4*aQ)*p.rowPitch + aNx)*8, aOffY = (uint32_t) ((4*aQ)*p.rowPitch + p.Kx + aM)*8;
+        // Z item: (|nz| slot, quad); both the cos and the sin row
+        constexpr int Z_ITEMS = (NN/2)*8;
+        const bool hasZ = ft < Z_ITEMS;
+        const int zL = (ft >> 2) % (NN/2), zQ = ((ft >> 2)/(NN/2))*4 + (ft & 3);
+        const bool zValid = hasZ && zL < p.Kz;
+        const uint32_t zMask = zValid ? 0xFFFFFFFFu : 0u;
+        const uint32_t zDst = (uint32_t) (zQ >> 2)*B_CHUNK + (uint32_t) (2*zL)*16 + (uint32_t) (zQ & 3)*4;
+        const uint32_t zOff = (uint32_t) ((4*zQ)*p.rowPitch + p.zOff + (zValid ? zL : 0))*8;
+        const uint32_t pitchBytes = (uint32_t) p.rowPitch*8;
+
+        int b = 0, rs = 0; uint32_t phB = 0, phR = 0;
+        for (int st = 0; st < numStages; st++) {
+            mbarWait(&rowsFull[rs], phR);
+            mbarWait(&abEmpty[b], phB ^ 1);                       // the MMAs that read this operand buffer are complete
+            const unsigned char* rows = smem + (size_t) rs*p.rowStagePad;
+            unsigned char* aBuf = smem + p.offOp + (size_t) b*p.opBytes;
+            unsigned char* zBuf = aBuf + A_BYTES;
+            if (hasA) {
+                uint32_t u[4][4], ul[4][4];                        // [comp][atom of the quad]: digits 2..0, residual digit
+                #pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    float2 x = *reinterpret_cast<const float2*>(rows + aOffX + j*pitchBytes);
+                    const float2 y = *reinterpret_cast<const float2*>(rows + aOffY + j*pitchBytes);
+                    x.x *= sA; x.y *= sA;
+                    const float t0 = fmaf(x.x, y.x, SI_MAGIC), t1 = fmaf(x.x, y.y, SI_MAGIC), t2 = fmaf(x.y, y.x, SI_MAGIC), t3 = fmaf(x.y, y.y, SI_MAGIC);
+                    u[0][j] = __float_as_uint(t0); u[1][j] = __float_as_uint(t1); u[2][j] = __float_as_uint(t2); u[3][j] = __float_as_uint(t3);
+                    if (ND == 4) {
+                        ul[0][j] = siResidual(x.x, y.x, t0); ul[1][j] = siResidual(x.x, y.y, t1);
+                        ul[2][j] = siResidual(x.y, y.x, t2); ul[3][j] = siResidual(x.y, y.y, t3);
+                    }
+                }
+                #pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    unsigned char* dst = aBuf + aDst + c*(32*16);
+                    #pragma unroll
+                    for (int pl = 0; pl < 3; pl++)                 // plane 0 of the buffer = D2 ... plane 2 = D0
+                        *reinterpret_cast<uint32_t*>(dst + pl*SI_A_PLANE) = siPlane(u[c][0], u[c][1], u[c][2], u[c][3], 2 - pl, aMask);
+                    if (ND == 4) *reinterpret_cast<uint32_t*>(dst + 3*SI_A_PLANE) = siPlane(ul[c][0], ul[c][1], ul[c][2], ul[c][3], 0, aMask);
+                }
+            }
+            if (hasZ) {
+                uint32_t uc[4], us[4], lc[4], ls[4];
+                #pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const float2 z = *reinterpret_cast<const float2*>(rows + zOff + j*pitchBytes);
+                    const float tc = fmaf(z.x, sZ, SI_MAGIC), ts = fmaf(z.y, sZ, SI_MAGIC);
+                    uc[j] = __float_as_uint(tc); us[j] = __float_as_uint(ts);
+                    if (ND == 4) { lc[j] = siResidual(z.x, sZ, tc); ls[j] = siResidual(z.y, sZ, ts); }
+                }
+                #pragma unroll
+                for (int pl = 0; pl < 3; pl++) {
+                    unsigned char* dst = zBuf + zDst + pl*(NN*16);
+                    *reinterpret_cast<uint32_t*>(dst) = siPlane(uc[0], uc[1], uc[2], uc[3], 2 - pl, zMask);
+                    *reinterpret_cast<uint32_t*>(dst + 16) = siPlane(us[0], us[1], us[2], us[3], 2 - pl, zMask);
+                }
+                if (ND == 4) {
+                    unsigned char* dst = zBuf + zDst + 3*(NN*16);
+                    *reinterpret_cast<uint32_t*>(dst) = siPlane(lc[0], lc[1], lc[2], lc[3], 0, zMask);
+                    *reinterpret_cast<uint32_t*>(dst + 16) = siPlane(ls[0], ls[1], ls[2], ls[3], 0, zMask);
+                }
+            }
+            fenceProxyAsync();                                    // operands visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) { mbarArrive(&abFull[b]); mbarArrive(&rowsEmpty[rs]); }
+            if (++b == OB) { b = 0; phB ^= 1; }
+            if (++rs == RS) { rs = 0; phR ^= 1; }
+        }
+        // ---------------- epilogue: exact 64-bit combination of the four groups, scaled back, one FP32 rounding ----------------
+        {
+            if (numStages > 0) mbarWait(dFull, 0);                 // (an empty split still writes its zeros)
+            tcgen05FenceAfter();
+            const int blk = fw >> 2;                               // 32 of the TT*NN columns of every group
+            const int t = blk/(NN/32), colOff = (blk % (NN/32))*32;
+            const uint32_t tD = tmem + ((uint32_t) (q4*32) << 16) + (uint32_t) t*(4*NN) + colOff;
+            const double inv = 1.0/((double) sA*(double) sZ);
+            const int row = rowBase + t*32 + lane;
+            float* out = p.part + (((size_t) blockIdx.y*p.numRows + row)*p.kzPad + colOff/2)*8 + q4*2;
+            #pragma unroll
+            for (int c = 0; c < 2; c++) {
+                int g3[16], g2[16], g1[16], g0[16];
+                tmemLoad16i(tD + 16*c, g3); tmemLoad16i(tD + NN + 16*c, g2); tmemLoad16i(tD + 2*NN + 16*c, g1); tmemLoad16i(tD + 3*NN + 16*c, g0);
+                #pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    float v[2];
+                    #pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const int k = 2*i + h;
+                        const long long sum = ((long long) g3[k] << 32) + ((long long) g2[k] << 24) + ((long long) g1[k] << 16) + ((long long) g0[k] << 8);
+                        v[h] = (float) ((double) sum*inv);
+                    }
+                    const int l = colOff/2 + 8*c + i;
+                    if (row < p.rowHi && l < p.Kz) *reinterpret_cast<float2*>(out + (size_t) (8*c + i)*8) = make_float2(v[0], v[1]);
+                }
+            }
+        }
+    }
+    tcgen05FenceBefore();
+    __syncthreads();
+    if (warp == 0) tmemFree<512>(tmem);
+}
+
 } // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -672,9 +930,10 @@ void planStructureTensor(State& st) {
     t.rowTiles = (rowsHere + 32*TT - 1)/(32*TT);
     // atom splits: the smallest count that fills >= 95 % of the SM slots of its last wave (one CTA per SM)
     const int maxSplits = std::max(1, st.Npad/(4*ST_ATOMS));
-    int splits = 1;
+    const int minSplits = (st.Npad + SI_MAX_ATOMS - 1)/SI_MAX_ATOMS;   // int32 accumulators of the integer kernel
+    int splits = minSplits;
     double bestUtil = 0.0;
-    for (int sp = 1; sp <= std::min(maxSplits, 4*numSM); sp++) {
+    for (int sp = minSplits; sp <= std::max(minSplits, std::min(maxSplits, 4*numSM)); sp++) {
         const int ctas = t.rowTiles*sp;
         const double util = (double) ctas/((double) ((ctas + numSM - 1)/numSM)*numSM);
         if (util > bestUtil + 1e-9) { bestUtil = util; splits = sp; }
@@ -695,9 +954,30 @@ void planStructureTensor(State& st) {
     if (t.smem > 227*1024 - 256) { ks.tensorS = false; return; }
     CFX_CUDA(cudaFuncSetAttribute(structureFactorTensorKernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024));
     CFX_CUDA(cudaFuncSetAttribute(structureFactorTensorKernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024));
+    // integer tensor-core kernel (exact sums: serves the energy call too, with a fourth digit plane): same row tiles / atom
+    // splits / partial-sum layout; sized for four digit planes, deepest operand ring that fits beside the row stages
+    ks.i8S = false;
+    const char* mode = getenv("CFX_KSPACE_S");                  // "tf32": keep the TF32 kernel (and FP32 for energies)
+    if (!(mode && !strcmp(mode, "tf32")) && t.atomsPerSplit <= SI_MAX_ATOMS) {
+        const size_t opBytes = (size_t) TT*4*SI_A_PLANE + 2*(size_t) (4*NN)*16;
+        const size_t cap = 227*1024 - 256 - 256;
+        for (int rsN = 3; rsN >= 2 && !ks.i8S; rsN--)
+            for (int ob = 4; ob >= 2; ob--)
+                if (rsN*rowStagePad + ob*opBytes <= cap) {
+                    ks.i8S = true; ks.siRowStages = rsN; ks.siOpStages = ob;
+                    ks.siRowStagePad = (uint32_t) rowStagePad; ks.siOpBytes = (uint32_t) opBytes;
+                    ks.siOffOp = (uint32_t) (rsN*rowStagePad); ks.siOffBar = (uint32_t) (ks.siOffOp + ob*opBytes);
+                    ks.siSmem = ks.siOffBar + 256;
+                    break;
+                }
+        CFX_CUDA(cudaFuncSetAttribute(structureFactorI8Kernel<64, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024));
+        CFX_CUDA(cudaFuncSetAttribute(structureFactorI8Kernel<128, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024));
+        CFX_CUDA(cudaFuncSetAttribute(structureFactorI8Kernel<64, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024));
+        CFX_CUDA(cudaFuncSetAttribute(structureFactorI8Kernel<128, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024));
+    }
 }
 
-void launchStructureTensor(State& st, cudaStream_t s) {
+void launchStructureTensor(State& st, bool energy, cudaStream_t s) {
     KSpacePlan& ks = st.ks;
     const SGeom& t = ks.sT;
     STParams sp;
@@ -705,6 +985,26 @@ void launchStructureTensor(State& st, cudaStream_t s) {
     sp.rowPitch = t.rowPitch; sp.Kx = ks.K[0]; sp.Ky = ks.K[1]; sp.Kz = ks.K[2]; sp.zOff = t.rowPitch - t.kzPad; sp.kzPad = t.kzPad;
     sp.rowLo = ks.rowLo; sp.rowHi = ks.rowHi; sp.numRows = ks.numRows;
     sp.atomsPerSplit = t.atomsPerSplit; sp.Npad = st.Npad;
+    if (ks.i8S) {
+        SIParams ip;
+        ip.rowS = st.rowS; ip.part = st.sPart; ip.qmaxSlot = reinterpret_cast<const unsigned long long*>(st.energyFixed + CFX_SLOT_QMAX);
+        ip.rowPitch = t.rowPitch; ip.Kx = ks.K[0]; ip.Ky = ks.K[1]; ip.Kz = ks.K[2]; ip.zOff = t.rowPitch - t.kzPad; ip.kzPad = t.kzPad;
+        ip.rowLo = ks.rowLo; ip.rowHi = ks.rowHi; ip.numRows = ks.numRows;
+        ip.atomsPerSplit = t.atomsPerSplit; ip.Npad = st.Npad;
+        ip.rowStages = ks.siRowStages; ip.opStages = ks.siOpStages;
+        ip.rowStageBytes = ks.tsRowStageBytes; ip.rowStagePad = ks.siRowStagePad; ip.offOp = ks.siOffOp; ip.opBytes = ks.siOpBytes; ip.offBar = ks.siOffBar;
+        const dim3 grid(t.rowTiles, t.splits);
+        if (t.kzPad == 32) {
+            if (energy) structureFactorI8Kernel<64, 2, 4><<<grid, SI_THREADS, ks.siSmem, s>>>(ip);
+            else        structureFactorI8Kernel<64, 2, 3><<<grid, SI_THREADS, ks.siSmem, s>>>(ip);
+        }
+        else {
+            if (energy) structureFactorI8Kernel<128, 1, 4><<<grid, SI_THREADS, ks.siSmem, s>>>(ip);
+            else        structureFactorI8Kernel<128, 1, 3><<<grid, SI_THREADS, ks.siSmem, s>>>(ip);
+        }
+        CFX_LAUNCH_CHECK(); st.launches++;
+        return;
+    }
     sp.rowStageBytes = ks.tsRowStageBytes; sp.offA = ks.tsOffA; sp.offB = ks.tsOffB; sp.offBar = ks.tsOffBar;
     if (t.kzPad == 32) structureFactorTensorKernel<64, 2><<<dim3(t.rowTiles, t.splits), ST_THREADS, t.smem, s>>>(sp);
     else               structureFactorTensorKernel<128, 1><<<dim3(t.rowTiles, t.splits), ST_THREADS, t.smem, s>>>(sp);

@@ -98,6 +98,18 @@ __device__ __forceinline__ void tmemStore4(uint32_t taddr, float4 v) {
                  :: "r"(taddr), "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)), "r"(__float_as_uint(v.w)) : "memory");
 }
 __device__ __forceinline__ void tmemWaitStore() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmemLoad16i(uint32_t taddr, int (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// 16 columns of zeros into the warp's 32 lanes
+__device__ __forceinline__ void tmemStoreZero16(uint32_t taddr) {
+    const uint32_t z = 0;
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" :: "r"(taddr), "r"(z) : "memory");
+}
 
 // one lane of a converged warp
 __device__ __forceinline__ bool electOne() {
@@ -133,6 +145,15 @@ __device__ __forceinline__ void ummaTf32TS(uint32_t tmemD, uint32_t tmemA, uint6
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                  "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
                  :: "r"(tmemD), "r"(tmemA), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// integer MMA: D = S32, A = B = signed 8 bit, both K-major, dense; one instruction = 32 int8 along K (two 16-byte chunks)
+__host__ __device__ constexpr uint32_t ummaIdescS8(int M, int N) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t) (N >> 3) << 17) | ((uint32_t) (M >> 4) << 24);
+}
+__device__ __forceinline__ void ummaI8SS(uint32_t tmemD, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n"
+                 :: "r"(tmemD), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 // arrive on an mbarrier once every MMA issued so far by this thread has completed
 __device__ __forceinline__ void ummaCommit(uint64_t* bar) {
