@@ -250,15 +250,18 @@ def run_reference_arm(args, pos, box, force, workload):
 # --------------------------------------------------------------------------------------------------
 # the CUDA path
 # --------------------------------------------------------------------------------------------------
-def algorithmic_flops(n_atoms, n_k, pairs, n_terms, n_rows, n_excl):
-    """FMA = 2 FLOP."""
-    return {"structure_factor": 4.0 * n_atoms * n_k, "kspace_gather": 8.0 * n_atoms * n_k, "direct_pairs": 80.0 * pairs,
+def algorithmic_flops(n_atoms, n_k, pairs, n_terms, n_rows, n_excl, energy):
+    """FMA = 2 FLOP. Of the 80 FLOP of an in-cutoff pair 12 are its energy terms (E_coul 2, LJ energy 10):
+    an energy+forces call runs them as a second, half-shell FP64 pass (`direct_pairs_energy`)."""
+    return {"structure_factor": 4.0 * n_atoms * n_k, "kspace_gather": 8.0 * n_atoms * n_k,
+            "direct_pairs": (68.0 if energy else 80.0) * pairs, "direct_pairs_energy": 12.0 * pairs,
             "total": 12.0 * n_atoms * n_k + 80.0 * pairs + 150.0 * n_terms + 6.0 * n_rows + 40.0 * n_excl + 4.0 * n_atoms}
 
 
-def executed_tensor_flops(n_atoms, kmax, energy):
-    """TF32 FLOP the tensor-core k-space kernels execute per launch: three products, padded tiles.
-    Evaluations that return the energy run the FP32 CUDA-core structure-factor kernel instead of the tensor one."""
+def executed_tensor_ops(n_atoms, kmax, energy):
+    """Operations the tensor-core k-space kernels execute per launch (padded tiles, split operands):
+    name -> (ops, kind). Gather: tcgen05 kind::tf32, three products. Structure factors: tcgen05 kind::i8 on digit planes --
+    per row tile and 32-atom stage the MMAs span 8 NN columns (3 digits, forces-only call) or 10 NN (4 digits, energy call)."""
     kx, ky, kz = kmax
     npad = (n_atoms + 255) // 256 * 256
     out = {}
@@ -267,12 +270,12 @@ def executed_tensor_flops(n_atoms, kmax, energy):
         nt = 128 if kp <= 56 else 64
         signed = ky + (kx - 1) * (2 * ky - 1)
         cols = (signed + nt // 4 - 1) // (nt // 4) * nt
-        out["kspace_gather"] = 3 * 2.0 * npad * kp * cols
-    if kz <= 64 and not energy:
+        out["kspace_gather"] = (3 * 2.0 * npad * kp * cols, "tf32")
+    if kz <= 64 and os.environ.get("CFX_KSPACE_S", "") not in ("tf32", "fp32"):
         nn = 64 if kz <= 32 else 128
         rows_per_cta = 32 * (128 // nn)
         rows = (kx * ky + rows_per_cta - 1) // rows_per_cta * rows_per_cta
-        out["structure_factor"] = 3 * 2.0 * (4 * rows) * nn * npad
+        out["structure_factor"] = (2.0 * 128 * (10 if energy else 8) * nn * npad * (rows // 32), "i8")
     return out
 
 
@@ -507,12 +510,13 @@ def run_ours(args, pos, box, force, workload):
         # per-kernel durations (CUDA events on the launching stream) and the roofline of the dominant one
         tf_peak, _ = runtime.measure_fp32_peak(local, 5)
         tf32_peak = runtime.measure_tf32_peak(local)
+        i8_peak = runtime.measure_i8_peak(local)
         kt = me.kernel.time_kernels(me.d_pos.data_ptr(), box, 10, True, INCLUDE_ENERGY)
         kt_f = me.kernel.time_kernels(me.d_pos.data_ptr(), box, 10, True, False)
         pairs = me.kernel.stats().pairs_in_cutoff
-        fl = algorithmic_flops(n, nk, pairs, force.getNumFluxBonds() + force.getNumFluxAngles() + force.getNumFluxWaters(),
-                               4 * force.getNumFluxBonds() + 9 * force.getNumFluxAngles() + 9 * force.getNumFluxWaters(),
-                               force.getNumExceptions())
+        terms = (force.getNumFluxBonds() + force.getNumFluxAngles() + force.getNumFluxWaters(),
+                 4 * force.getNumFluxBonds() + 9 * force.getNumFluxAngles() + 9 * force.getNumFluxWaters(), force.getNumExceptions())
+        fl = algorithmic_flops(n, nk, pairs, *terms, INCLUDE_ENERGY)
         try:
             traffic_db = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json"))) if args.workload == "c3" else {}
         except (OSError, ValueError):
@@ -523,35 +527,40 @@ def run_ours(args, pos, box, force, workload):
             return tr["dram_read_bytes"] + tr["dram_write_bytes"] if tr else None
 
         def kernel_rows(times, energy):
-            ex = executed_tensor_flops(n, kmax, energy)
+            ex = executed_tensor_ops(n, kmax, energy)
+            flk = algorithmic_flops(n, nk, pairs, *terms, energy)
             total = sum(times.values())
             rows = []
-            for name in ("direct_pairs", "kspace_gather", "structure_factor"):
+            for name in ("direct_pairs", "direct_pairs_energy", "kspace_gather", "structure_factor"):
                 if name not in times:
                     continue
-                tensor = name in ex
-                peak = tf32_peak if tensor else tf_peak
-                a = fl[name] / (times[name] * 1e-3) / 1e12
-                row = {"kernel": name, "bound": "tensor" if tensor else "fp32", "ms": times[name], "share_of_step": times[name] / total,
-                       "algorithmic_flop_per_launch": fl[name], "achieved": a, "peak": peak, "unit": "TFLOP/s", "frac": a / peak,
-                       "traffic": traffic_of(name + ("_energy" if energy else ""))}
-                if tensor:
-                    row["executed_tf32_flop_per_launch"] = ex[name]
-                    row["executed_tflops"] = ex[name] / (times[name] * 1e-3) / 1e12
-                    row["executed_frac"] = row["executed_tflops"] / peak
+                kind = ex[name][1] if name in ex else None
+                peak, unit = {"tf32": (tf32_peak, "TFLOP/s"), "i8": (i8_peak, "TOP/s"), None: (tf_peak, "TFLOP/s")}[kind]
+                a = flk[name] / (times[name] * 1e-3) / 1e12
+                row = {"kernel": name, "bound": "tensor" if kind else "fp32", "ms": times[name], "share_of_step": times[name] / total,
+                       "algorithmic_flop_per_launch": flk[name], "achieved": a, "peak": peak, "unit": unit, "frac": a / peak,
+                       "traffic": traffic_of(name + ("@E" if energy else "@F"))}
+                if kind:
+                    row["tensor_kind"] = "tcgen05.mma kind::" + kind
+                    row["executed_ops_per_launch"] = ex[name][0]
+                    row["executed_tops"] = ex[name][0] / (times[name] * 1e-3) / 1e12
+                    row["executed_frac"] = row["executed_tops"] / peak
                     row["fp32_equivalent_frac_of_fp32_peak"] = a / tf_peak
+                if name == "direct_pairs_energy":
+                    row["note"] = "half-shell FP64 pass (34 FP64 instructions per pair); fraction quoted against the FP32 peak as SURVEY.md 8d defines"
                 rows.append(row)
             return rows
 
         rows = kernel_rows(kt, INCLUDE_ENERGY)
         top = max(rows, key=lambda r: r["ms"])
         line["roofline"] = {"bound": top["bound"], "kernel": top["kernel"], "achieved": top["achieved"], "peak": top["peak"],
-                            "unit": "TFLOP/s", "frac": top["frac"], "traffic": top["traffic"],
+                            "unit": top["unit"], "frac": top["frac"], "traffic": top["traffic"],
                             "traffic_note": "DRAM bytes per launch of this kernel from the committed ncu capture (profiles/); far below "
                                             "the algorithmic FLOP x 4 B: the kernel is instruction-issue bound, not HBM bound",
                             "peak_source": "NOT in MEASURED_PEAKS.json (it holds HBM and bf16 figures only): FP32 FMA microbenchmark run "
                                            "in this process (cfx_measure_fp32_peak; theoretical 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4) "
-                                           "and tcgen05 kind::tf32 128x128x8 microbenchmark run in this process (cfx_measure_tf32_peak)",
+                                           "and tcgen05 kind::tf32 128x128x8 / kind::i8 128x256x32 microbenchmarks run in this process "
+                                           "(cfx_measure_tf32_peak, cfx_measure_i8_peak)",
                             "kernel_ms": top["ms"], "kernel_share_of_step": top["share_of_step"],
                             "algorithmic_flop_per_launch": top["algorithmic_flop_per_launch"],
                             "kernels": rows,
@@ -573,7 +582,7 @@ def run_ours(args, pos, box, force, workload):
                                      "whose displacement check fires; the other steps launch the same kernels, which return at once"}
         line["kernels_ms"] = {k: round(v, 5) for k, v in kt.items()}
         line["kernels_ms_forces_only"] = {k: round(v, 5) for k, v in kt_f.items()}
-        line["peaks"] = {"fp32_fma_tflops": tf_peak, "tf32_tcgen05_tflops": tf32_peak}
+        line["peaks"] = {"fp32_fma_tflops": tf_peak, "tf32_tcgen05_tflops": tf32_peak, "i8_tcgen05_tops": i8_peak}
         line["config"]["pairs_in_cutoff"] = int(pairs)
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(pos, box, force)

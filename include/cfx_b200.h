@@ -224,6 +224,9 @@ int  cfx_measure_fp32_peak(int device, int iters, double* tflops, double* sm_clo
 /* Sustained dense TF32 tensor-core throughput (TFLOP/s) of tcgen05.mma kind::tf32 128x128x8, the roofline denominator
  * of the tensor-core reciprocal-space kernels (MEASURED_PEAKS.json holds a bf16 figure only). */
 int  cfx_measure_tf32_peak(int device, int iters, double* tflops);
+/* Sustained dense INT8 tensor-core throughput (TOP/s) of tcgen05.mma kind::i8 128x256x32, the roofline denominator of the
+ * integer structure-factor kernel. */
+int  cfx_measure_i8_peak(int device, int iters, double* tops);
 
 /* ------------------------------------------------------------------------------------------------
  * MD harness: what sits either side of the path in an OpenMM simulation of

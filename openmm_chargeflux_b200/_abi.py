@@ -52,6 +52,6 @@ EXPORTED_SYMBOLS = [
     "cfx_multi_create", "cfx_multi_destroy", "cfx_multi_num_devices", "cfx_multi_handle", "cfx_multi_execute",
     "cfx_padded_num_particles", "cfx_get_ewald_params", "cfx_get_stats", "cfx_get_charges", "cfx_get_dedq",
     "cfx_num_jacobian_rows", "cfx_get_jacobian", "cfx_get_neighbor_pairs", "cfx_get_exclusions",
-    "cfx_time_device", "cfx_time_kernels", "cfx_measure_fp32_peak", "cfx_measure_tf32_peak",
+    "cfx_time_device", "cfx_time_kernels", "cfx_measure_fp32_peak", "cfx_measure_tf32_peak", "cfx_measure_i8_peak",
     "cfx_md_create", "cfx_md_destroy", "cfx_md_set_state", "cfx_md_get_state", "cfx_md_minimize", "cfx_md_step", "cfx_md_energies",
 ]

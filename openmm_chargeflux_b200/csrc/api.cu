@@ -986,6 +986,16 @@ int cfx_measure_tf32_peak(int device, int iters, double* tflops) {
     CFX_CATCH
 }
 
+int cfx_measure_i8_peak(int device, int iters, double* tops) {
+    CFX_TRY
+    if (!tops || iters < 1) throw ArgError("bad argument");
+    int dev = device;
+    if (dev < 0) CFX_CUDA(cudaGetDevice(&dev));
+    *tops = measureI8Peak(dev, iters);
+    return CFX_OK;
+    CFX_CATCH
+}
+
 // debug only (not part of include/cfx_b200.h): phase timestamps of the last tensor-gather launch, [148][32] ns
 extern "C" int cfx_debug_gather_trace(cfx_handle* h, unsigned long long* out) {
     if (!h || !h->st.gtTrace) return CFX_ERR_STATE;

@@ -249,6 +249,7 @@ bool structureTensorEligible(const State& st);                                  
 void planStructureTensor(State& st);
 void launchStructureTensor(State& st, bool energy, cudaStream_t s);
 double measureTf32Peak(int device, int iters);
+double measureI8Peak(int device, int iters);
 void planKSpaceTensor(State& st);                                                       // kspace_tc.cu
 void launchGatherTensor(State& st, long long* dForce, long long* dDedq, cudaStream_t s);
 void planCells(State& st);

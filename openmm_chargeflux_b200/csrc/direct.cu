@@ -1213,8 +1213,8 @@ void launchDirect(State& st, const double* dPos, bool forces, int emode, bool em
         if (emitPairs) dispatchPair<false, true>(pp, f, em, grid, s);
         else           dispatchPair<false, false>(pp, f, em, grid, s);
         CFX_LAUNCH_CHECK(); st.launches++;
+        mark(st, k == 0 ? "direct_pairs" : "direct_pairs_energy", s);      // force (or only) pass / FP64 energy pass
     }
-    mark(st, "direct_pairs", s);
 }
 
 } // namespace cfx

@@ -1056,6 +1056,65 @@ __global__ void __launch_bounds__(128) tf32PeakKernel(int iters, float* sink) {
 }
 } // namespace
 
+namespace {
+// the same for tcgen05.mma kind::i8 128x256x32 (both operands in shared memory: the integer structure-factor kernel's form)
+__global__ void __launch_bounds__(128) i8PeakKernel(int iters, int* sink) {
+    constexpr int N = 256;
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmemSlot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int e = tid; e < (128 + N)*32/4; e += 128) reinterpret_cast<uint32_t*>(smem)[e] = 0x01010101u*(e & 3);
+    fenceProxyAsync();
+    if (tid == 0) { mbarInit(&bar, 1); mbarFenceInit(); }
+    if (warp == 0) tmemAlloc<512>(&tmemSlot);
+    tcgen05FenceBefore();
+    __syncthreads();
+    tcgen05FenceAfter();
+    const uint32_t tmem = tmemSlot;
+    if (warp == 0) {
+        const uint64_t ad = ummaSmemDesc(smemU32(smem), 128*16, 128), bd = ummaSmemDesc(smemU32(smem) + 128*32, N*16, 128);
+        if (electOne()) {
+            for (int i = 0; i < iters; i++) ummaI8SS(tmem + (i & 1)*N, ad, bd, ummaIdescS8(128, N), i > 1);
+            ummaCommit(&bar);
+        }
+        __syncwarp();
+    }
+    mbarWait(&bar, 0);
+    tcgen05FenceAfter();
+    int v[16];
+    tmemLoad16i(tmem + ((uint32_t) (warp*32) << 16), v);
+    if (v[0] == 123456789) sink[tid] = v[1];
+    tcgen05FenceBefore();
+    __syncthreads();
+    if (warp == 0) tmemFree<512>(tmem);
+}
+} // namespace
+
+double measureI8Peak(int device, int iters) {
+    CFX_CUDA(cudaSetDevice(device));
+    int numSM = 148;
+    cudaDeviceGetAttribute(&numSM, cudaDevAttrMultiProcessorCount, device);
+    int* sink = nullptr;
+    CFX_CUDA(cudaMalloc(&sink, 4096));
+    cudaEvent_t e0, e1;
+    CFX_CUDA(cudaEventCreate(&e0)); CFX_CUDA(cudaEventCreate(&e1));
+    const size_t smem = (128 + 256)*32;
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; rep++) {
+        CFX_CUDA(cudaEventRecord(e0));
+        i8PeakKernel<<<numSM, 128, smem>>>(iters, sink);
+        CFX_CUDA(cudaEventRecord(e1));
+        CFX_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CFX_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0) best = std::min(best, ms);
+    }
+    CFX_CUDA(cudaGetLastError());
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+    return 2.0*128*256*32*(double) iters*numSM/(best*1e-3)*1e-12;
+}
+
 double measureTf32Peak(int device, int iters) {
     CFX_CUDA(cudaSetDevice(device));
     int numSM = 148;

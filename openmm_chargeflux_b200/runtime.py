@@ -314,6 +314,16 @@ def measure_tf32_peak(device=-1, iters=20000):
     return tf.value
 
 
+def measure_i8_peak(device=-1, iters=20000):
+    """Dense INT8 tcgen05 throughput in TOP/s (roofline denominator of the integer structure-factor kernel)."""
+    lib = load_library()
+    lib.cfx_measure_i8_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]
+    tops = C.c_double(0.0)
+    if lib.cfx_measure_i8_peak(int(device), int(iters), C.byref(tops)) != 0:
+        raise CfxError(lib.cfx_last_error().decode())
+    return tops.value
+
+
 def measure_fp32_peak(device=-1, iters=5):
     lib = load_library()
     tf, mhz = C.c_double(0), C.c_double(0)

@@ -1,7 +1,7 @@
 """Summarise an .ncu-rep (ncu --set full) launch by launch: duration, instructions, issue rate, pipes, stalls, DRAM / L2 bytes.
    python tools/ncu_summary.py file.ncu-rep [traffic.json [bench]]   -- the optional JSON gets {kernel: dram bytes} of the LAST launch
    of each name; with "bench" the keys are bench.py's kernel groups (capture of tools/probe_both.py: energy+forces calls first, then
-   forces only; "<group>_energy" = the energy+forces call, pair passes of one call added up)"""
+   forces only; "<group>@E" = the energy+forces call, "<group>@F" = the forces-only call)"""
 import csv, io, json, subprocess, sys
 rep = sys.argv[1]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -36,7 +36,9 @@ for r in rows[2:]:
         pass
 if len(sys.argv) > 3 and sys.argv[3] == "bench":
     def group(name):
-        if "pairKernel" in name: return "direct_pairs"
+        if "pairKernel" in name:                       # pairKernel<FAST, FORCES, EMODE, EMIT>: <., 0, 2, .> is the FP64 energy pass
+            args = name.split("<")[1].split(">")[0].replace(" ", "").split(",")
+            return "direct_pairs_energy" if (args[1] == "0" and args[2] == "2") else "direct_pairs"
         if "gatherTensorKernel" in name or "gatherKernel" in name: return "kspace_gather"
         if "structureFactor" in name: return "structure_factor"
         return None
@@ -48,14 +50,13 @@ if len(sys.argv) > 3 and sys.argv[3] == "bench":
             evals.append(cur)
         g = group(name)
         if g:
-            acc = cur.setdefault(g, {"dram_read_bytes": 0.0, "dram_write_bytes": 0.0, "duration_us": 0.0, "fp32_s": False})
+            acc = cur.setdefault(g, {"dram_read_bytes": 0.0, "dram_write_bytes": 0.0, "duration_us": 0.0})
             for k in ("dram_read_bytes", "dram_write_bytes", "duration_us"): acc[k] += t[k]
-            if "structureFactorKernel" in name: acc["fp32_s"] = True
     out = {}
-    for ev in evals:                                   # later evaluations overwrite earlier ones (warm lists)
-        energy = ev.get("structure_factor", {}).get("fp32_s", False)
+    for ev in evals:                                   # later evaluations overwrite earlier ones (warm lists); @E = energy+forces call
+        tag = "@E" if "direct_pairs_energy" in ev else "@F"
         for g, acc in ev.items():
-            out[g + ("_energy" if energy else "")] = {k: v for k, v in acc.items() if k != "fp32_s"}
+            out[g + tag] = acc
     json.dump(out, open(sys.argv[2], "w"), indent=1)
 elif len(sys.argv) > 2:
     json.dump(traffic, open(sys.argv[2], "w"), indent=1)
