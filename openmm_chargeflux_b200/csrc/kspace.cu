@@ -20,10 +20,10 @@
 //
 // All main loops are FP32 FMA; cross-CTA reductions, a_k and energies are FP64 / fixed point.
 //
-// structureFactorKernel and gatherKernel here are the CUDA-core versions: the structure-factor one serves every
-// evaluation that returns the energy (round-to-nearest sums), both serve geometries outside the tensor-core variants.
-// Whenever the geometry allows, launchKSpace runs the tcgen05 kernels of kspace_tc.cu instead (same tables, same
-// coefficient kernel).
+// structureFactorKernel and gatherKernel here are the CUDA-core versions: they serve geometries outside the tensor-core
+// variants (kmax_z > 64, ...) and A/B measurements (CFX_KSPACE_S=fp32, CFX_KSPACE_GATHER=fp32). Whenever the geometry
+// allows, launchKSpace runs the tcgen05 kernels of kspace_tc.cu instead (same tables, same coefficient kernel): the
+// integer structure-factor kernel (exact sums: energy and forces-only calls alike) and the TF32 x 3 gather.
 #include "cfx_internal.cuh"
 #include "ptx_sm100.cuh"
 

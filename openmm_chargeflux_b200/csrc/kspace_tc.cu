@@ -5,8 +5,10 @@
 //                      Z[a][2l] = cos(2 pi l z_a), Z[a][2l+1] = sin(..), coefficient rows Ur: (Ar, Br), Ui: (Ai, Bi),
 //                      Vr: (l Bi, -l Ai), Vi: (-l Br, l Ar) (A, B as defined in coefficientKernel): [atoms x K] x [K x 4 rows]
 //   structure factors  P[(comp,row)][(l,c|s)] = sum_atoms A[(comp,row)][atom] * Z[(l,c|s)][atom], A = q Ex(nx) x Ey(|ny|)
-// Both run as tcgen05.mma kind::tf32 with FP32 accumulators in tensor memory, made FP32-accurate by the three-product
-// split x = hi + lo: product ~ lo*hi + hi*lo + hi*hi (relative RMS error 1.7e-7 at K = 56, tools/umma_test.cu).
+// The gather runs as tcgen05.mma kind::tf32 with FP32 accumulators in tensor memory, made FP32-accurate by the three-product
+// split x = hi + lo: product ~ lo*hi + hi*lo + hi*hi (relative RMS error 1.7e-7 at K = 56, tools/umma_test.cu). The structure
+// factors run as tcgen05.mma kind::i8 on signed base-256 digit planes of fixed-point operands with int32 accumulators: exact
+// sums, which is what lets the same kernel serve the energy call (structureFactorI8Kernel below; tools/imma_test.cu).
 // Operands are written in the K-major, no-swizzle core-matrix layout (8 rows x 16 bytes contiguous) that the UMMA
 // shared-memory descriptor addresses with two strides, so tiles can be produced by ordinary stores or one bulk-TMA copy.
 //
@@ -18,7 +20,11 @@
 //   warps 4-19    split the arrived FP32 tile into the TF32 hi/lo operand planes (double buffered); then, for 8 rows each:
 //                 tcgen05.ld the accumulators, release the slot, T = Ex Ey, dE/dq += Re(T U), F += q g (nx Im TU, ny Im TU,
 //                 Im TU') in registers; one fixed-point atomic per atom/output/warp when the atom group changes
-// structureFactorTensorKernel<NN, TT>: CTA = TT row tiles x one split of the atoms.
+// structureFactorI8Kernel<NN, TT, ND>: CTA = TT row tiles x one split of the atoms; ND = 3 digit planes (forces-only call) or 4
+//   (energy call).  warp 0: bulk-TMA ring of 32 atoms' phase rows per stage;  warp 1: MMA issuer, 3-4 MMAs of K = 32 atoms
+//   per row tile and stage into four int32 weight groups that stay in tensor memory until the end;  warps 2-17: form the
+//   digit planes of both operands (fixed point inside an FMA, PRMT byte gathers), then the one-off 64-bit epilogue.
+// structureFactorTensorKernel<NN, TT> (TF32 x 3; fall-back, CFX_KSPACE_S=tf32): CTA = TT row tiles x one split of the atoms.
 //   warp 0        bulk-TMA of 32 atoms' phase rows per stage
 //   warps 2-9     form both operands (products + hi/lo split) in shared memory
 //   warps 1, 18   MMA issuers, one per operand buffer / accumulator slot
