@@ -104,9 +104,7 @@ struct KSpacePlan {
     uint32_t tsRowStageBytes = 0, tsOffA = 0, tsOffB = 0, tsOffBar = 0;
     // integer tensor-core structure factors (exact; energy and forces-only calls)
     bool i8S = false;
-    int siRowStages = 0, siOpStages = 0;
-    uint32_t siRowStagePad = 0, siOpBytes = 0, siOffOp = 0, siOffBar = 0;
-    size_t siSmem = 0;
+    uint32_t siRowStagePad = 0;
     // tensor-core gather (kspace_tc.cu): K padded to 8, atom tiles per work unit, columns per coefficient tile
     bool tensorGather = false;
     int tKp = 0, tKC = 0, tMT = 2, tNT = 128, tStages = 0, tColTiles = 0;

@@ -924,6 +924,28 @@ bool structureTensorEligible(const State& st) {
     return st.ks.K[2] <= 64;                                    // 2*Kz columns must fit one N <= 128 MMA
 }
 
+// shared-memory layout of the integer kernel for ND digit planes: [row stages][operand ring][barriers]; the deepest operand
+// ring that fits beside three (else two) row stages
+struct SiLayout { int rowStages = 0, opStages = 0; uint32_t opBytes = 0, offOp = 0, offBar = 0; size_t smem = 0; };
+static bool siLayout(int NN, int TT, int ND, size_t rowStagePad, SiLayout& l) {
+    const size_t opBytes = (size_t) TT*ND*SI_A_PLANE + 2*(size_t) (ND*NN)*16;
+    const size_t cap = 227*1024 - 256 - 256;
+    int rsFixed = 0, obFixed = 0;                                // experiments
+    if (const char* e = getenv("CFX_SI_ROW_STAGES")) rsFixed = atoi(e);
+    if (const char* e = getenv("CFX_SI_OP_STAGES")) obFixed = atoi(e);
+    for (int rsN = 3; rsN >= 2; rsN--)
+        for (int ob = 4; ob >= 2; ob--) {
+            if ((rsFixed && rsN != rsFixed) || (obFixed && ob != obFixed)) continue;
+            if (rsN*rowStagePad + ob*opBytes <= cap) {
+                l.rowStages = rsN; l.opStages = ob; l.opBytes = (uint32_t) opBytes;
+                l.offOp = (uint32_t) (rsN*rowStagePad); l.offBar = (uint32_t) (l.offOp + ob*opBytes);
+                l.smem = l.offBar + 256;
+                return true;
+            }
+        }
+    return false;
+}
+
 void planStructureTensor(State& st) {
     KSpacePlan& ks = st.ks;
     SGeom& t = ks.sT;
@@ -965,17 +987,9 @@ void planStructureTensor(State& st) {
     ks.i8S = false;
     const char* mode = getenv("CFX_KSPACE_S");                  // "tf32": keep the TF32 kernel (and FP32 for energies)
     if (!(mode && !strcmp(mode, "tf32")) && t.atomsPerSplit <= SI_MAX_ATOMS) {
-        const size_t opBytes = (size_t) TT*4*SI_A_PLANE + 2*(size_t) (4*NN)*16;
-        const size_t cap = 227*1024 - 256 - 256;
-        for (int rsN = 3; rsN >= 2 && !ks.i8S; rsN--)
-            for (int ob = 4; ob >= 2; ob--)
-                if (rsN*rowStagePad + ob*opBytes <= cap) {
-                    ks.i8S = true; ks.siRowStages = rsN; ks.siOpStages = ob;
-                    ks.siRowStagePad = (uint32_t) rowStagePad; ks.siOpBytes = (uint32_t) opBytes;
-                    ks.siOffOp = (uint32_t) (rsN*rowStagePad); ks.siOffBar = (uint32_t) (ks.siOffOp + ob*opBytes);
-                    ks.siSmem = ks.siOffBar + 256;
-                    break;
-                }
+        ks.siRowStagePad = (uint32_t) rowStagePad;
+        SiLayout l3, l4;
+        ks.i8S = siLayout(NN, TT, 3, rowStagePad, l3) && siLayout(NN, TT, 4, rowStagePad, l4);
         CFX_CUDA(cudaFuncSetAttribute(structureFactorI8Kernel<64, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024));
         CFX_CUDA(cudaFuncSetAttribute(structureFactorI8Kernel<128, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024));
         CFX_CUDA(cudaFuncSetAttribute(structureFactorI8Kernel<64, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024));
@@ -997,16 +1011,19 @@ void launchStructureTensor(State& st, bool energy, cudaStream_t s) {
         ip.rowPitch = t.rowPitch; ip.Kx = ks.K[0]; ip.Ky = ks.K[1]; ip.Kz = ks.K[2]; ip.zOff = t.rowPitch - t.kzPad; ip.kzPad = t.kzPad;
         ip.rowLo = ks.rowLo; ip.rowHi = ks.rowHi; ip.numRows = ks.numRows;
         ip.atomsPerSplit = t.atomsPerSplit; ip.Npad = st.Npad;
-        ip.rowStages = ks.siRowStages; ip.opStages = ks.siOpStages;
-        ip.rowStageBytes = ks.tsRowStageBytes; ip.rowStagePad = ks.siRowStagePad; ip.offOp = ks.siOffOp; ip.opBytes = ks.siOpBytes; ip.offBar = ks.siOffBar;
+        const int NN = 2*t.kzPad, TT = 128/NN;
+        SiLayout lay;
+        siLayout(NN, TT, energy ? 4 : 3, ks.siRowStagePad, lay);          // (feasible: checked by the plan)
+        ip.rowStages = lay.rowStages; ip.opStages = lay.opStages;
+        ip.rowStageBytes = ks.tsRowStageBytes; ip.rowStagePad = ks.siRowStagePad; ip.offOp = lay.offOp; ip.opBytes = lay.opBytes; ip.offBar = lay.offBar;
         const dim3 grid(t.rowTiles, t.splits);
         if (t.kzPad == 32) {
-            if (energy) structureFactorI8Kernel<64, 2, 4><<<grid, SI_THREADS, ks.siSmem, s>>>(ip);
-            else        structureFactorI8Kernel<64, 2, 3><<<grid, SI_THREADS, ks.siSmem, s>>>(ip);
+            if (energy) structureFactorI8Kernel<64, 2, 4><<<grid, SI_THREADS, lay.smem, s>>>(ip);
+            else        structureFactorI8Kernel<64, 2, 3><<<grid, SI_THREADS, lay.smem, s>>>(ip);
         }
         else {
-            if (energy) structureFactorI8Kernel<128, 1, 4><<<grid, SI_THREADS, ks.siSmem, s>>>(ip);
-            else        structureFactorI8Kernel<128, 1, 3><<<grid, SI_THREADS, ks.siSmem, s>>>(ip);
+            if (energy) structureFactorI8Kernel<128, 1, 4><<<grid, SI_THREADS, lay.smem, s>>>(ip);
+            else        structureFactorI8Kernel<128, 1, 3><<<grid, SI_THREADS, lay.smem, s>>>(ip);
         }
         CFX_LAUNCH_CHECK(); st.launches++;
         return;
