@@ -14,11 +14,12 @@ from it.
             L2 flushed between steps, max over ranks.
   e2e       the same through the reference-facing call with HOST buffers: pinned H2D of the positions
             and D2H of forces + energy inside the timed region.
-  roofline  dominant kernel (the direct-space pair kernel): algorithmic FLOP / its CUDA-event duration, against
-            the FP32 FMA peak measured live on this GPU (MEASURED_PEAKS.json has no CUDA-core figure).
-            `roofline.kernels` lists every large kernel with its own bound: the reciprocal-space kernels run on
-            the tensor cores (tcgen05 kind::tf32, three-product split) and are held against the TF32 peak measured
-            live, both as algorithmic FP32-equivalent FLOP and as executed TF32 FLOP.
+  roofline  the longest kernel launch of the step: algorithmic FLOP / its CUDA-event duration against the peak of the unit
+            it runs on, measured live on this GPU (MEASURED_PEAKS.json has neither a CUDA-core nor a TF32 / INT8 figure).
+            `roofline.kernels` lists every large kernel with its own bound: pair passes against the FP32 FMA peak, the
+            gather (tcgen05 kind::tf32, three-product split) against the TF32 peak, the structure factors (tcgen05 kind::i8
+            on digit planes of fixed-point operands) against the INT8 peak -- each as algorithmic FLOP and as executed
+            tensor operations.
   cpu_baseline  the plugin's Reference-platform kernel (oracle/_ref when present, else the oracle port)
             on one host core, bounded sample, extrapolated in the number of k-vectors.
 
@@ -433,7 +434,7 @@ def run_ours(args, pos, box, force, workload):
         value = 1e3 / ms_per_step
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": "f32 (f64 energies/accumulation, int64 fixed-point forces)", "data": "synthetic",
+                "dtype": "f32 pair terms and tf32x3 gather, s8 digit planes / s32 sums for the structure factors (f64 energies and cross-CTA sums, int64 fixed-point forces)", "data": "synthetic",
                 "config": {"workload": workload, "atoms": n, "kmax": list(kmax), "kvectors": int(nk), "alpha": alpha,
                            "flags": FLAGS_NOTE,
                            "positions": "the atoms move every step: thermal (300 K) straight-line motion, %.1f fs per step, %d frames "
@@ -570,7 +571,7 @@ def run_ours(args, pos, box, force, workload):
                                            "frac_forces_only": fl["total"] / (ms_f * 1e-3) / 1e12 / tf_peak,
                                            "algorithmic_flop": fl["total"],
                                            "note": "algorithmic FP32-equivalent FLOP of the whole evaluation / step time, against the "
-                                                   "FP32 FMA peak; the reciprocal-space gather (and, forces only, the structure factors) run on tensor cores"}}
+                                                   "FP32 FMA peak; both reciprocal-space sums run on tensor cores (gather: kind::tf32 x 3, structure factors: kind::i8 digit planes)"}}
         # what one list build costs (a handle that rebuilds at every evaluation): re-sort + list kernel
         rb = runtime.CalcCoulForceKernel(device=local, list_skin=0.0)
         rb.initialize(box, force)
