@@ -61,6 +61,16 @@ double ewaldErrorEstimate(int kmax, double width, double alpha) {
     return 0.05*sqrt(width*alpha)*kmax*exp(-t*t);
 }
 
+// Digit planes of the integer structure-factor kernel in the forces-only call: three (23-bit fixed point, scaled by the
+// largest |q|) are FP32-grade as long as the charges are of similar size; when the largest base charge dwarfs the typical
+// one, the small charges would lose bits, so such systems use the four-digit variant of the energy call throughout.
+int forceDigitsFor(const std::vector<double>& q0) {
+    double sum2 = 0.0, big = 0.0;
+    for (double q : q0) { sum2 += q*q; big = std::max(big, fabs(q)); }
+    const double rms = q0.empty() ? 0.0 : sqrt(sum2/q0.size());
+    return (big > 4.0*rms) ? 4 : 3;
+}
+
 void checkBox(const double* box) {
     if (box[1] != 0 || box[2] != 0 || box[3] != 0 || box[5] != 0 || box[6] != 0 || box[7] != 0)
         throw ArgError("only rectangular periodic boxes are supported (the reference's reciprocal sum uses the box diagonal only)");
@@ -408,6 +418,7 @@ int cfx_create(const cfx_system_desc* d, const cfx_options* opts, cfx_handle** o
     CFX_CUDA(cudaEventCreateWithFlags(&st.evJoin, cudaEventDisableTiming));
     CFX_CUDA(cudaEventCreateWithFlags(&st.evStart, cudaEventDisableTiming));
     st.q0 = upload(q0); st.lj = upload(lj); st.ljd = upload(ljd);
+    st.siForceDigits = forceDigitsFor(q0);
     st.termIdx = upload(termIdx); st.termPar = upload(termPar);
     st.qcsrPtr = upload(csrPtr, 2); st.qcsrSlot = upload(csrSlot); st.qcsrCoef = upload(csrCoef);
     st.rowDq = upload(rowDq); st.rowDx = upload(rowDx);
@@ -967,6 +978,7 @@ int cfx_update_parameters(cfx_handle* h, const cfx_system_desc* d) {
     for (int t = 0; t < st.nw; t++) { const size_t g = (size_t) st.nb + st.na + t; for (int a = 0; a < 5; a++) termPar[5*g + a] = d->flux_water_params[5*t + a]; }
     if (st.stream) CFX_CUDA(cudaStreamSynchronize(st.stream));
     CFX_CUDA(cudaMemcpy(st.q0, q0.data(), sizeof(double)*N, cudaMemcpyHostToDevice));
+    if (forceDigitsFor(q0) != st.siForceDigits) { st.siForceDigits = forceDigitsFor(q0); dropGraphs(st); }
     CFX_CUDA(cudaMemcpy(st.lj, lj.data(), sizeof(float2)*N, cudaMemcpyHostToDevice));
     CFX_CUDA(cudaMemcpy(st.ljd, ljd.data(), sizeof(double2)*N, cudaMemcpyHostToDevice));
     if (st.numTerms) CFX_CUDA(cudaMemcpy(st.termPar, termPar.data(), sizeof(double)*termPar.size(), cudaMemcpyHostToDevice));

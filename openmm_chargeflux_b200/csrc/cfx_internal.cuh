@@ -135,6 +135,7 @@ struct State {
     bool skipDiscardedEnergy = false;   // cfx_options.flags & CFX_OPT_SKIP_DISCARDED_ENERGY
     bool pinCallerBuffers = false;      // cfx_options.flags & CFX_OPT_PIN_CALLER_BUFFERS
     bool kmaxFollowsBox = false;        // cfx_options.flags & CFX_OPT_KMAX_FOLLOWS_BOX
+    int siForceDigits = 3;              // digit planes of the integer structure factors in the forces-only call (api.cu: forceDigitsFor)
     bool hostCopyKernels = true;        // host path: positions fetched / results stored by kernels on page-locked memory, no copy nodes
     KSpacePlan ks;
     CellPlan cells;

@@ -1013,17 +1013,18 @@ void launchStructureTensor(State& st, bool energy, cudaStream_t s) {
         ip.atomsPerSplit = t.atomsPerSplit; ip.Npad = st.Npad;
         const int NN = 2*t.kzPad, TT = 128/NN;
         SiLayout lay;
-        siLayout(NN, TT, energy ? 4 : 3, ks.siRowStagePad, lay);          // (feasible: checked by the plan)
+        const bool four = energy || st.siForceDigits == 4;
+        siLayout(NN, TT, four ? 4 : 3, ks.siRowStagePad, lay);            // (feasible: checked by the plan)
         ip.rowStages = lay.rowStages; ip.opStages = lay.opStages;
         ip.rowStageBytes = ks.tsRowStageBytes; ip.rowStagePad = ks.siRowStagePad; ip.offOp = lay.offOp; ip.opBytes = lay.opBytes; ip.offBar = lay.offBar;
         const dim3 grid(t.rowTiles, t.splits);
         if (t.kzPad == 32) {
-            if (energy) structureFactorI8Kernel<64, 2, 4><<<grid, SI_THREADS, lay.smem, s>>>(ip);
-            else        structureFactorI8Kernel<64, 2, 3><<<grid, SI_THREADS, lay.smem, s>>>(ip);
+            if (four) structureFactorI8Kernel<64, 2, 4><<<grid, SI_THREADS, lay.smem, s>>>(ip);
+            else      structureFactorI8Kernel<64, 2, 3><<<grid, SI_THREADS, lay.smem, s>>>(ip);
         }
         else {
-            if (energy) structureFactorI8Kernel<128, 1, 4><<<grid, SI_THREADS, lay.smem, s>>>(ip);
-            else        structureFactorI8Kernel<128, 1, 3><<<grid, SI_THREADS, lay.smem, s>>>(ip);
+            if (four) structureFactorI8Kernel<128, 1, 4><<<grid, SI_THREADS, lay.smem, s>>>(ip);
+            else      structureFactorI8Kernel<128, 1, 3><<<grid, SI_THREADS, lay.smem, s>>>(ip);
         }
         CFX_LAUNCH_CHECK(); st.launches++;
         return;

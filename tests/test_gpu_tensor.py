@@ -70,3 +70,37 @@ def test_large_kmax_variants_of_the_tensor_kernels_against_the_oracle(build_nati
 def test_tf32_peak_measurement_is_plausible(build_native):
     tf = runtime.measure_tf32_peak(iters=5000)
     assert 300.0 < tf < 2500.0, tf
+
+
+def test_i8_peak_measurement_is_plausible(build_native):
+    tops = runtime.measure_i8_peak(iters=4000)
+    assert 2000.0 < tops < 5000.0          # B200 dense INT8 nominal 4.5 POP/s
+
+
+def test_one_large_charge_switches_the_forces_only_call_to_four_digit_planes(build_native):
+    """The integer structure-factor kernel scales its fixed point by the largest |q|: when one charge dwarfs the others
+    (api.cu: forceDigitsFor), the forces-only call must use the four-digit variant to keep the small charges' bits. A
+    +-6 e ion pair in water (10x the typical charge): forces-only and energy calls against the oracle."""
+    from openmm_chargeflux_b200.force import CoulForce
+    pos, box, f = synthetic.water_box(512, seed=9, cutoff=0.9, ewald_tol=1e-5)
+    g = CoulForce()
+    for i in range(f.getNumParticles()):
+        q, s, e = f.getParticleParameters(i)
+        g.addParticle(6.0 if i == 0 else (-6.0 if i == 300 else q), s, e)
+    for i in range(f.getNumExceptions()):
+        g.addException(*f.getExceptionParameters(i))
+    for i in range(f.getNumFluxBonds()):
+        g.addFluxBond(*f.getFluxBondParameters(i))
+    for i in range(f.getNumFluxAngles()):
+        g.addFluxAngle(*f.getFluxAngleParameters(i))
+    g.setCutoffDistance(f.getCutoffDistance()); g.setEwaldErrorTolerance(f.getEwaldErrorTolerance())
+    g.setUsesPeriodicBoundaryConditions(True)
+    o = Oracle(g, box)
+    ctx = runtime.CoulContext(g, box)
+    for inc_e in (False, True):
+        e, frc, _ = ctx.evaluate(pos, True, inc_e)
+        eo, fo = o.execute(pos, box, True, inc_e)
+        assert rel_rms(frc, fo) <= F_RTOL, inc_e
+        if inc_e:
+            assert abs(e - eo[4]) <= 1e-6 * max(abs(eo[4]), 1e-3 * np.abs(eo[:4]).max())
+    assert rel_rms(ctx.kernel.dedq(), o.dedq()) <= F_RTOL
