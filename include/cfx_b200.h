@@ -222,7 +222,7 @@ int  cfx_time_kernels(cfx_handle* h, const double* d_positions, const double* bo
  * bounded by (MEASURED_PEAKS.json has no FP32 CUDA-core figure). */
 int  cfx_measure_fp32_peak(int device, int iters, double* tflops, double* sm_clock_mhz_est);
 /* Sustained dense TF32 tensor-core throughput (TFLOP/s) of tcgen05.mma kind::tf32 128x128x8, the roofline denominator
- * of the tensor-core reciprocal-space kernels (MEASURED_PEAKS.json holds a bf16 figure only). */
+ * of the tensor-core gather (MEASURED_PEAKS.json holds a bf16 figure only). */
 int  cfx_measure_tf32_peak(int device, int iters, double* tflops);
 /* Sustained dense INT8 tensor-core throughput (TOP/s) of tcgen05.mma kind::i8 128x256x32, the roofline denominator of the
  * integer structure-factor kernel. */
