@@ -104,3 +104,28 @@ def test_one_large_charge_switches_the_forces_only_call_to_four_digit_planes(bui
         if inc_e:
             assert abs(e - eo[4]) <= 1e-6 * max(abs(eo[4]), 1e-3 * np.abs(eo[:4]).max())
     assert rel_rms(ctx.kernel.dedq(), o.dedq()) <= F_RTOL
+
+
+def test_integer_structure_factors_do_not_depend_on_the_pipeline_depth(build_native, monkeypatch):
+    """Integer sums are exact, so nothing about the kernel's schedule may show in the result: the same evaluation with
+    2/2, 3/2 and the default row / operand ring depths must agree to the last bit (a race in the TMA -> formers -> MMA
+    pipeline would not)."""
+    pos, box, force = synthetic.config("c2")
+    results = []
+    for rs, ob in ((None, None), ("2", "2"), ("3", "2")):
+        for name, val in (("CFX_SI_ROW_STAGES", rs), ("CFX_SI_OP_STAGES", ob)):
+            if val is None:
+                monkeypatch.delenv(name, raising=False)
+            else:
+                monkeypatch.setenv(name, val)
+        ctx = runtime.CoulContext(force, box)
+        out = []
+        for inc_e in (True, False, True):
+            e, f, comps = ctx.evaluate(pos, True, inc_e)
+            out.append((e, f.copy(), comps.copy()))
+        assert out[0][0] == out[2][0] and np.array_equal(out[0][1], out[2][1])      # repeatable within a handle
+        results.append(out)
+        ctx.kernel.close()
+    for other in results[1:]:
+        for a, b in zip(results[0], other):
+            assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
